@@ -156,6 +156,11 @@ const char* zs_last_error(void);
 /* Pure host arithmetic: validates cfg/map and fills the layout.  Needs no GPU. */
 int zs_layout(const ZsConfig* cfg, const ZsMap* map, ZsLayout* out);
 
+/* Select the CUDA device for the calling thread inside this library's own CUDA runtime instance
+ * (the library links cudart statically; call it with the ordinal of the device the caller's
+ * tensors live on before zs_create). */
+int zs_set_device(int32_t device);
+
 /* Uploads the map tables (handle-owned device memory) on the current device. */
 int zs_create(const ZsConfig* cfg, const ZsMap* map, ZsHandle** out);
 int zs_destroy(ZsHandle* h);
@@ -163,12 +168,17 @@ int zs_destroy(ZsHandle* h);
 /* Bind the caller-allocated state buffer (>= layout.state_bytes, 16-byte aligned, device). */
 int zs_bind_state(ZsHandle* h, void* state_dev, int64_t bytes);
 
-/* (Re)initialise the worlds selected by env_mask_dev (uint8 [N], NULL = all) and, if obs_dev
- * is not NULL, write their observation.  Static lives are NOT restored: wall/box damage
- * persists across resets exactly as in the reference (game.py:154-155).
- * zs_init_static_life sets every box/wall to its MAX_LIFE (what constructing a new env does). */
+/* zs_init_static_life: what constructing a new env does before its first world init — every
+ * box/wall gets its MAX_LIFE (Map.from_file builds the objects once, game.py:76-79) and the
+ * episode counter is set so that the next zs_reset is world initialisation #0 (game.py:138).
+ * The state buffer must have been zero-filled by the caller.
+ *
+ * zs_reset: (re)initialise the worlds selected by env_mask_dev (uint8 [N], NULL = all) and, if
+ * obs_dev is not NULL, write their observation; draws_dev (int32 [N], may be NULL) receives the
+ * number of draws each init consumed.  Static lives are NOT restored: wall/box damage persists
+ * across resets exactly as in the reference (game.py:154-155). */
 int zs_init_static_life(ZsHandle* h, void* stream);
-int zs_reset(ZsHandle* h, const uint8_t* env_mask_dev, int32_t* obs_dev, void* stream);
+int zs_reset(ZsHandle* h, const uint8_t* env_mask_dev, int32_t* obs_dev, int32_t* draws_dev, void* stream);
 
 /* One env transition for all N envs.
  *   actions_dev     per action_format

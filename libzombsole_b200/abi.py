@@ -66,12 +66,13 @@ class ZsLayout(C.Structure):
 PROTOTYPES = {
     "zs_abi_version": (C.c_int, []),
     "zs_last_error": (C.c_char_p, []),
+    "zs_set_device": (C.c_int, [C.c_int32]),
     "zs_layout": (C.c_int, [C.POINTER(ZsConfig), C.POINTER(ZsMap), C.POINTER(ZsLayout)]),
     "zs_create": (C.c_int, [C.POINTER(ZsConfig), C.POINTER(ZsMap), C.POINTER(C.c_void_p)]),
     "zs_destroy": (C.c_int, [C.c_void_p]),
     "zs_bind_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "zs_init_static_life": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "zs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_encode_obs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

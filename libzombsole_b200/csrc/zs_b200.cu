@@ -1,0 +1,484 @@
+// zs_b200.cu — kernels and C ABI (include/zs_b200.h) of the B200-native batched zombsole simulator.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+// No CPU fallback: every entry point that computes launches CUDA kernels.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "zs_device.cuh"
+#include "zs_world.cuh"
+#include "zs_obs.cuh"
+
+// ================================================================ kernels
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
+
+__device__ __forceinline__ int synthetic_action(const ZsParams& p, uint32_t env_global, uint32_t step_index, int agent) {
+    uint32_t o[4];
+    philox4x32_10(env_global, step_index, 0u, (uint32_t)(agent >> 2), p.key0, p.key1 ^ 0xAC710115u, o);
+    const int w = agent & 3;
+    const uint32_t u = w == 0 ? o[0] : w == 1 ? o[1] : w == 2 ? o[2] : o[3];
+    return below(u, p.n_discrete);
+}
+
+// discrete id -> (type, dx, dy): ZombsoleGymEnvDiscreteAction.game_actions (gym_env.py:328-351),
+// MultiagentZombsoleEnvDiscreteAction.game_actions (multiagent_env.py:259-285)
+__device__ __forceinline__ void discrete_to_action(const ZsParams& p, int id, int& type, int& dx, int& dy) {
+    type = ZS_ACT_NONE; dx = 0; dy = 0;
+    if (id < 0) { if (p.obs_per_agent) type = ZS_ACT_ABSENT; return; }
+    if (id >= p.n_discrete) return;
+    if (id < 4) { type = ZS_ACT_MOVE; dx = id == 1 ? -1 : id == 3 ? 1 : 0; dy = id == 0 ? 1 : id == 2 ? -1 : 0; }
+    else type = id == 4 ? ZS_ACT_ATTACK_CLOSEST : id == 5 ? ZS_ACT_HEAL : ZS_ACT_HEAL_CLOSEST;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ZS_WPC * 32) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int env = blockIdx.x * ZS_WPC + wid;
+    if (env >= p.N) return;
+    Env e;
+    env_bind(p, e, smem + (size_t)wid * p.smem_per_warp, env, lane);
+
+    if (MODE == MODE_RESET) {
+        if (io.env_mask && !io.env_mask[env]) return;
+        // slots keep their last position/life until re-placed; bring them in so the store is complete
+        load_state(p, e);
+        const int k = initialize_world(p, e, e.episode + 1);
+        if (io.draws && lane == 0) io.draws[env] = k;
+        if (io.obs) encode_obs(p, e, io.obs + (size_t)env * p.obs_elems);
+        store_state(p, e);
+        return;
+    }
+    load_state(p, e);
+    build_grid(p, e);
+    if (MODE == MODE_ENCODE) {
+        encode_obs(p, e, io.obs + (size_t)env * p.obs_elems);
+        return;
+    }
+
+    const int A = p.A, NP = p.P + p.A;
+    const int R = p.obs_per_agent ? A : 1;
+    for (int step = 0; step < io.n_steps; ++step) {
+        const size_t sn = (size_t)step * p.N + env;
+        // ---- Agent.set_action (agent.py:22-25)
+        for (int a = lane; a < A; a += 32) {
+            int type, dx, dy;
+            if (io.actions == nullptr) discrete_to_action(p, synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), a), type, dx, dy);
+            else if (io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, io.actions[sn * A + a], type, dx, dy);
+            else { const int32_t* q = io.actions + (sn * A + a) * 3; type = q[0]; dx = q[1]; dy = q[2]; }
+            e.acts[3 * a] = type; e.acts[3 * a + 1] = dx; e.acts[3 * a + 2] = dy;
+        }
+        unsigned alive_before = 0;  // agents alive before the step: keys of the multi-agent dicts
+        for (int a = 0; a < A; ++a) alive_before |= (e.tl[p.P + a] > 0 ? 1u : 0u) << a;
+        __syncwarp();
+
+        int k = world_step(p, e);
+        e.ep_steps += 1;
+
+        // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order
+        double rew = 0.0;  // lane a holds agent a's reward (single-agent: lane 0)
+        if (!p.obs_per_agent) {
+            int sum_prev = 0, sum_new = 0;
+            for (int a = 0; a < A; ++a) { sum_prev += e.prev[a]; sum_new += e.tl[p.P + a]; }
+            rew = __dsub_rn(total_reward(e.zd, sum_new), total_reward(e.prev_zd, sum_prev));
+        } else if (lane < A) {
+            rew = __dsub_rn(total_reward(e.zd, e.tl[p.P + lane]), total_reward(e.prev_zd, e.prev[lane]));
+        }
+        __syncwarp();
+        for (int a = lane; a < A; a += 32) e.prev[a] = e.tl[p.P + a];
+        e.prev_zd = e.zd;
+        __syncwarp();
+
+        // ---- Game.spawn_zombies_to_maintain_minimum (game.py:196-201)
+        if (p.minimum_zombies > 0) {
+            int zc = 0;
+            for (int s = NP + lane; s < p.M; s += 32) zc += (e.tm[s] & 0x80) != 0;
+            for (int o = 16; o; o >>= 1) zc += __shfl_xor_sync(ZS_FULL, zc, o);
+            if (zc < p.minimum_zombies) k = spawn_zombies(p, e, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc);
+        }
+
+        // ---- rules and end reward (gym_env.py:130-141, multiagent_env.py:143-162)
+        bool ended, won, agents_alive;
+        rules_eval(p, e, ended, won, agents_alive);
+        bool done = false, trunc = false;
+        double end_reward = 0.0;
+        if (ended) { done = true; end_reward = won ? 10.0 : -10.0; }
+        else if (!agents_alive) { trunc = true; end_reward = -10.0; }
+        if (!p.obs_per_agent) {
+            if (done || trunc) rew = __dadd_rn(rew, end_reward);
+        } else if (lane < A) {
+            if (!((alive_before >> lane) & 1u)) rew = 0.0;
+            else if (e.tl[p.P + lane] > 0) rew = __dadd_rn(rew, end_reward);
+        }
+        if (p.max_steps > 0 && e.ep_steps >= p.max_steps) trunc = true;  // gymnasium TimeLimit
+
+        if (io.reward) {
+            if (!p.obs_per_agent) { if (lane == 0) io.reward[sn] = rew; }
+            else if (lane < A) io.reward[sn * R + lane] = rew;
+        }
+        if (lane == 0) {
+            if (io.terminated) io.terminated[sn] = done;
+            if (io.truncated) io.truncated[sn] = trunc;
+            if (io.draws) io.draws[sn] = k;
+        }
+        if (io.agent_mask && lane < A) io.agent_mask[sn * A + lane] = (alive_before >> lane) & 1u;
+
+        // ---- same-step auto-reset
+        if ((done || trunc) && (p.auto_reset || io.force_auto_reset)) {
+            if (lane == 0) {
+                atomicAdd(p.stats + 0, 1ull);
+                if (done && won) atomicAdd(p.stats + 1, 1ull);
+                atomicAdd(p.stats + 2, (unsigned long long)e.ep_steps);
+                atomicAdd(p.stats + 3, (unsigned long long)e.zd);
+            }
+            initialize_world(p, e, e.episode + 1);
+        }
+        if (io.obs) {
+            const size_t slot = io.obs_slots > 1 ? (size_t)(step % io.obs_slots) : 0;
+            encode_obs(p, e, io.obs + (slot * p.N + env) * p.obs_elems);
+        }
+        __syncwarp();
+    }
+    store_state(p, e);
+}
+
+__global__ void zs_init_static_life_kernel(const __grid_constant__ ZsParams p) {
+    const size_t n = (size_t)p.N * p.Sp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p.SLIFE[i] = __ldg(p.static_max + (i % p.Sp));
+    // the next zs_reset is world initialisation #0 (what Game.__init__ does, game.py:138)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)p.N; i += (size_t)gridDim.x * blockDim.x)
+        p.SCAL[i * 8 + ZS_S_EPISODE] = -1;
+}
+
+__global__ void zs_fill_actions_kernel(const __grid_constant__ ZsParams p, uint32_t step_index, int32_t* actions) {
+    const int n = p.N * p.A;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int env = i / p.A, a = i - env * p.A;
+        actions[i] = synthetic_action(p, p.env_base + (uint32_t)env, step_index, a);
+    }
+}
+
+__global__ void zs_stats_kernel(unsigned long long* stats, int64_t* out, int reset) {
+    const int i = threadIdx.x;
+    if (i < 4) {
+        out[i] = (int64_t)stats[i];
+        if (reset) stats[i] = 0ull;
+    }
+}
+
+// ================================================================ host side
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, const char* a = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a);
+    return 1;
+}
+#define CU(call)                                                                  \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) {                                                  \
+            snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(_e)); \
+            return 2;                                                             \
+        }                                                                         \
+    } while (0)
+
+struct ZsHandle {
+    ZsConfig cfg;
+    ZsLayout lay;
+    ZsParams p;
+    std::vector<void*> dev_allocs;
+    int64_t launches;
+    int64_t bound_bytes;
+    int sm_count;
+};
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+extern "C" __attribute__((visibility("default"))) int zs_abi_version(void) { return ZS_ABI_VERSION; }
+extern "C" __attribute__((visibility("default"))) int zs_set_device(int32_t device) {
+    CU(cudaSetDevice(device));
+    return 0;
+}
+extern "C" __attribute__((visibility("default"))) const char* zs_last_error(void) { return g_err; }
+
+static int validate(const ZsConfig* cfg, const ZsMap* map) {
+    if (!cfg || !map) return fail("null config or map");
+    if (cfg->abi_version != ZS_ABI_VERSION) return fail("ABI version mismatch");
+    if (cfg->num_envs < 1) return fail("num_envs must be >= 1");
+    if (cfg->rules < 0 || cfg->rules > ZS_RULES_SAFEHOUSE) return fail("unknown rules id");
+    if (cfg->n_bots < 0 || cfg->n_bots > ZS_MAX_BOTS) return fail("n_bots out of range");
+    for (int i = 0; i < cfg->n_bots; ++i)
+        if (cfg->bot_kinds[i] != ZS_KIND_TERMINATOR) return fail("unsupported bot kind (only terminator)");
+    if (cfg->n_agents < 1 || cfg->n_agents > ZS_MAX_AGENTS) return fail("n_agents out of range");
+    for (int i = 0; i < cfg->n_agents; ++i) {
+        int w = cfg->agent_weapons[i];
+        if (!(w == ZS_WEAPON_RANDOM || (w >= ZS_WEAPON_KNIFE && w <= ZS_WEAPON_SHOTGUN))) return fail("bad agent weapon code");
+    }
+    if (cfg->initial_zombies < 0 || cfg->minimum_zombies < 0) return fail("negative zombie count");
+    int Z = cfg->initial_zombies > cfg->minimum_zombies ? cfg->initial_zombies : cfg->minimum_zombies;
+    if (cfg->n_bots + cfg->n_agents + Z > ZS_MAX_SLOTS) return fail("too many things per env (ZS_MAX_SLOTS)");
+    if (map->width < 1 || map->height < 1 || (int64_t)map->width * map->height > 65535) return fail("map size out of range");
+    if (map->n_statics < 0 || map->n_statics > 30000) return fail("too many statics");
+    if (cfg->obs_scope == ZS_OBS_SURROUNDINGS) {
+        if (cfg->surroundings_width <= 1 || cfg->surroundings_width % 2 == 0) return fail("surroundings width must be an odd number greater than 1");
+    } else if (cfg->obs_scope != ZS_OBS_WORLD) return fail("bad obs_scope");
+    if (cfg->obs_encoding != ZS_OBS_SIMPLE && cfg->obs_encoding != ZS_OBS_CHANNELS) return fail("bad obs_encoding");
+    if (cfg->obs_per_agent && cfg->obs_scope != ZS_OBS_SURROUNDINGS) return fail("per-agent observations need the surroundings scope");
+    if (cfg->rules == ZS_RULES_SAFEHOUSE && map->n_objectives == 0) return fail("Safe house game requires objectives defined.");
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_layout(const ZsConfig* cfg, const ZsMap* map, ZsLayout* out) {
+    if (int rc = validate(cfg, map)) return rc;
+    if (!out) return fail("null layout");
+    memset(out, 0, sizeof(*out));
+    const int64_t N = cfg->num_envs;
+    const int Z = cfg->initial_zombies > cfg->minimum_zombies ? cfg->initial_zombies : cfg->minimum_zombies;
+    out->n_slots = cfg->n_bots + cfg->n_agents + Z;
+    out->slot_pitch = round_up(out->n_slots, 16);
+    out->agent_pitch = round_up(cfg->n_agents, 8);
+    out->static_pitch = round_up(map->n_statics > 0 ? map->n_statics : 1, 8);
+    out->cells = map->width * map->height;
+    out->dead_words = round_up((out->cells + 31) / 32, 4);
+    const int elem[ZS_F_COUNT] = {2, 2, 2, 4, 1, 2, 2, 4, 4};
+    const int pitch[ZS_F_COUNT] = {out->slot_pitch, out->slot_pitch, out->slot_pitch, out->slot_pitch, out->slot_pitch,
+                                   out->agent_pitch, out->static_pitch, out->dead_words, 8};
+    int64_t off = 0;
+    for (int f = 0; f < ZS_F_COUNT; ++f) {
+        out->offset[f] = off;
+        out->row_bytes[f] = elem[f] * pitch[f];
+        off += (int64_t)out->row_bytes[f] * N;
+        off = (off + 255) / 256 * 256;
+    }
+    out->state_bytes = off;
+    out->obs_channels = cfg->obs_encoding == ZS_OBS_CHANNELS ? 3 : 1;
+    if (cfg->obs_scope == ZS_OBS_WORLD) { out->obs_height = map->height; out->obs_width = map->width; }
+    else { out->obs_height = out->obs_width = cfg->surroundings_width; }
+    out->obs_count = cfg->obs_per_agent ? cfg->n_agents : 1;
+    out->obs_elems_per_env = (int64_t)out->obs_count * out->obs_channels * out->obs_height * out->obs_width;
+    out->n_discrete_actions = cfg->obs_per_agent ? 7 : 6;
+    return 0;
+}
+
+template <typename T>
+static int upload(ZsHandle* h, const std::vector<T>& v, const T** out) {
+    void* d = nullptr;
+    size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+    bytes = (bytes + 15) / 16 * 16;
+    CU(cudaMalloc(&d, bytes));
+    h->dev_allocs.push_back(d);
+    CU(cudaMemset(d, 0, bytes));
+    if (v.size()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* cfg, const ZsMap* map, ZsHandle** out) {
+    if (!out) return fail("null out");
+    *out = nullptr;
+    ZsLayout lay;
+    if (int rc = zs_layout(cfg, map, &lay)) return rc;
+    int dev = 0;
+    cudaDeviceProp prop;
+    CU(cudaGetDevice(&dev));
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail("this library is built for sm_100a (B200) only");
+    ZsHandle* h = new ZsHandle();
+    h->cfg = *cfg; h->lay = lay; h->launches = 0; h->bound_bytes = 0; h->sm_count = prop.multiProcessorCount;
+    ZsParams& p = h->p;
+    memset(&p, 0, sizeof(p));
+    p.N = cfg->num_envs; p.env_base = (uint32_t)cfg->env_index_base;
+    p.key0 = (uint32_t)cfg->seed; p.key1 = (uint32_t)(cfg->seed >> 32);
+    p.rules = cfg->rules; p.P = cfg->n_bots; p.A = cfg->n_agents;
+    p.Z = cfg->initial_zombies > cfg->minimum_zombies ? cfg->initial_zombies : cfg->minimum_zombies;
+    p.M = lay.n_slots; p.Mp = lay.slot_pitch; p.Ap = lay.agent_pitch; p.S = map->n_statics; p.Sp = lay.static_pitch;
+    p.W = map->width; p.H = map->height; p.cells = lay.cells; p.cells_pad = round_up(lay.cells, 16); p.dead_words = lay.dead_words;
+    p.initial_zombies = cfg->initial_zombies; p.minimum_zombies = cfg->minimum_zombies;
+    p.obs_scope = cfg->obs_scope; p.obs_enc = cfg->obs_encoding; p.sw = cfg->surroundings_width;
+    p.obs_count = lay.obs_count; p.obs_C = lay.obs_channels; p.obs_per_agent = cfg->obs_per_agent;
+    p.max_steps = cfg->max_episode_steps; p.auto_reset = cfg->auto_reset; p.n_discrete = lay.n_discrete_actions;
+    p.n_ps = map->n_player_spawns; p.n_zs = map->n_zombie_spawns; p.obs_elems = lay.obs_elems_per_env;
+    memcpy(p.agent_weapons, cfg->agent_weapons, sizeof(p.agent_weapons));
+    memcpy(p.agent_obs_ids, cfg->agent_obs_ids, sizeof(p.agent_obs_ids));
+
+    // ---- map tables
+    const int cells = p.cells, S = p.S;
+    std::vector<int16_t> cell_static(cells, -1), static_max(p.Sp, 0);
+    std::vector<uint16_t> static_cell(p.Sp, 0), ps(p.n_ps), zs(p.n_zs);
+    std::vector<uint8_t> static_label(p.Sp, 0), tmpl_grid(p.cells_pad, 0);
+    std::vector<int32_t> tmpl_obs(2 * (size_t)cells, 0);
+    std::vector<uint32_t> objective_bits(p.dead_words, 0);
+    auto cell_of = [&](const int16_t* xy, int i, int* c) {
+        int x = xy[2 * i], y = xy[2 * i + 1];
+        if (x < 0 || x >= p.W || y < 0 || y >= p.H) return false;
+        *c = y * p.W + x;
+        return true;
+    };
+    int c = 0;
+    for (int i = 0; i < map->n_objectives; ++i) {
+        if (!cell_of(map->objective_xy, i, &c)) { delete h; return fail("objective outside the map"); }
+        objective_bits[c >> 5] |= 1u << (c & 31);
+        tmpl_obs[c] = cfg->obs_encoding == ZS_OBS_SIMPLE ? 256 * ZS_LABEL_OBJECTIVE : ZS_LABEL_OBJECTIVE;
+    }
+    for (int i = 0; i < S; ++i) {
+        if (!cell_of(map->static_xy, i, &c)) { delete h; return fail("static thing outside the map"); }
+        const int label = map->static_label[i];
+        if (label != ZS_LABEL_BOX && label != ZS_LABEL_WALL) { delete h; return fail("static label must be box or wall"); }
+        if (cell_static[c] >= 0) { delete h; return fail("two static things on one cell"); }
+        const int mx = label == ZS_LABEL_BOX ? 10 : 200;
+        cell_static[c] = (int16_t)i; static_cell[i] = (uint16_t)c; static_max[i] = (int16_t)mx; static_label[i] = (uint8_t)label;
+        tmpl_grid[c] = G_STATIC;
+        if (cfg->obs_encoding == ZS_OBS_SIMPLE) tmpl_obs[c] = 256 * label + (15 * (mx < 100 ? mx : 100)) / 100;
+        else { tmpl_obs[c] = label; tmpl_obs[cells + c] = mx; }
+    }
+    for (int i = 0; i < p.n_ps; ++i) { if (!cell_of(map->player_spawn_xy, i, &c)) { delete h; return fail("spawn outside the map"); } ps[i] = (uint16_t)c; }
+    for (int i = 0; i < p.n_zs; ++i) { if (!cell_of(map->zombie_spawn_xy, i, &c)) { delete h; return fail("spawn outside the map"); } zs[i] = (uint16_t)c; }
+    int rc = 0;
+    rc |= upload(h, cell_static, &p.cell_static); rc |= upload(h, static_cell, &p.static_cell);
+    rc |= upload(h, static_max, &p.static_max); rc |= upload(h, static_label, &p.static_label);
+    rc |= upload(h, tmpl_grid, &p.tmpl_grid); rc |= upload(h, tmpl_obs, &p.tmpl_obs);
+    rc |= upload(h, objective_bits, &p.objective_bits); rc |= upload(h, ps, &p.ps_cells); rc |= upload(h, zs, &p.zs_cells);
+    std::vector<unsigned long long> zero(4, 0ull);
+    const unsigned long long* st = nullptr;
+    rc |= upload(h, zero, &st);
+    p.stats = (unsigned long long*)st;
+    if (rc) { zs_destroy(h); return rc; }
+
+    // ---- shared-memory carve-up per warp
+    int off = p.cells_pad;
+    auto take = [&](int bytes) { int o = off; off = round_up(off + bytes, 16); return o; };
+    p.off_dead = take(p.dead_words * 4);
+    p.off_tx = take(p.Mp * 2); p.off_ty = take(p.Mp * 2); p.off_tl = take(p.Mp * 2); p.off_ts = take(p.Mp * 4); p.off_tm = take(p.Mp);
+    p.off_dtype = take(p.Mp); p.off_da = take(p.Mp * 2); p.off_db = take(p.Mp * 2); p.off_act = take(p.Mp * 8);
+    p.draws_cap = round_up(3 * p.M + 4, 4);
+    p.off_draws = take(p.draws_cap * 4);
+    int cand = 1;
+    if (p.P + p.A > 0) cand = p.n_ps > 0 ? p.n_ps : cells;
+    if (p.Z > 0) { int zc = p.n_zs > 0 ? p.n_zs : cells; if (zc > cand) cand = zc; }
+    p.cand_cap = cand;
+    p.off_cand = take(cand * 2);
+    p.off_list = take(p.Mp * 2);
+    p.off_prev = take(p.Ap * 2);
+    p.off_acts = take(p.A * 12);
+    p.smem_per_warp = off;
+    const int smem = p.smem_per_warp * ZS_WPC;
+    if (smem > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
+    CU(cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    *out = h;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_destroy(ZsHandle* h) {
+    if (!h) return 0;
+    cudaDeviceSynchronize();
+    for (void* d : h->dev_allocs) cudaFree(d);
+    delete h;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_bind_state(ZsHandle* h, void* state_dev, int64_t bytes) {
+    if (!h) return fail("null handle");
+    if (!state_dev || bytes < h->lay.state_bytes) return fail("state buffer too small");
+    if (((uintptr_t)state_dev & 15) != 0) return fail("state buffer must be 16-byte aligned");
+    unsigned char* b = (unsigned char*)state_dev;
+    ZsParams& p = h->p;
+    p.X = (int16_t*)(b + h->lay.offset[ZS_F_X]); p.Y = (int16_t*)(b + h->lay.offset[ZS_F_Y]);
+    p.LIFE = (int16_t*)(b + h->lay.offset[ZS_F_LIFE]); p.STAMP = (int32_t*)(b + h->lay.offset[ZS_F_STAMP]);
+    p.META = (uint8_t*)(b + h->lay.offset[ZS_F_META]); p.PREV = (int16_t*)(b + h->lay.offset[ZS_F_PREV_LIFE]);
+    p.SLIFE = (int16_t*)(b + h->lay.offset[ZS_F_STATIC_LIFE]); p.DEAD = (uint32_t*)(b + h->lay.offset[ZS_F_DEAD_BODY]);
+    p.SCAL = (int32_t*)(b + h->lay.offset[ZS_F_SCALARS]);
+    h->bound_bytes = bytes;
+    return 0;
+}
+
+static int check_bound(ZsHandle* h) {
+    if (!h) return fail("null handle");
+    if (!h->bound_bytes) return fail("no state buffer bound (zs_bind_state)");
+    return 0;
+}
+static int launched(ZsHandle* h) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "kernel launch: %s", cudaGetErrorString(e)); return 2; }
+    h->launches++;
+    return 0;
+}
+static dim3 sim_grid(const ZsHandle* h) { return dim3((h->p.N + ZS_WPC - 1) / ZS_WPC); }
+
+extern "C" __attribute__((visibility("default"))) int zs_init_static_life(ZsHandle* h, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    zs_init_static_life_kernel<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(h->p);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_reset(ZsHandle* h, const uint8_t* env_mask_dev, int32_t* obs_dev, int32_t* draws_dev, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    ZsIO io;
+    memset(&io, 0, sizeof(io));
+    io.env_mask = env_mask_dev; io.obs = obs_dev; io.obs_slots = 1; io.draws = draws_dev;
+    zs_sim_kernel<MODE_RESET><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_step(ZsHandle* h, const int32_t* actions_dev, int32_t action_format, int32_t* obs_dev, double* reward_dev,
+                       uint8_t* terminated_dev, uint8_t* truncated_dev, uint8_t* agent_mask_dev, int32_t* draws_dev, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    if (!actions_dev) return fail("zs_step needs an action tensor");
+    if (action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
+    ZsIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1; io.reward = reward_dev;
+    io.terminated = terminated_dev; io.truncated = truncated_dev; io.agent_mask = agent_mask_dev; io.draws = draws_dev;
+    io.n_steps = 1;
+    zs_sim_kernel<MODE_STEP><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_encode_obs(ZsHandle* h, int32_t* obs_dev, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    if (!obs_dev) return fail("null obs");
+    ZsIO io;
+    memset(&io, 0, sizeof(io));
+    io.obs = obs_dev; io.obs_slots = 1;
+    zs_sim_kernel<MODE_ENCODE><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_rollout(ZsHandle* h, int32_t n_steps, int64_t first_step_index, const int32_t* actions_dev,
+                          int32_t action_format, int32_t* obs_dev, int32_t obs_slots, double* reward_dev,
+                          uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    if (n_steps < 1) return fail("n_steps must be >= 1");
+    if (obs_dev && obs_slots < 1) return fail("obs_slots must be >= 1");
+    if (actions_dev && action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
+    ZsIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = obs_slots; io.reward = reward_dev;
+    io.terminated = terminated_dev; io.truncated = truncated_dev; io.n_steps = n_steps; io.first_step = first_step_index;
+    io.force_auto_reset = 1;
+    zs_sim_kernel<MODE_STEP><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_fill_synthetic_actions(ZsHandle* h, int64_t step_index, int32_t* actions_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (!actions_dev) return fail("null actions");
+    const int n = h->p.N * h->p.A;
+    int blocks = (n + 255) / 256;
+    if (blocks > h->sm_count * 8) blocks = h->sm_count * 8;
+    zs_fill_actions_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->p, (uint32_t)step_index, actions_dev);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_episode_stats(ZsHandle* h, int64_t* out_dev, int32_t reset, void* stream) {
+    if (!h) return fail("null handle");
+    if (!out_dev) return fail("null out");
+    zs_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->p.stats, out_dev, reset);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t zs_launch_count(const ZsHandle* h) { return h ? h->launches : 0; }

@@ -1,0 +1,576 @@
+// zs_world.cuh — the world transition, rules, rewards and world (re)initialisation, one warp per env.
+// Reference line numbers are relative to the reference tree (jvstinian/libzombsole v0.13.2).
+#pragma once
+#include "zs_device.cuh"
+
+// ---------------------------------------------------------------- state <-> shared memory
+__device__ __forceinline__ void env_bind(const ZsParams& p, Env& e, unsigned char* base, int env, int lane) {
+    e.grid = base;
+    e.dead = (uint32_t*)(base + p.off_dead);
+    e.tx = (int16_t*)(base + p.off_tx); e.ty = (int16_t*)(base + p.off_ty); e.tl = (int16_t*)(base + p.off_tl);
+    e.ts = (int32_t*)(base + p.off_ts); e.tm = base + p.off_tm;
+    e.dtype = base + p.off_dtype; e.da = (int16_t*)(base + p.off_da); e.db = (int16_t*)(base + p.off_db);
+    e.act = (unsigned long long*)(base + p.off_act); e.draws = (uint32_t*)(base + p.off_draws);
+    e.cand = (uint16_t*)(base + p.off_cand); e.list = (uint16_t*)(base + p.off_list);
+    e.prev = (int16_t*)(base + p.off_prev); e.acts = (int32_t*)(base + p.off_acts);
+    e.env = env; e.env_global = p.env_base + (uint32_t)env; e.lane = lane;
+    e.slife = p.SLIFE + (size_t)env * p.Sp;
+}
+
+__device__ __forceinline__ void load_scalars(const ZsParams& p, Env& e) {
+    int sc = e.lane < 8 ? p.SCAL[(size_t)e.env * 8 + e.lane] : 0;
+    e.t = __shfl_sync(ZS_FULL, sc, ZS_S_T); e.episode = __shfl_sync(ZS_FULL, sc, ZS_S_EPISODE);
+    e.deaths = __shfl_sync(ZS_FULL, sc, ZS_S_DEATHS); e.zd = __shfl_sync(ZS_FULL, sc, ZS_S_ZOMBIE_DEATHS);
+    e.stampctr = __shfl_sync(ZS_FULL, sc, ZS_S_STAMP_COUNTER); e.flags = __shfl_sync(ZS_FULL, sc, ZS_S_FLAGS);
+    e.prev_zd = __shfl_sync(ZS_FULL, sc, ZS_S_PREV_ZOMBIE_DEATHS); e.ep_steps = __shfl_sync(ZS_FULL, sc, ZS_S_EPISODE_STEPS);
+}
+
+__device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
+    const size_t row = (size_t)e.env * p.Mp;
+    for (int s = e.lane; s < p.Mp; s += 32) {
+        e.tx[s] = p.X[row + s]; e.ty[s] = p.Y[row + s]; e.tl[s] = p.LIFE[row + s];
+        e.ts[s] = p.STAMP[row + s]; e.tm[s] = p.META[row + s];
+    }
+    for (int w = e.lane; w < p.dead_words; w += 32) e.dead[w] = p.DEAD[(size_t)e.env * p.dead_words + w];
+    for (int a = e.lane; a < p.Ap; a += 32) e.prev[a] = p.PREV[(size_t)e.env * p.Ap + a];
+    load_scalars(p, e);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void store_state(const ZsParams& p, Env& e) {
+    __syncwarp();
+    const size_t row = (size_t)e.env * p.Mp;
+    for (int s = e.lane; s < p.Mp; s += 32) {
+        p.X[row + s] = e.tx[s]; p.Y[row + s] = e.ty[s]; p.LIFE[row + s] = e.tl[s];
+        p.STAMP[row + s] = e.ts[s]; p.META[row + s] = e.tm[s];
+    }
+    for (int w = e.lane; w < p.dead_words; w += 32) p.DEAD[(size_t)e.env * p.dead_words + w] = e.dead[w];
+    for (int a = e.lane; a < p.Ap; a += 32) p.PREV[(size_t)e.env * p.Ap + a] = e.prev[a];
+    if (e.lane < 8) {
+        int v = e.lane == ZS_S_T ? e.t : e.lane == ZS_S_EPISODE ? e.episode : e.lane == ZS_S_DEATHS ? e.deaths
+              : e.lane == ZS_S_ZOMBIE_DEATHS ? e.zd : e.lane == ZS_S_STAMP_COUNTER ? e.stampctr
+              : e.lane == ZS_S_FLAGS ? e.flags : e.lane == ZS_S_PREV_ZOMBIE_DEATHS ? e.prev_zd : e.ep_steps;
+        p.SCAL[(size_t)e.env * 8 + e.lane] = v;
+    }
+}
+
+__device__ __forceinline__ int16_t half_of(const uint4& v, int q) {
+    uint32_t w = q < 2 ? v.x : q < 4 ? v.y : q < 6 ? v.z : v.w;
+    return (int16_t)((q & 1) ? (w >> 16) : (w & 0xffffu));
+}
+
+// Rebuild the occupancy grid from the compact state.  `fresh` = first step after a world init:
+// boxes/walls whose life is already <= 0 are still in World.things (game.py:154-155) until the
+// first clean_dead_things.
+__device__ __forceinline__ void build_grid(const ZsParams& p, Env& e) {
+    const bool fresh = e.flags & 1;
+    const uint4* tg = (const uint4*)p.tmpl_grid;
+    uint4* g4 = (uint4*)e.grid;
+    for (int i = e.lane; i < (p.cells_pad >> 4); i += 32) g4[i] = __ldg(tg + i);
+    __syncwarp();
+    const uint4* sl4 = (const uint4*)e.slife;
+    const uint4* mx4 = (const uint4*)p.static_max;
+    for (int i = e.lane; i < (p.Sp >> 3); i += 32) {
+        uint4 a = sl4[i];
+        uint4 m = __ldg(mx4 + i);
+        if (a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                int life = half_of(a, q), mx = half_of(m, q);
+                if (life != mx) e.grid[__ldg(p.static_cell + i * 8 + q)] = (life <= 0 && !fresh) ? G_EMPTY : G_STATIC_DMG;
+            }
+        }
+    }
+    __syncwarp();
+    for (int w = e.lane; w < p.dead_words; w += 32) {
+        uint32_t bits = e.dead[w];
+        while (bits) {
+            int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            int c = w * 32 + b;
+            if (e.grid[c] == G_EMPTY) e.grid[c] = G_DEAD;
+        }
+    }
+    __syncwarp();
+    for (int s = e.lane; s < p.M; s += 32)
+        if (e.tm[s] & 0x80) e.grid[e.ty[s] * p.W + e.tx[s]] = (uint8_t)(s + 1);
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- decide phase
+// closest(self, others) with others = in-world slots [lo, hi): sorted() is stable, so ties in the
+// distance go to the thing that comes first in World.things = smallest stamp (utils.py:23-31).
+__device__ __forceinline__ int closest_slot(const Env& e, int lo, int hi, int x, int y, int skip, int& best_d2) {
+    unsigned long long best = ~0ull;
+    int arg = -1;
+    for (int j = lo; j < hi; ++j) {
+        if (!(e.tm[j] & 0x80) || j == skip) continue;
+        unsigned long long key = ((unsigned long long)(uint32_t)dist2(x, y, e.tx[j], e.ty[j]) << 32) | (uint32_t)e.ts[j];
+        if (key < best) { best = key; arg = j; }
+    }
+    best_d2 = (int)(best >> 32);
+    return arg;
+}
+
+// target id: mobile slot s -> s, static i -> M + i
+__device__ __forceinline__ int target_of_cell(const ZsParams& p, int g, int cell) {
+    return g <= G_MAX_SLOT ? g - 1 : p.M + (int)__ldg(p.cell_static + cell);
+}
+
+// Zombie.next_step (zombsole/things.py:70-105)
+__device__ __forceinline__ void decide_zombie(const ZsParams& p, const Env& e, int s, bool has_humans, int& type, int& a, int& b) {
+    const int x = e.tx[s], y = e.ty[s];
+    unsigned freemask = 0, gs[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {  // possible_moves: no bounds check (utils.py:47-52)
+        gs[d] = grid_at(p, e, x + adj_dx(d), y + adj_dy(d));
+        if (!g_is_thing(gs[d])) freemask |= 1u << d;
+    }
+    type = D_IDLE; a = 0; b = 0;
+    if (!has_humans) {
+        if (freemask) { type = D_WANDER; a = (int)freemask; }
+        return;
+    }
+    int d2;
+    const int tg = closest_slot(e, 0, p.P + p.A, x, y, -1, d2);
+    if (d2 <= 2) { type = D_ATTACK; a = tg; return; }  // distance < 1.5 (things.py:83)
+    const int gx = e.tx[tg], gy = e.ty[tg];
+    int best = -1, best_d = 0x7fffffff;
+    if (freemask) {  // closest(target, positions): first minimum in adjacency order
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int dd = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
+            if (((freemask >> d) & 1u) && dd < best_d) { best = d; best_d = dd; }
+        }
+        type = D_MOVE; a = x + adj_dx(best); b = y + adj_dy(best);
+        return;
+    }
+    // boxed in: first Box/Wall among the adjacent cells stably sorted by distance to the target (things.py:93-99)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        int dd = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
+        if (g_is_static(gs[d]) && dd < best_d) { best = d; best_d = dd; }
+    }
+    if (best >= 0) {
+        int cx = x + adj_dx(best), cy = y + adj_dy(best);
+        type = D_ATTACK; a = p.M + (int)__ldg(p.cell_static + cy * p.W + cx);
+    }
+}
+
+// Terminator.next_step (zombsole/players/terminator.py:9-37)
+__device__ __forceinline__ void decide_terminator(const ZsParams& p, const Env& e, int s, int& type, int& a, int& b) {
+    const int x = e.tx[s], y = e.ty[s];
+    int d2;
+    const int tg = closest_slot(e, p.P + p.A, p.M, x, y, -1, d2);
+    b = 0;
+    if (tg < 0) { type = D_HEAL; a = s; return; }
+    if (d2 > c_range2[e.tm[s] & 15]) {
+        const int gx = e.tx[tg], gy = e.ty[tg];
+        int best = 0, best_d = 0x7fffffff;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {  // closest(target, adjacent_positions(self)): out-of-bounds cells included
+            int dd = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
+            if (dd < best_d) { best = d; best_d = dd; }
+        }
+        const int bx = x + adj_dx(best), by = y + adj_dy(best);
+        const int g = grid_at(p, e, bx, by);
+        if (g_is_thing(g)) {
+            const bool is_player = g <= G_MAX_SLOT && (g - 1) < p.P + p.A;
+            type = is_player ? D_HEAL : D_ATTACK;
+            a = target_of_cell(p, g, by * p.W + bx);
+        } else { type = D_MOVE; a = bx; b = by; }
+        return;
+    }
+    type = D_ATTACK; a = tg;
+}
+
+// Agent.next_step (zombsole/players/agent.py:28-96)
+__device__ __forceinline__ void decide_agent(const ZsParams& p, const Env& e, int s, int& type, int& a, int& b) {
+    const int x = e.tx[s], y = e.ty[s];
+    const int ai = s - p.P;
+    int at = e.acts[3 * ai], dx = e.acts[3 * ai + 1], dy = e.acts[3 * ai + 2];
+    if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; dx = 0; dy = 0; }  // multiagent_env.py:129-131
+    type = D_IDLE; a = 0; b = 0;
+    int d2;
+    switch (at) {
+        case ZS_ACT_MOVE: type = D_MOVE; a = x + dx; b = y + dy; break;
+        case ZS_ACT_ATTACK_CLOSEST: {
+            int tg = closest_slot(e, p.P + p.A, p.M, x, y, -1, d2);
+            if (tg >= 0) { type = D_ATTACK; a = tg; }
+            break;
+        }
+        case ZS_ACT_ATTACK: {
+            int g = grid_at(p, e, x + dx, y + dy);
+            if (g_is_thing(g)) { type = D_ATTACK; a = target_of_cell(p, g, (y + dy) * p.W + (x + dx)); }
+            break;
+        }
+        case ZS_ACT_HEAL: {
+            if (dx == 0 && dy == 0) { type = D_HEAL; a = s; break; }
+            int g = grid_at(p, e, x + dx, y + dy);
+            // Player / Box / Wall only (agent.py:69-75)
+            if (g_is_static(g) || (g_is_thing(g) && (g - 1) < p.P + p.A)) {
+                type = D_HEAL; a = target_of_cell(p, g, (y + dy) * p.W + (x + dx));
+            }
+            break;
+        }
+        case ZS_ACT_HEAL_CLOSEST: {
+            int tg = closest_slot(e, 0, p.P + p.A, x, y, s, d2);
+            type = D_HEAL; a = tg >= 0 ? tg : s;
+            break;
+        }
+        default: break;
+    }
+}
+
+__device__ __forceinline__ unsigned long long pack_action(int actor, int type, int a, int b) {
+    return (unsigned long long)(uint32_t)actor | ((unsigned long long)(uint32_t)type << 8) |
+           ((unsigned long long)(uint16_t)(int16_t)a << 16) | ((unsigned long long)(uint16_t)(int16_t)b << 32);
+}
+
+// ---------------------------------------------------------------- World.step (core.py:72-78)
+// Returns the number of draws consumed so far in this step's draw cell.
+__device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
+    const int lane = e.lane;
+    const int NP = p.P + p.A;
+    e.t += 1;
+    const uint32_t t_word = (uint32_t)(e.t + 1);
+
+    // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
+    bool hh = false;
+    for (int s = lane; s < NP; s += 32) hh |= (e.tm[s] & 0x80) != 0;
+    const bool has_humans = __any_sync(ZS_FULL, hh);
+    for (int s = lane; s < p.M; s += 32) {
+        int type = D_IDLE, a = 0, b = 0;
+        if (e.tm[s] & 0x80) {
+            if (s >= NP) decide_zombie(p, e, s, has_humans, type, a, b);
+            else if (s >= p.P) decide_agent(p, e, s, type, a, b);
+            else decide_terminator(p, e, s, type, a, b);
+        }
+        e.dtype[s] = (uint8_t)type; e.da[s] = (int16_t)a; e.db[s] = (int16_t)b;
+    }
+    __syncwarp();
+    int nd = 0;
+    if (!has_humans) {
+        // wandering zombies draw random.choice(positions) in dict (= stamp) order (things.py:101-103)
+        int mine = 0;
+        for (int s = lane; s < p.M; s += 32) {
+            if (e.dtype[s] != D_WANDER) continue;
+            int rank = 0;
+            for (int j = NP; j < p.M; ++j) rank += (e.dtype[j] == D_WANDER && e.ts[j] < e.ts[s]);
+            unsigned fm = (unsigned)e.da[s];
+            int pick = below(draw_at(p, e, t_word, rank), __popc(fm));
+            int d = 0;
+            for (int q = 0; q < 4; ++q) if ((fm >> q) & 1u) { if (pick == 0) { d = q; break; } --pick; }
+            e.da[s] = (int16_t)(e.tx[s] + adj_dx(d)); e.db[s] = (int16_t)(e.ty[s] + adj_dy(d));
+            ++mine;
+        }
+        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(ZS_FULL, mine, o);
+        nd = mine;
+        __syncwarp();
+        for (int s = lane; s < p.M; s += 32) if (e.dtype[s] == D_WANDER) e.dtype[s] = D_MOVE;
+        __syncwarp();
+    }
+    // actions list in actor (dict) order: position = number of acting things with a smaller stamp
+    int cnt = 0, n_ah = 0;
+    for (int s = lane; s < p.M; s += 32) {
+        const int type = e.dtype[s];
+        if (type == D_IDLE) continue;
+        const int st = e.ts[s];
+        int pos = 0;
+        for (int j = 0; j < p.M; ++j) pos += (e.dtype[j] != D_IDLE && e.ts[j] < st);
+        e.act[pos] = pack_action(s, type, e.da[s], e.db[s]);
+        ++cnt;
+        n_ah += type != D_MOVE;
+    }
+    for (int o = 16; o; o >>= 1) {
+        cnt += __shfl_xor_sync(ZS_FULL, cnt, o);
+        n_ah += __shfl_xor_sync(ZS_FULL, n_ah, o);
+    }
+    const int L = cnt;
+    // ---- draws of this step, generated 4 per lane (counter-based: any k is available directly)
+    const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
+    for (int blk = lane; blk * 4 < n_need; blk += 32) {
+        uint32_t o[4];
+        philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)blk, p.key0, p.key1, o);
+        *(uint4*)(e.draws + 4 * blk) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncwarp();
+
+    // ---- random.shuffle + execute_actions: order-dependent by definition, run by lane 0
+    int k = nd;
+    if (lane == 0) {
+        for (int i = L - 1; i >= 1; --i) {  // CPython Random.shuffle
+            int j = below(e.draws[k++], i + 1);
+            unsigned long long tmp = e.act[i]; e.act[i] = e.act[j]; e.act[j] = tmp;
+        }
+        int n_touched = 0;
+        for (int i = 0; i < L; ++i) {
+            const unsigned long long pk = e.act[i];
+            const int actor = (int)(pk & 0xff), type = (int)((pk >> 8) & 0xff);
+            const int a = (int16_t)(pk >> 16), b = (int16_t)(pk >> 32);
+            const int ax = e.tx[actor], ay = e.ty[actor];
+            if (type == D_MOVE) {  // World.thing_move (core.py:140-166)
+                if ((unsigned)a < (unsigned)p.W && (unsigned)b < (unsigned)p.H) {
+                    const int c = b * p.W + a;
+                    if (!g_is_thing(e.grid[c]) && dist2(ax, ay, a, b) <= 1) {
+                        const int old = ay * p.W + ax;
+                        e.grid[old] = dead_bit(e, old) ? G_DEAD : G_EMPTY;
+                        e.grid[c] = (uint8_t)(actor + 1);
+                        e.tx[actor] = (int16_t)a; e.ty[actor] = (int16_t)b;
+                        e.ts[actor] = e.stampctr++;  // things[dest] = thing; del things[old]: goes last
+                    }
+                }
+                continue;
+            }
+            int gx, gy, cell = 0;
+            const bool is_static = a >= p.M;
+            if (is_static) {
+                cell = __ldg(p.static_cell + (a - p.M));
+                gy = cell / p.W; gx = cell - gy * p.W;
+            } else { gx = e.tx[a]; gy = e.ty[a]; }
+            const int d2 = dist2(ax, ay, gx, gy);
+            if (type == D_ATTACK) {  // World.thing_attack (core.py:168-184)
+                const int w = e.tm[actor] & 15;
+                if (d2 > c_range2[w]) continue;
+                const int dmg = c_dmg_lo[w] + below(e.draws[k++], c_dmg_n[w]);
+                if (is_static) {
+                    e.slife[a - p.M] = (int16_t)(e.slife[a - p.M] - dmg);
+                    e.grid[cell] = G_STATIC_DMG;
+                    e.list[n_touched++] = (uint16_t)(a - p.M);
+                } else e.tl[a] = (int16_t)(e.tl[a] - dmg);
+            } else {  // World.thing_heal (core.py:186-202)
+                if (d2 > 9) continue;
+                const int mx = is_static ? max_life_of_label(__ldg(p.static_label + (a - p.M))) : 100;
+                const int heal = mx / 10 + below(e.draws[k++], mx / 4 - mx / 10 + 1);
+                if (is_static) {
+                    const int nl = e.slife[a - p.M] + heal;
+                    e.slife[a - p.M] = (int16_t)(nl < mx ? nl : mx);
+                    e.grid[cell] = G_STATIC_DMG;
+                } else {
+                    const int nl = e.tl[a] + heal;
+                    e.tl[a] = (int16_t)(nl < mx ? nl : mx);
+                }
+            }
+        }
+        // clean_dead_things for boxes/walls hit this step (core.py:121-138); the full scan below
+        // covers them on the first step of a world
+        if (!(e.flags & 1)) {
+            for (int i = 0; i < n_touched; ++i) {
+                const int si = e.list[i];
+                const int cell = __ldg(p.static_cell + si);
+                if (e.slife[si] <= 0 && g_is_static(e.grid[cell])) { e.grid[cell] = G_EMPTY; e.deaths++; }
+            }
+        }
+    }
+    k = __shfl_sync(ZS_FULL, k, 0);
+    e.stampctr = __shfl_sync(ZS_FULL, e.stampctr, 0);
+    e.deaths = __shfl_sync(ZS_FULL, e.deaths, 0);
+    __syncwarp();
+
+    // ---- clean_dead_things (core.py:121-138)
+    int nd_all = 0, nd_z = 0;
+    if (e.flags & 1) {  // first step of this world: every box/wall with life <= 0 leaves now
+        for (int i = lane; i < p.S; i += 32) {
+            if (e.slife[i] <= 0) {
+                const int cell = __ldg(p.static_cell + i);
+                if (g_is_static(e.grid[cell])) { e.grid[cell] = G_EMPTY; ++nd_all; }
+            }
+        }
+        e.flags &= ~1;
+    }
+    for (int s = lane; s < p.M; s += 32) {
+        if ((e.tm[s] & 0x80) && e.tl[s] <= 0) {
+            const int c = e.ty[s] * p.W + e.tx[s];
+            e.grid[c] = G_DEAD;                       // DeadBody overwrites any decoration (core.py:30-31,126-128)
+            atomicOr(&e.dead[c >> 5], 1u << (c & 31));
+            e.tm[s] &= 0x7f;
+            ++nd_all;
+            nd_z += s >= NP;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        nd_all += __shfl_xor_sync(ZS_FULL, nd_all, o);
+        nd_z += __shfl_xor_sync(ZS_FULL, nd_z, o);
+    }
+    e.deaths += nd_all;
+    e.zd += nd_z;
+    __syncwarp();
+    return k;
+}
+
+// ---------------------------------------------------------------- World.spawn_in_random (core.py:40-66)
+// Places the `count` slots listed in e.list[0..count) on shuffled free cells of `spawn` (or of the
+// whole map, x-major, when the map has no such spawn cells).  Only the first `count` Fisher-Yates
+// iterations decide placements (spawns.pop() takes from the end); the rest of the shuffle only
+// advances the draw counter.  Returns the new draw index.
+__device__ __forceinline__ int spawn_in_random(const ZsParams& p, Env& e, uint32_t t_word, int k, int count,
+                                               const uint16_t* spawn, int n_spawn) {
+    const int lane = e.lane;
+    const int n_src = n_spawn > 0 ? n_spawn : p.cells;
+    int n = 0;
+    for (int base = 0; base < n_src; base += 32) {
+        const int i = base + lane;
+        bool ok = false;
+        int c = 0;
+        if (i < n_src) {
+            if (n_spawn > 0) c = __ldg(spawn + i);
+            else { int x = i / p.H; int y = i - x * p.H; c = y * p.W + x; }
+            ok = !g_is_thing(e.grid[c]);
+        }
+        const unsigned m = __ballot_sync(ZS_FULL, ok);
+        if (ok) e.cand[n + __popc(m & ((1u << lane) - 1u))] = (uint16_t)c;
+        n += __popc(m);
+    }
+    __syncwarp();
+    const int placed = count < n ? count : n;
+    for (int it = lane; it < placed; it += 32) {
+        const int i = n - 1 - it;
+        e.draws[it] = i >= 1 ? (uint32_t)below(draw_at(p, e, t_word, k + it), i + 1) : 0u;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int it = 0; it < placed; ++it) {
+            const int i = n - 1 - it;
+            if (i >= 1) { const int j = (int)e.draws[it]; uint16_t tmp = e.cand[i]; e.cand[i] = e.cand[j]; e.cand[j] = tmp; }
+            const int c = e.cand[i];
+            const int s = e.list[it];
+            const int y = c / p.W;
+            e.tx[s] = (int16_t)(c - y * p.W); e.ty[s] = (int16_t)y;
+            e.tm[s] |= 0x80;
+            e.ts[s] = e.stampctr + it;
+            e.grid[c] = (uint8_t)(s + 1);
+        }
+    }
+    e.stampctr += placed;
+    __syncwarp();
+    return k + (n > 1 ? n - 1 : 0);
+}
+
+// Game.spawn_zombies (game.py:189-194): `count` Zombie() constructions (life draws, things.py:62)
+// followed by spawn_in_random on the zombie spawn cells; free zombie slots are taken in ascending order.
+__device__ __forceinline__ int spawn_zombies(const ZsParams& p, Env& e, uint32_t t_word, int k, int count) {
+    const int lane = e.lane;
+    const int NP = p.P + p.A;
+    int n = 0;
+    for (int base = NP; base < p.M; base += 32) {
+        const int s = base + lane;
+        const bool free_slot = s < p.M && !(e.tm[s] & 0x80);
+        const unsigned m = __ballot_sync(ZS_FULL, free_slot);
+        const int pos = n + __popc(m & ((1u << lane) - 1u));
+        if (free_slot && pos < count) e.list[pos] = (uint16_t)s;
+        n += __popc(m);
+    }
+    const int made = count < n ? count : n;
+    __syncwarp();
+    for (int i = lane; i < made; i += 32) {
+        const int s = e.list[i];
+        e.tl[s] = (int16_t)(50 + below(draw_at(p, e, t_word, k + i), 51));
+        e.tm[s] = ZS_WEAPON_CLAWS;
+    }
+    __syncwarp();
+    return spawn_in_random(p, e, t_word, k + count, made, p.zs_cells, p.n_zs);
+}
+
+// Game.__initialize_world__ (game.py:151-169) + reward_tracker.reset (reward.py:26-28).
+// Returns the number of draws consumed.
+__device__ __forceinline__ int initialize_world(const ZsParams& p, Env& e, int episode) {
+    const int lane = e.lane;
+    const int NP = p.P + p.A;
+    e.episode = episode;
+    e.t = -1; e.deaths = 0; e.zd = 0; e.ep_steps = 0; e.stampctr = 0; e.flags = 1; e.prev_zd = 0;
+    for (int w = lane; w < p.dead_words; w += 32) e.dead[w] = 0;
+    int k = 0;
+    for (int s = lane; s < p.Mp; s += 32) {
+        int w = 0;
+        if (s < p.P) w = ZS_WEAPON_SHOTGUN;            // terminator.py:41-42
+        else if (s < NP) w = p.agent_weapons[s - p.P];
+        else w = ZS_WEAPON_CLAWS;
+        e.tm[s] = (uint8_t)(w == ZS_WEAPON_RANDOM ? 15 : w);
+        if (s < NP) e.tl[s] = 100;
+    }
+    __syncwarp();
+    // agent_weapon="random": one random.choice per agent, in agent order (weapons.py:43)
+    for (int a = 0; a < p.A; ++a) {
+        if (p.agent_weapons[a] == ZS_WEAPON_RANDOM) {
+            const int pick = below(draw_at(p, e, 0u, k), 5);
+            ++k;
+            if (lane == 0) e.tm[p.P + a] = (uint8_t)(pick == 0 ? ZS_WEAPON_KNIFE : pick == 1 ? ZS_WEAPON_AXE
+                                                     : pick == 2 ? ZS_WEAPON_GUN : pick == 3 ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN);
+        }
+    }
+    __syncwarp();
+    build_grid(p, e);  // every slot is out of the world here: statics (all present) only
+    for (int s = lane; s < p.P; s += 32) e.list[s] = (uint16_t)s;
+    __syncwarp();
+    k = spawn_in_random(p, e, 0u, k, p.P, p.ps_cells, p.n_ps);
+    for (int a = lane; a < p.A; a += 32) e.list[a] = (uint16_t)(p.P + a);
+    __syncwarp();
+    k = spawn_in_random(p, e, 0u, k, p.A, p.ps_cells, p.n_ps);
+    k = spawn_zombies(p, e, 0u, k, p.initial_zombies);
+    for (int a = lane; a < p.A; a += 32) e.prev[a] = e.tl[p.P + a];
+    __syncwarp();
+    return k;
+}
+
+// ---------------------------------------------------------------- rules (zombsole/rules/*.py)
+__device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, bool& ended, bool& won, bool& agents_alive) {
+    const int lane = e.lane;
+    const int NP = p.P + p.A;
+    int alive = 0, ag = 0;
+    for (int s = lane; s < NP; s += 32) {
+        const bool al = e.tl[s] > 0;
+        alive += al;
+        ag += al && s >= p.P;
+    }
+    for (int o = 16; o; o >>= 1) {
+        alive += __shfl_xor_sync(ZS_FULL, alive, o);
+        ag += __shfl_xor_sync(ZS_FULL, ag, o);
+    }
+    agents_alive = ag > 0;                    // rules/rules.py:13-18
+    const bool players_alive = alive > 0;     // rules/rules.py:6-11
+    won = players_alive;
+    if (p.rules == ZS_RULES_EXTERMINATION) {  // extermination.py:12-26
+        bool z = false;
+        for (int s = NP + lane; s < p.M; s += 32) z |= (e.tm[s] & 0x80) && e.tl[s] > 0;
+        ended = !players_alive || !__any_sync(ZS_FULL, z);
+    } else if (p.rules == ZS_RULES_SURVIVAL) {  // survival.py:5-7
+        ended = !players_alive;
+    } else if (p.rules == ZS_RULES_SAFEHOUSE) {  // safehouse.py:10-32
+        bool out = false;
+        for (int s = lane; s < NP; s += 32)
+            out |= e.tl[s] > 0 && !objective_bit(p, e.ty[s] * p.W + e.tx[s]);
+        ended = players_alive ? !__any_sync(ZS_FULL, out) : true;
+    } else {  // evacuation.py:13-57: at least half the team alive and the living form one 4-connected cluster
+        const bool half = 2 * alive >= NP;  // len(alive) >= len(all) / 2.0
+        won = half;
+        ended = true;
+        if (half) {
+            int together = 0;
+            if (lane == 0) {
+                unsigned long long seen = 0, pending = 0;
+                int first = 0;
+                while (e.tl[first] <= 0) ++first;
+                pending = 1ull << first;
+                while (pending) {
+                    const int s = __ffsll((long long)pending) - 1;
+                    pending &= pending - 1;
+                    seen |= 1ull << s;
+                    ++together;
+                    const int x = e.tx[s], y = e.ty[s];
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int g = grid_at(p, e, x + adj_dx(d), y + adj_dy(d));
+                        if (g >= 1 && g <= NP && e.tl[g - 1] > 0 && !((seen | pending) >> (g - 1) & 1ull)) pending |= 1ull << (g - 1);
+                    }
+                }
+            }
+            together = __shfl_sync(ZS_FULL, together, 0);
+            ended = together == alive;
+        }
+    }
+}
+
+__device__ __forceinline__ double total_reward(int zombie_deaths, int life_sum) {
+    // reward.py:37-41 / 90-92: int + float, the division first
+    return __dadd_rn(__int2double_rn(zombie_deaths), __ddiv_rn(__int2double_rn(life_sum), 100.0));
+}

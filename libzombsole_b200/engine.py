@@ -1,0 +1,127 @@
+"""ZsEngine: N worlds resident in HBM, driven through the C ABI (include/zs_b200.h).
+
+PyTorch is the plumbing here — it owns the device memory (state buffer, action / observation /
+reward tensors) and the stream; every transition is computed by the hand-written sm_100a
+kernels in csrc/.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+from ._native import lib, check, ZsError
+
+_TORCH_DTYPES = {np.int16: torch.int16, np.int32: torch.int32, np.uint8: torch.uint8, np.uint32: torch.int32}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class ZsEngine(object):
+    def __init__(self, cfg, map_, device="cuda"):
+        if not torch.cuda.is_available():
+            raise ZsError("no CUDA device: the batched zombsole simulator has no CPU path")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ZsError("device must be a CUDA device, got %r" % (device,))
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.L = lib()
+        self.cfg = cfg
+        self.map_arg = abi.MapArg(abi.resolve_map(map_))
+        self.map = self.map_arg.map
+        self.layout = abi.ZsLayout()
+        check(self.L.zs_layout(C.byref(cfg), C.byref(self.map_arg.struct), C.byref(self.layout)))
+        self.N = cfg.num_envs
+        self.A = cfg.n_agents
+        self.P = cfg.n_bots
+        self.M = self.layout.n_slots
+        self.S = len(self.map.statics)
+        self.cells = self.layout.cells
+        self.obs_elems = int(self.layout.obs_elems_per_env)
+        self.per_agent = bool(cfg.obs_per_agent)
+        self.R = self.A if self.per_agent else 1
+        lay = self.layout
+        if self.per_agent:
+            self.obs_shape = (self.A, lay.obs_channels, lay.obs_height, lay.obs_width)
+        else:
+            self.obs_shape = (lay.obs_channels, lay.obs_height, lay.obs_width)
+        self.n_discrete_actions = lay.n_discrete_actions
+        self.h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream()  # make sure the primary context exists
+            check(self.L.zs_set_device(self.device.index))
+            check(self.L.zs_create(C.byref(cfg), C.byref(self.map_arg.struct), C.byref(self.h)))
+            self.state = torch.zeros(int(lay.state_bytes), dtype=torch.uint8, device=self.device)
+            check(self.L.zs_bind_state(self.h, self.state.data_ptr(), int(lay.state_bytes)))
+            check(self.L.zs_init_static_life(self.h, self._stream()))
+        self.fields = {}
+        for f, name in abi.FIELD_NAMES.items():
+            dt = abi.FIELD_DTYPES[f]
+            nbytes = lay.row_bytes[f] * self.N
+            flat = self.state[lay.offset[f]: lay.offset[f] + nbytes]
+            self.fields[name] = flat.view(_TORCH_DTYPES[dt]).view(self.N, -1)
+        self.reset_draws = torch.zeros(self.N, dtype=torch.int32, device=self.device)
+        self.reset()  # world initialisation #0: what the reference's constructor does (game.py:138)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.zs_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def new_obs(self, slots=None):
+        shape = (self.N,) + self.obs_shape if slots is None else (slots, self.N) + self.obs_shape
+        return torch.empty(shape, dtype=torch.int32, device=self.device)
+
+    def new_outputs(self, steps=None):
+        lead = (self.N,) if steps is None else (steps, self.N)
+        rshape = lead + ((self.A,) if self.per_agent else ())
+        return (torch.empty(rshape, dtype=torch.float64, device=self.device),
+                torch.empty(lead, dtype=torch.uint8, device=self.device),
+                torch.empty(lead, dtype=torch.uint8, device=self.device))
+
+    # ------------------------------------------------------------------ the ABI calls
+    def reset(self, mask=None, obs=None):
+        """zs_reset: re-initialise the masked worlds (all if mask is None)."""
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self.L.zs_reset(self.h, _ptr(mask), _ptr(obs), _ptr(self.reset_draws), self._stream()))
+        return obs
+
+    def step(self, actions, fmt, obs, reward, terminated, truncated, agent_mask=None, draws=None):
+        check(self.L.zs_step(self.h, _ptr(actions), fmt, _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated),
+                             _ptr(agent_mask), _ptr(draws), self._stream()))
+
+    def encode_obs(self, obs):
+        check(self.L.zs_encode_obs(self.h, _ptr(obs), self._stream()))
+        return obs
+
+    def rollout(self, n_steps, first_step_index=0, actions=None, fmt=abi.ACTIONS_DISCRETE, obs=None, reward=None,
+                terminated=None, truncated=None):
+        slots = 0 if obs is None else (obs.shape[0] if obs.dim() == len(self.obs_shape) + 2 else 1)
+        check(self.L.zs_rollout(self.h, int(n_steps), int(first_step_index), _ptr(actions), fmt, _ptr(obs), slots,
+                                _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream()))
+
+    def fill_synthetic_actions(self, step_index, actions):
+        check(self.L.zs_fill_synthetic_actions(self.h, int(step_index), _ptr(actions), self._stream()))
+        return actions
+
+    def episode_stats(self, reset=False):
+        out = torch.zeros(4, dtype=torch.int64, device=self.device)
+        check(self.L.zs_episode_stats(self.h, _ptr(out), 1 if reset else 0, self._stream()))
+        return out
+
+    def launch_count(self):
+        return int(self.L.zs_launch_count(self.h))
