@@ -34,7 +34,7 @@ __device__ __forceinline__ void discrete_to_action(const ZsParams& p, int id, in
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(ZS_WPC * 32) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
+__global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int env = blockIdx.x * ZS_WPC + wid;
@@ -63,6 +63,13 @@ __global__ void __launch_bounds__(ZS_WPC * 32) zs_sim_kernel(const __grid_consta
     const int R = p.obs_per_agent ? A : 1;
     for (int step = 0; step < io.n_steps; ++step) {
         const size_t sn = (size_t)step * p.N + env;
+        int32_t* obs_out = nullptr;
+        if (io.obs) {
+            const size_t slot = io.obs_slots > 1 ? (size_t)(step % io.obs_slots) : 0;
+            obs_out = io.obs + (slot * p.N + env) * p.obs_elems;
+            // pass 1 of the world observation does not depend on the transition: issue its stores now
+            if (p.obs_scope == ZS_OBS_WORLD) obs_world_template(p, e, obs_out);
+        }
         // ---- Agent.set_action (agent.py:22-25)
         for (int a = lane; a < A; a += 32) {
             int type, dx, dy;
@@ -136,9 +143,9 @@ __global__ void __launch_bounds__(ZS_WPC * 32) zs_sim_kernel(const __grid_consta
             }
             initialize_world(p, e, e.episode + 1);
         }
-        if (io.obs) {
-            const size_t slot = io.obs_slots > 1 ? (size_t)(step % io.obs_slots) : 0;
-            encode_obs(p, e, io.obs + (slot * p.N + env) * p.obs_elems);
+        if (obs_out) {
+            if (p.obs_scope == ZS_OBS_WORLD) obs_world_patch(p, e, obs_out);
+            else encode_surroundings(p, e, obs_out);
         }
         __syncwarp();
     }

@@ -18,6 +18,7 @@
 #include "../../include/zs_b200.h"
 
 #define ZS_WPC 4              // warps (= environments) per CTA
+#define ZS_MIN_CTAS 7         // 7 CTAs x 4 warps = 28 envs resident per SM: 4,096 envs fit the 148 SMs in one wave
 #define ZS_FULL 0xffffffffu
 
 // occupancy-grid byte codes

@@ -1,10 +1,7 @@
 // zs_obs.cuh — observation encoder (zombsole/gym/observation.py:36-173), lanes over cells.
 //
-// World scope: the occupancy grid is compared, four cells (one 32-bit word) at a time, with the
-// map's pristine template; where they agree (almost everywhere) the precomputed observation of
-// the static layer is forwarded as one 128-bit load + one 128-bit streaming store per lane, so a
-// warp writes 512 contiguous bytes per instruction.  Cells that differ (mobile things, dead
-// bodies, damaged or destroyed boxes/walls) take the per-cell path.
+// World scope: template stream + ordered patches (obs_world_template / obs_world_patch below).
+// Surroundings scope: per-cell encoding of the agent-centred window from the occupancy grid.
 #pragma once
 #include "zs_device.cuh"
 
@@ -39,55 +36,86 @@ __device__ __forceinline__ int channel_label(const ZsParams& p, const CellInfo& 
     return ci.label == ZS_LABEL_AGENT ? 8 + p.agent_obs_ids[ci.agent] : ci.label;
 }
 
-__device__ __forceinline__ void encode_world(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
+// World scope, pass 1: the observation of the pristine static layer (boxes, walls, objectives) is the
+// same for every env and every step, so it is streamed from the L1-resident template to the env's
+// observation row with 128-bit loads/stores — 512 contiguous bytes per warp instruction — and no
+// per-cell work.  The stores are fire-and-forget, so the step kernel issues them BEFORE the world
+// transition and lets them drain underneath the latency-bound game logic.
+__device__ __forceinline__ void obs_world_template(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
     const int lane = e.lane;
     const int cells = p.cells;
+    const bool channels = p.obs_enc == ZS_OBS_CHANNELS;
     if ((cells & 3) == 0) {
         const int n4 = cells >> 2;
-        const uint32_t* g32 = (const uint32_t*)e.grid;
-        const uint32_t* t32 = (const uint32_t*)p.tmpl_grid;
         const uint4* to4 = (const uint4*)p.tmpl_obs;
         uint4* o4 = (uint4*)obs;
-        if (p.obs_enc == ZS_OBS_SIMPLE) {
-#pragma unroll 2
+#pragma unroll 4
+        for (int i = lane; i < n4; i += 32) __stcs(o4 + i, __ldg(to4 + i));
+        if (channels) {
+#pragma unroll 4
             for (int i = lane; i < n4; i += 32) {
-                const uint32_t g = g32[i];
-                uint4 v;
-                if (g == __ldg(t32 + i)) v = __ldg(to4 + i);
-                else {
-                    v.x = encode_simple(cell_info(p, e, 4 * i, g & 255));
-                    v.y = encode_simple(cell_info(p, e, 4 * i + 1, (g >> 8) & 255));
-                    v.z = encode_simple(cell_info(p, e, 4 * i + 2, (g >> 16) & 255));
-                    v.w = encode_simple(cell_info(p, e, 4 * i + 3, g >> 24));
-                }
-                __stcs(o4 + i, v);
-            }
-        } else {
-            for (int i = lane; i < n4; i += 32) {
-                const uint32_t g = g32[i];
-                uint4 v0, v1, v2 = make_uint4(0, 0, 0, 0);
-                if (g == __ldg(t32 + i)) { v0 = __ldg(to4 + i); v1 = __ldg(to4 + n4 + i); }
-                else {
-                    CellInfo a = cell_info(p, e, 4 * i, g & 255), b = cell_info(p, e, 4 * i + 1, (g >> 8) & 255);
-                    CellInfo c = cell_info(p, e, 4 * i + 2, (g >> 16) & 255), d = cell_info(p, e, 4 * i + 3, g >> 24);
-                    v0 = make_uint4(channel_label(p, a), channel_label(p, b), channel_label(p, c), channel_label(p, d));
-                    v1 = make_uint4(a.life, b.life, c.life, d.life);
-                    v2 = make_uint4(a.weapon, b.weapon, c.weapon, d.weapon);
-                }
-                __stcs(o4 + i, v0); __stcs(o4 + n4 + i, v1); __stcs(o4 + 2 * n4 + i, v2);
+                __stcs(o4 + n4 + i, __ldg(to4 + n4 + i));
+                __stcs(o4 + 2 * n4 + i, make_uint4(0, 0, 0, 0));
             }
         }
         return;
     }
-    // maps whose cell count is not a multiple of 4 (rows of an env are then not 16-byte aligned)
+    // maps whose cell count is not a multiple of 4 (an env's row is then not 16-byte aligned)
     for (int c = lane; c < cells; c += 32) {
-        const CellInfo ci = cell_info(p, e, c, e.grid[c]);
-        if (p.obs_enc == ZS_OBS_SIMPLE) __stcs(obs + c, encode_simple(ci));
-        else {
-            __stcs(obs + c, channel_label(p, ci));
-            __stcs(obs + cells + c, ci.life);
-            __stcs(obs + 2 * cells + c, ci.weapon);
+        __stcs(obs + c, __ldg(p.tmpl_obs + c));
+        if (channels) { __stcs(obs + cells + c, __ldg(p.tmpl_obs + cells + c)); __stcs(obs + 2 * cells + c, 0); }
+    }
+}
+
+__device__ __forceinline__ void obs_store_cell(const ZsParams& p, int32_t* obs, int c, const CellInfo& ci) {
+    if (p.obs_enc == ZS_OBS_SIMPLE) obs[c] = encode_simple(ci);
+    else { obs[c] = channel_label(p, ci); obs[p.cells + c] = ci.life; obs[2 * p.cells + c] = ci.weapon; }
+}
+
+// World scope, pass 2: the cells that differ from the pristine layer are patched with scalar stores, in the
+// layering order of the reference (decorations under things, observation.py:41-42): damaged or destroyed
+// boxes/walls, then dead bodies, then the mobile things.  Each layer is separated by __syncwarp(), which
+// orders the stores of different lanes to the same address (and all of them after pass 1).
+__device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e, int32_t* obs) {
+    const int lane = e.lane;
+    const bool fresh = e.flags & 1;
+    __syncwarp();
+    const uint4* sl4 = (const uint4*)e.slife;
+    const uint4* mx4 = (const uint4*)p.static_max;
+    for (int i = lane; i < (p.Sp >> 3); i += 32) {
+        const uint4 a = sl4[i];
+        const uint4 m = __ldg(mx4 + i);
+        if (a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int life = half_of(a, q), mx = half_of(m, q);
+                if (life == mx) continue;
+                CellInfo ci;
+                ci.life = life; ci.weapon = 0; ci.agent = -1;
+                ci.label = __ldg(p.static_label + i * 8 + q);
+                if (life <= 0 && !fresh) { ci.label = 0; ci.life = 0; }  // destroyed: gone from World.things
+                obs_store_cell(p, obs, __ldg(p.static_cell + i * 8 + q), ci);
+            }
         }
+    }
+    __syncwarp();
+    for (int w = lane; w < p.dead_words; w += 32) {
+        uint32_t bits = e.dead[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            CellInfo ci;
+            ci.label = ZS_LABEL_DEAD_BODY; ci.life = 0; ci.weapon = 0; ci.agent = -1;
+            obs_store_cell(p, obs, w * 32 + b, ci);
+        }
+    }
+    __syncwarp();
+    for (int s = lane; s < p.M; s += 32) {
+        if (!(e.tm[s] & 0x80)) continue;
+        CellInfo ci;
+        ci.life = e.tl[s]; ci.weapon = e.tm[s] & 15; ci.agent = s - p.P;
+        ci.label = s < p.P ? ZS_LABEL_PLAYER : s < p.P + p.A ? ZS_LABEL_AGENT : ZS_LABEL_ZOMBIE;
+        obs_store_cell(p, obs, e.ty[s] * p.W + e.tx[s], ci);
     }
 }
 
@@ -120,6 +148,6 @@ __device__ __forceinline__ void encode_surroundings(const ZsParams& p, const Env
 }
 
 __device__ __forceinline__ void encode_obs(const ZsParams& p, const Env& e, int32_t* obs) {
-    if (p.obs_scope == ZS_OBS_WORLD) encode_world(p, e, obs);
+    if (p.obs_scope == ZS_OBS_WORLD) { obs_world_template(p, e, obs); obs_world_patch(p, e, obs); }
     else encode_surroundings(p, e, obs);
 }

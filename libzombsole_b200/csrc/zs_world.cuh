@@ -98,133 +98,29 @@ __device__ __forceinline__ void build_grid(const ZsParams& p, Env& e) {
 }
 
 // ---------------------------------------------------------------- decide phase
-// closest(self, others) with others = in-world slots [lo, hi): sorted() is stable, so ties in the
-// distance go to the thing that comes first in World.things = smallest stamp (utils.py:23-31).
-__device__ __forceinline__ int closest_slot(const Env& e, int lo, int hi, int x, int y, int skip, int& best_d2) {
-    unsigned long long best = ~0ull;
-    int arg = -1;
-    for (int j = lo; j < hi; ++j) {
-        if (!(e.tm[j] & 0x80) || j == skip) continue;
-        unsigned long long key = ((unsigned long long)(uint32_t)dist2(x, y, e.tx[j], e.ty[j]) << 32) | (uint32_t)e.ts[j];
-        if (key < best) { best = key; arg = j; }
-    }
-    best_d2 = (int)(best >> 32);
-    return arg;
-}
-
 // target id: mobile slot s -> s, static i -> M + i
 __device__ __forceinline__ int target_of_cell(const ZsParams& p, int g, int cell) {
     return g <= G_MAX_SLOT ? g - 1 : p.M + (int)__ldg(p.cell_static + cell);
 }
 
-// Zombie.next_step (zombsole/things.py:70-105)
-__device__ __forceinline__ void decide_zombie(const ZsParams& p, const Env& e, int s, bool has_humans, int& type, int& a, int& b) {
-    const int x = e.tx[s], y = e.ty[s];
-    unsigned freemask = 0, gs[4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {  // possible_moves: no bounds check (utils.py:47-52)
-        gs[d] = grid_at(p, e, x + adj_dx(d), y + adj_dy(d));
-        if (!g_is_thing(gs[d])) freemask |= 1u << d;
-    }
-    type = D_IDLE; a = 0; b = 0;
-    if (!has_humans) {
-        if (freemask) { type = D_WANDER; a = (int)freemask; }
-        return;
-    }
-    int d2;
-    const int tg = closest_slot(e, 0, p.P + p.A, x, y, -1, d2);
-    if (d2 <= 2) { type = D_ATTACK; a = tg; return; }  // distance < 1.5 (things.py:83)
-    const int gx = e.tx[tg], gy = e.ty[tg];
-    int best = -1, best_d = 0x7fffffff;
-    if (freemask) {  // closest(target, positions): first minimum in adjacency order
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            int dd = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
-            if (((freemask >> d) & 1u) && dd < best_d) { best = d; best_d = dd; }
-        }
-        type = D_MOVE; a = x + adj_dx(best); b = y + adj_dy(best);
-        return;
-    }
-    // boxed in: first Box/Wall among the adjacent cells stably sorted by distance to the target (things.py:93-99)
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        int dd = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
-        if (g_is_static(gs[d]) && dd < best_d) { best = d; best_d = dd; }
-    }
-    if (best >= 0) {
-        int cx = x + adj_dx(best), cy = y + adj_dy(best);
-        type = D_ATTACK; a = p.M + (int)__ldg(p.cell_static + cy * p.W + cx);
-    }
-}
-
-// Terminator.next_step (zombsole/players/terminator.py:9-37)
-__device__ __forceinline__ void decide_terminator(const ZsParams& p, const Env& e, int s, int& type, int& a, int& b) {
-    const int x = e.tx[s], y = e.ty[s];
-    int d2;
-    const int tg = closest_slot(e, p.P + p.A, p.M, x, y, -1, d2);
-    b = 0;
-    if (tg < 0) { type = D_HEAL; a = s; return; }
-    if (d2 > c_range2[e.tm[s] & 15]) {
-        const int gx = e.tx[tg], gy = e.ty[tg];
-        int best = 0, best_d = 0x7fffffff;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {  // closest(target, adjacent_positions(self)): out-of-bounds cells included
-            int dd = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
-            if (dd < best_d) { best = d; best_d = dd; }
-        }
-        const int bx = x + adj_dx(best), by = y + adj_dy(best);
-        const int g = grid_at(p, e, bx, by);
-        if (g_is_thing(g)) {
-            const bool is_player = g <= G_MAX_SLOT && (g - 1) < p.P + p.A;
-            type = is_player ? D_HEAL : D_ATTACK;
-            a = target_of_cell(p, g, by * p.W + bx);
-        } else { type = D_MOVE; a = bx; b = by; }
-        return;
-    }
-    type = D_ATTACK; a = tg;
-}
-
-// Agent.next_step (zombsole/players/agent.py:28-96)
-__device__ __forceinline__ void decide_agent(const ZsParams& p, const Env& e, int s, int& type, int& a, int& b) {
-    const int x = e.tx[s], y = e.ty[s];
-    const int ai = s - p.P;
-    int at = e.acts[3 * ai], dx = e.acts[3 * ai + 1], dy = e.acts[3 * ai + 2];
-    if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; dx = 0; dy = 0; }  // multiagent_env.py:129-131
-    type = D_IDLE; a = 0; b = 0;
-    int d2;
-    switch (at) {
-        case ZS_ACT_MOVE: type = D_MOVE; a = x + dx; b = y + dy; break;
-        case ZS_ACT_ATTACK_CLOSEST: {
-            int tg = closest_slot(e, p.P + p.A, p.M, x, y, -1, d2);
-            if (tg >= 0) { type = D_ATTACK; a = tg; }
-            break;
-        }
-        case ZS_ACT_ATTACK: {
-            int g = grid_at(p, e, x + dx, y + dy);
-            if (g_is_thing(g)) { type = D_ATTACK; a = target_of_cell(p, g, (y + dy) * p.W + (x + dx)); }
-            break;
-        }
-        case ZS_ACT_HEAL: {
-            if (dx == 0 && dy == 0) { type = D_HEAL; a = s; break; }
-            int g = grid_at(p, e, x + dx, y + dy);
-            // Player / Box / Wall only (agent.py:69-75)
-            if (g_is_static(g) || (g_is_thing(g) && (g - 1) < p.P + p.A)) {
-                type = D_HEAL; a = target_of_cell(p, g, (y + dy) * p.W + (x + dx));
-            }
-            break;
-        }
-        case ZS_ACT_HEAL_CLOSEST: {
-            int tg = closest_slot(e, 0, p.P + p.A, x, y, s, d2);
-            type = D_HEAL; a = tg >= 0 ? tg : s;
-            break;
-        }
-        default: break;
-    }
-}
-
-__device__ __forceinline__ unsigned long long pack_action(int actor, int type, int a, int b) {
-    return (unsigned long long)(uint32_t)actor | ((unsigned long long)(uint32_t)type << 8) |
-           ((unsigned long long)(uint16_t)(int16_t)a << 16) | ((unsigned long long)(uint16_t)(int16_t)b << 32);
+// A decided action, packed so that the sequential execute loop touches as little as possible:
+//   bits 0-7 actor | 8-10 kind | 11-26 a | 27-42 b | 43-49 range^2 | 50-56 lo | 57-62 n
+// kind: X_NOP (an action that can no longer have an effect but still takes part in the shuffle),
+// X_MOVE (a, b = destination, already known to be in bounds and one step away), X_ATTACK_M /
+// X_HEAL_M (a = mobile target slot; range is checked against current positions at execute time),
+// X_ATTACK_S / X_HEAL_S (a = static index, already known to be in range: neither end can move
+// before the actor acts).  lo/n: the draw is lo + randbelow(n).
+#define X_NOP 0
+#define X_MOVE 1
+#define X_ATTACK_M 2
+#define X_HEAL_M 3
+#define X_ATTACK_S 4
+#define X_HEAL_S 5
+__device__ __forceinline__ unsigned long long pack_action(int actor, int kind, int a, int b, int r2, int lo, int n) {
+    return (unsigned long long)(uint32_t)actor | ((unsigned long long)(uint32_t)kind << 8) |
+           ((unsigned long long)(uint16_t)(int16_t)a << 11) | ((unsigned long long)(uint16_t)(int16_t)b << 27) |
+           ((unsigned long long)(uint32_t)r2 << 43) | ((unsigned long long)(uint32_t)lo << 50) |
+           ((unsigned long long)(uint32_t)n << 57);
 }
 
 // ---------------------------------------------------------------- World.step (core.py:72-78)
@@ -239,18 +135,103 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     bool hh = false;
     for (int s = lane; s < NP; s += 32) hh |= (e.tm[s] & 0x80) != 0;
     const bool has_humans = __any_sync(ZS_FULL, hh);
-    for (int s = lane; s < p.M; s += 32) {
-        int type = D_IDLE, a = 0, b = 0;
-        if (e.tm[s] & 0x80) {
-            if (s >= NP) decide_zombie(p, e, s, has_humans, type, a, b);
-            else if (s >= p.P) decide_agent(p, e, s, type, a, b);
-            else decide_terminator(p, e, s, type, a, b);
+    bool any_wander = false;
+    for (int s0 = 0; s0 < p.M; s0 += 32) {
+        const int s = s0 + lane;
+        const bool live = s < p.M && (e.tm[s] & 0x80);
+        const int x = live ? e.tx[s] : 0, y = live ? e.ty[s] : 0;
+        const bool zombie = s >= NP, agent = !zombie && s >= p.P;
+        int at = ZS_ACT_NONE, adx = 0, ady = 0;
+        if (live && agent) {
+            at = e.acts[3 * (s - p.P)]; adx = e.acts[3 * (s - p.P) + 1]; ady = e.acts[3 * (s - p.P) + 2];
+            if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; adx = 0; ady = 0; }  // multiagent_env.py:129-131
         }
-        e.dtype[s] = (uint8_t)type; e.da[s] = (int16_t)a; e.db[s] = (int16_t)b;
+        // closest(self, others) (utils.py:23-31): zombies look at players (things.py:73-82), terminators and
+        // attack_closest at zombies (terminator.py:10-14, agent.py:41-47), heal_closest at the other players
+        // (agent.py:79-86).  sorted() is stable: ties go to the smaller dict-order stamp.  One uniform loop
+        // over the union of the lanes' candidate ranges; shared-memory reads are warp broadcasts.
+        int lo = 0x7fffffff, hi = 0, skip = -1;
+        if (live) {
+            if (zombie) { if (has_humans) { lo = 0; hi = NP; } }
+            else if (!agent || at == ZS_ACT_ATTACK_CLOSEST) { lo = NP; hi = p.M; }
+            else if (at == ZS_ACT_HEAL_CLOSEST) { lo = 0; hi = NP; skip = s; }
+        }
+        const int wlo = __reduce_min_sync(ZS_FULL, lo), whi = __reduce_max_sync(ZS_FULL, hi);
+        unsigned long long best = ~0ull;
+        int tg = -1;
+        for (int j = wlo; j < whi; ++j) {
+            const bool ok = (e.tm[j] & 0x80) && j >= lo && j < hi && j != skip;
+            const unsigned long long key = ((unsigned long long)(uint32_t)dist2(x, y, e.tx[j], e.ty[j]) << 32) | (uint32_t)e.ts[j];
+            if (ok && key < best) { best = key; tg = j; }
+        }
+        const int d2 = (int)(best >> 32);
+        int type = D_IDLE, a = 0, b = 0;
+        if (live) {
+            const int gx = tg >= 0 ? e.tx[tg] : 0, gy = tg >= 0 ? e.ty[tg] : 0;
+            if (zombie) {  // Zombie.next_step (things.py:70-105)
+                unsigned freemask = 0, gs[4];
+                int dd[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {  // possible_moves: no bounds check (utils.py:47-52)
+                    gs[d] = grid_at(p, e, x + adj_dx(d), y + adj_dy(d));
+                    dd[d] = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
+                    if (!g_is_thing(gs[d])) freemask |= 1u << d;
+                }
+                if (!has_humans) {
+                    if (freemask) { type = D_WANDER; a = (int)freemask; any_wander = true; }
+                } else if (d2 <= 2) { type = D_ATTACK; a = tg; }  // distance < 1.5 (things.py:83)
+                else {
+                    // free cells: closest(target, positions), first minimum in adjacency order; boxed in: the
+                    // first Box/Wall among the adjacent cells stably sorted by distance to the target (things.py:88-99)
+                    int bd = -1, bdist = 0x7fffffff;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const bool cand = freemask ? ((freemask >> d) & 1u) : g_is_static(gs[d]);
+                        if (cand && dd[d] < bdist) { bd = d; bdist = dd[d]; }
+                    }
+                    if (bd >= 0) {
+                        const int cx = x + adj_dx(bd), cy = y + adj_dy(bd);
+                        if (freemask) { type = D_MOVE; a = cx; b = cy; }
+                        else { type = D_ATTACK; a = p.M + (int)__ldg(p.cell_static + cy * p.W + cx); }
+                    }
+                }
+            } else if (!agent) {  // Terminator.next_step (players/terminator.py:9-37)
+                if (tg < 0) { type = D_HEAL; a = s; }
+                else if (d2 > c_range2[e.tm[s] & 15]) {
+                    int bd = 0, bdist = 0x7fffffff;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {  // closest(target, adjacent_positions(self)): out-of-bounds cells included
+                        const int q = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
+                        if (q < bdist) { bd = d; bdist = q; }
+                    }
+                    const int bx = x + adj_dx(bd), by = y + adj_dy(bd);
+                    const int g = grid_at(p, e, bx, by);
+                    if (g_is_thing(g)) {
+                        type = (g <= G_MAX_SLOT && (g - 1) < NP) ? D_HEAL : D_ATTACK;
+                        a = target_of_cell(p, g, by * p.W + bx);
+                    } else { type = D_MOVE; a = bx; b = by; }
+                } else { type = D_ATTACK; a = tg; }
+            } else {  // Agent.next_step (players/agent.py:28-96)
+                if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + adx; b = y + ady; }
+                else if (at == ZS_ACT_ATTACK_CLOSEST) { if (tg >= 0) { type = D_ATTACK; a = tg; } }
+                else if (at == ZS_ACT_HEAL_CLOSEST) { type = D_HEAL; a = tg >= 0 ? tg : s; }
+                else if (at == ZS_ACT_ATTACK || at == ZS_ACT_HEAL) {
+                    if (at == ZS_ACT_HEAL && adx == 0 && ady == 0) { type = D_HEAL; a = s; }
+                    else {
+                        const int g = grid_at(p, e, x + adx, y + ady);
+                        // attack: any thing; heal: Player / Box / Wall only (agent.py:69-75)
+                        const bool ok = at == ZS_ACT_ATTACK ? g_is_thing(g)
+                                                            : (g_is_static(g) || (g_is_thing(g) && (g - 1) < NP));
+                        if (ok) { type = at == ZS_ACT_ATTACK ? D_ATTACK : D_HEAL; a = target_of_cell(p, g, (y + ady) * p.W + (x + adx)); }
+                    }
+                }
+            }
+        }
+        if (s < p.Mp) { e.dtype[s] = (uint8_t)type; e.da[s] = (int16_t)a; e.db[s] = (int16_t)b; }
     }
     __syncwarp();
     int nd = 0;
-    if (!has_humans) {
+    if (__any_sync(ZS_FULL, any_wander)) {
         // wandering zombies draw random.choice(positions) in dict (= stamp) order (things.py:101-103)
         int mine = 0;
         for (int s = lane; s < p.M; s += 32) {
@@ -264,29 +245,45 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             e.da[s] = (int16_t)(e.tx[s] + adj_dx(d)); e.db[s] = (int16_t)(e.ty[s] + adj_dy(d));
             ++mine;
         }
-        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(ZS_FULL, mine, o);
-        nd = mine;
+        nd = __reduce_add_sync(ZS_FULL, mine);
         __syncwarp();
         for (int s = lane; s < p.M; s += 32) if (e.dtype[s] == D_WANDER) e.dtype[s] = D_MOVE;
         __syncwarp();
     }
-    // actions list in actor (dict) order: position = number of acting things with a smaller stamp
+    // actions list in actor (dict) order: position = number of acting things with a smaller stamp.
+    // Everything that cannot change before the actor acts is resolved here, in parallel.
     int cnt = 0, n_ah = 0;
-    for (int s = lane; s < p.M; s += 32) {
-        const int type = e.dtype[s];
-        if (type == D_IDLE) continue;
-        const int st = e.ts[s];
+    for (int s0 = 0; s0 < p.M; s0 += 32) {
+        const int s = s0 + lane;
+        const int type = s < p.M ? e.dtype[s] : D_IDLE;
+        const int st = s < p.M ? e.ts[s] : 0;
         int pos = 0;
         for (int j = 0; j < p.M; ++j) pos += (e.dtype[j] != D_IDLE && e.ts[j] < st);
-        e.act[pos] = pack_action(s, type, e.da[s], e.db[s]);
+        if (type == D_IDLE) continue;
+        const int a = e.da[s], b = e.db[s], x = e.tx[s], y = e.ty[s];
+        int kind = X_NOP, r2 = 0, dlo = 0, dn = 1;
+        if (type == D_MOVE) {  // in bounds and at most one step (core.py:149-153); occupancy is checked when it runs
+            if ((unsigned)a < (unsigned)p.W && (unsigned)b < (unsigned)p.H && dist2(x, y, a, b) <= 1) kind = X_MOVE;
+        } else {
+            const bool is_static = a >= p.M;
+            int mx = 100;
+            if (type == D_ATTACK) { const int w = e.tm[s] & 15; r2 = c_range2[w]; dlo = c_dmg_lo[w]; dn = c_dmg_n[w]; }
+            else {  // heal: randint(MAX_LIFE // 10, MAX_LIFE // 4) of the target's class, range 3 (core.py:194-198)
+                if (is_static) mx = max_life_of_label(__ldg(p.static_label + (a - p.M)));
+                r2 = 9; dlo = mx / 10; dn = mx / 4 - mx / 10 + 1;
+            }
+            if (is_static) {
+                const int cell = __ldg(p.static_cell + (a - p.M));
+                const int gy = cell / p.W, gx = cell - gy * p.W;
+                if (dist2(x, y, gx, gy) <= r2) kind = type == D_ATTACK ? X_ATTACK_S : X_HEAL_S;
+            } else kind = type == D_ATTACK ? X_ATTACK_M : X_HEAL_M;
+        }
+        e.act[pos] = pack_action(s, kind, kind >= X_ATTACK_S ? a - p.M : a, b, r2, dlo, dn);
         ++cnt;
-        n_ah += type != D_MOVE;
+        n_ah += kind >= X_ATTACK_M;
     }
-    for (int o = 16; o; o >>= 1) {
-        cnt += __shfl_xor_sync(ZS_FULL, cnt, o);
-        n_ah += __shfl_xor_sync(ZS_FULL, n_ah, o);
-    }
-    const int L = cnt;
+    const int L = __reduce_add_sync(ZS_FULL, cnt);
+    n_ah = __reduce_add_sync(ZS_FULL, n_ah);
     // ---- draws of this step, generated 4 per lane (counter-based: any k is available directly)
     const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
     for (int blk = lane; blk * 4 < n_need; blk += 32) {
@@ -295,61 +292,52 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         *(uint4*)(e.draws + 4 * blk) = make_uint4(o[0], o[1], o[2], o[3]);
     }
     __syncwarp();
+    // Fisher-Yates partner of every iteration (random.shuffle: for i = L-1 .. 1: j = randbelow(i + 1))
+    for (int i = 1 + lane; i < L; i += 32) e.dtype[i] = (uint8_t)below(e.draws[nd + (L - 1 - i)], i + 1);
+    __syncwarp();
 
     // ---- random.shuffle + execute_actions: order-dependent by definition, run by lane 0
-    int k = nd;
+    int k = nd + (L > 1 ? L - 1 : 0);
     if (lane == 0) {
-        for (int i = L - 1; i >= 1; --i) {  // CPython Random.shuffle
-            int j = below(e.draws[k++], i + 1);
-            unsigned long long tmp = e.act[i]; e.act[i] = e.act[j]; e.act[j] = tmp;
+        for (int i = L - 1; i >= 1; --i) {
+            const int j = e.dtype[i];
+            const unsigned long long tmp = e.act[i]; e.act[i] = e.act[j]; e.act[j] = tmp;
         }
         int n_touched = 0;
         for (int i = 0; i < L; ++i) {
             const unsigned long long pk = e.act[i];
-            const int actor = (int)(pk & 0xff), type = (int)((pk >> 8) & 0xff);
-            const int a = (int16_t)(pk >> 16), b = (int16_t)(pk >> 32);
-            const int ax = e.tx[actor], ay = e.ty[actor];
-            if (type == D_MOVE) {  // World.thing_move (core.py:140-166)
-                if ((unsigned)a < (unsigned)p.W && (unsigned)b < (unsigned)p.H) {
-                    const int c = b * p.W + a;
-                    if (!g_is_thing(e.grid[c]) && dist2(ax, ay, a, b) <= 1) {
-                        const int old = ay * p.W + ax;
-                        e.grid[old] = dead_bit(e, old) ? G_DEAD : G_EMPTY;
-                        e.grid[c] = (uint8_t)(actor + 1);
-                        e.tx[actor] = (int16_t)a; e.ty[actor] = (int16_t)b;
-                        e.ts[actor] = e.stampctr++;  // things[dest] = thing; del things[old]: goes last
-                    }
+            const int actor = (int)(pk & 0xff), kind = (int)((pk >> 8) & 7);
+            const int a = (int16_t)(pk >> 11), b = (int16_t)(pk >> 27);
+            if (kind == X_NOP) continue;
+            if (kind == X_MOVE) {  // World.thing_move (core.py:140-166)
+                const int c = b * p.W + a;
+                if (!g_is_thing(e.grid[c])) {
+                    const int old = e.ty[actor] * p.W + e.tx[actor];
+                    e.grid[old] = dead_bit(e, old) ? G_DEAD : G_EMPTY;
+                    e.grid[c] = (uint8_t)(actor + 1);
+                    e.tx[actor] = (int16_t)a; e.ty[actor] = (int16_t)b;
+                    e.ts[actor] = e.stampctr++;  // things[dest] = thing; del things[old]: goes last
                 }
                 continue;
             }
-            int gx, gy, cell = 0;
-            const bool is_static = a >= p.M;
-            if (is_static) {
-                cell = __ldg(p.static_cell + (a - p.M));
-                gy = cell / p.W; gx = cell - gy * p.W;
-            } else { gx = e.tx[a]; gy = e.ty[a]; }
-            const int d2 = dist2(ax, ay, gx, gy);
-            if (type == D_ATTACK) {  // World.thing_attack (core.py:168-184)
-                const int w = e.tm[actor] & 15;
-                if (d2 > c_range2[w]) continue;
-                const int dmg = c_dmg_lo[w] + below(e.draws[k++], c_dmg_n[w]);
-                if (is_static) {
-                    e.slife[a - p.M] = (int16_t)(e.slife[a - p.M] - dmg);
-                    e.grid[cell] = G_STATIC_DMG;
-                    e.list[n_touched++] = (uint16_t)(a - p.M);
-                } else e.tl[a] = (int16_t)(e.tl[a] - dmg);
-            } else {  // World.thing_heal (core.py:186-202)
-                if (d2 > 9) continue;
-                const int mx = is_static ? max_life_of_label(__ldg(p.static_label + (a - p.M))) : 100;
-                const int heal = mx / 10 + below(e.draws[k++], mx / 4 - mx / 10 + 1);
-                if (is_static) {
-                    const int nl = e.slife[a - p.M] + heal;
-                    e.slife[a - p.M] = (int16_t)(nl < mx ? nl : mx);
-                    e.grid[cell] = G_STATIC_DMG;
+            const int r2 = (int)((pk >> 43) & 127), dlo = (int)((pk >> 50) & 127), dn = (int)((pk >> 57) & 63);
+            if (kind <= X_HEAL_M) {  // mobile target: distance between CURRENT positions (core.py:176,194)
+                if (dist2(e.tx[actor], e.ty[actor], e.tx[a], e.ty[a]) > r2) continue;
+                const int amount = dlo + below(e.draws[k++], dn);
+                if (kind == X_ATTACK_M) e.tl[a] = (int16_t)(e.tl[a] - amount);
+                else { const int nl = e.tl[a] + amount; e.tl[a] = (int16_t)(nl < 100 ? nl : 100); }
+            } else {
+                const int amount = dlo + below(e.draws[k++], dn);
+                const int cell = __ldg(p.static_cell + a);
+                if (kind == X_ATTACK_S) {
+                    e.slife[a] = (int16_t)(e.slife[a] - amount);
+                    e.list[n_touched++] = (uint16_t)a;
                 } else {
-                    const int nl = e.tl[a] + heal;
-                    e.tl[a] = (int16_t)(nl < mx ? nl : mx);
+                    const int mx = dlo == 1 ? 10 : 200;  // MAX_LIFE // 10 is 1 for a Box, 20 for a Wall
+                    const int nl = e.slife[a] + amount;
+                    e.slife[a] = (int16_t)(nl < mx ? nl : mx);
                 }
+                e.grid[cell] = G_STATIC_DMG;
             }
         }
         // clean_dead_things for boxes/walls hit this step (core.py:121-138); the full scan below
@@ -388,12 +376,8 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             nd_z += s >= NP;
         }
     }
-    for (int o = 16; o; o >>= 1) {
-        nd_all += __shfl_xor_sync(ZS_FULL, nd_all, o);
-        nd_z += __shfl_xor_sync(ZS_FULL, nd_z, o);
-    }
-    e.deaths += nd_all;
-    e.zd += nd_z;
+    e.deaths += __reduce_add_sync(ZS_FULL, nd_all);
+    e.zd += __reduce_add_sync(ZS_FULL, nd_z);
     __syncwarp();
     return k;
 }
@@ -473,7 +457,7 @@ __device__ __forceinline__ int spawn_zombies(const ZsParams& p, Env& e, uint32_t
 
 // Game.__initialize_world__ (game.py:151-169) + reward_tracker.reset (reward.py:26-28).
 // Returns the number of draws consumed.
-__device__ __forceinline__ int initialize_world(const ZsParams& p, Env& e, int episode) {
+__device__ __noinline__ int initialize_world(const ZsParams& p, Env& e, int episode) {
     const int lane = e.lane;
     const int NP = p.P + p.A;
     e.episode = episode;
