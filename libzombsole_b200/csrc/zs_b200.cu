@@ -39,21 +39,23 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int env = blockIdx.x * ZS_WPC + wid;
     if (env >= p.N) return;
+    unsigned char* base = smem + (size_t)wid * p.smem_per_warp;
     Env e;
-    env_bind(p, e, smem + (size_t)wid * p.smem_per_warp, env, lane);
+    env_bind(p, e, base, env, lane);
 
     if (MODE == MODE_RESET) {
         if (io.env_mask && !io.env_mask[env]) return;
         // slots keep their last position/life until re-placed; bring them in so the store is complete
         load_state(p, e);
-        const int k = initialize_world(p, e, e.episode + 1);
+        const int k = initialize_world(p, base, env, lane, e.episode + 1, e.flags);
+        scalars_from_smem(e);
         if (io.draws && lane == 0) io.draws[env] = k;
         if (io.obs) encode_obs(p, e, io.obs + (size_t)env * p.obs_elems);
         store_state(p, e);
         return;
     }
     load_state(p, e);
-    build_grid(p, e);
+    build_grid(p, base, env, lane, e.flags);
     if (MODE == MODE_ENCODE) {
         encode_obs(p, e, io.obs + (size_t)env * p.obs_elems);
         return;
@@ -61,50 +63,63 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
 
     const int A = p.A, NP = p.P + p.A;
     const int R = p.obs_per_agent ? A : 1;
+    const bool world_obs = p.obs_scope == ZS_OBS_WORLD;
+    // this lane's agent action for the coming step, fetched one step ahead (Agent.set_action, agent.py:22-25)
+    int at = ZS_ACT_NONE, adx = 0, ady = 0;
+    auto fetch_action = [&](int step) {
+        if (lane >= A) return;
+        const size_t sn = (size_t)step * p.N + env;
+        if (io.actions == nullptr) discrete_to_action(p, synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), lane), at, adx, ady);
+        else if (io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, io.actions[sn * A + lane], at, adx, ady);
+        else { const int32_t* q = io.actions + (sn * A + lane) * 3; at = q[0]; adx = q[1]; ady = q[2]; }
+    };
+    fetch_action(0);
+    int slot = 0;
+#pragma unroll 1
     for (int step = 0; step < io.n_steps; ++step) {
         const size_t sn = (size_t)step * p.N + env;
         int32_t* obs_out = nullptr;
         if (io.obs) {
-            const size_t slot = io.obs_slots > 1 ? (size_t)(step % io.obs_slots) : 0;
-            obs_out = io.obs + (slot * p.N + env) * p.obs_elems;
+            obs_out = io.obs + ((size_t)slot * p.N + env) * p.obs_elems;
+            if (++slot >= io.obs_slots) slot = 0;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
-            if (p.obs_scope == ZS_OBS_WORLD) obs_world_template(p, e, obs_out);
+            if (world_obs) obs_world_template(p, e, obs_out);
         }
-        // ---- Agent.set_action (agent.py:22-25)
-        for (int a = lane; a < A; a += 32) {
-            int type, dx, dy;
-            if (io.actions == nullptr) discrete_to_action(p, synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), a), type, dx, dy);
-            else if (io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, io.actions[sn * A + a], type, dx, dy);
-            else { const int32_t* q = io.actions + (sn * A + a) * 3; type = q[0]; dx = q[1]; dy = q[2]; }
-            e.acts[3 * a] = type; e.acts[3 * a + 1] = dx; e.acts[3 * a + 2] = dy;
-        }
-        unsigned alive_before = 0;  // agents alive before the step: keys of the multi-agent dicts
-        for (int a = 0; a < A; ++a) alive_before |= (e.tl[p.P + a] > 0 ? 1u : 0u) << a;
+        if (lane < A) { e.acts[3 * lane] = at; e.acts[3 * lane + 1] = adx; e.acts[3 * lane + 2] = ady; }
+        // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
+        const unsigned alive_before = __ballot_sync(ZS_FULL, lane < A && e.tl[p.P + (lane < A ? lane : 0)] > 0);
+        const int zd_before = e.prev_zd;
+        const int life_before = lane < A ? e.prev[lane] : 0;
         __syncwarp();
+        if (step + 1 < io.n_steps) fetch_action(step + 1);
 
         int k = world_step(p, e);
         e.ep_steps += 1;
 
-        // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order
-        double rew = 0.0;  // lane a holds agent a's reward (single-agent: lane 0)
+        // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order.
+        // Lane a holds agent a's reward; a tracker whose inputs did not change yields exactly +0.0.
+        const int life_now = lane < A ? e.tl[p.P + lane] : 0;
+        double rew = 0.0;
         if (!p.obs_per_agent) {
-            int sum_prev = 0, sum_new = 0;
-            for (int a = 0; a < A; ++a) { sum_prev += e.prev[a]; sum_new += e.tl[p.P + a]; }
-            rew = __dsub_rn(total_reward(e.zd, sum_new), total_reward(e.prev_zd, sum_prev));
-        } else if (lane < A) {
-            rew = __dsub_rn(total_reward(e.zd, e.tl[p.P + lane]), total_reward(e.prev_zd, e.prev[lane]));
+            const int sum_prev = __reduce_add_sync(ZS_FULL, life_before), sum_new = __reduce_add_sync(ZS_FULL, life_now);
+            if (sum_prev != sum_new || zd_before != e.zd)
+                rew = __dsub_rn(total_reward(e.zd, sum_new), total_reward(zd_before, sum_prev));
+        } else if (lane < A && (life_before != life_now || zd_before != e.zd)) {
+            rew = __dsub_rn(total_reward(e.zd, life_now), total_reward(zd_before, life_before));
         }
-        __syncwarp();
-        for (int a = lane; a < A; a += 32) e.prev[a] = e.tl[p.P + a];
+        if (lane < A) e.prev[lane] = (int16_t)life_now;
         e.prev_zd = e.zd;
         __syncwarp();
 
         // ---- Game.spawn_zombies_to_maintain_minimum (game.py:196-201)
         if (p.minimum_zombies > 0) {
             int zc = 0;
-            for (int s = NP + lane; s < p.M; s += 32) zc += (e.tm[s] & 0x80) != 0;
-            for (int o = 16; o; o >>= 1) zc += __shfl_xor_sync(ZS_FULL, zc, o);
-            if (zc < p.minimum_zombies) k = spawn_zombies(p, e, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc);
+#pragma unroll 1
+            for (int s0 = NP; s0 < p.M; s0 += 32) zc += __popc(__ballot_sync(ZS_FULL, s0 + lane < p.M && (e.tm[s0 + lane] & 0x80)));
+            if (zc < p.minimum_zombies) {
+                k = spawn_zombies(p, base, env, lane, e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.stampctr);
+                e.stampctr = e.scal[ZS_S_STAMP_COUNTER];
+            }
         }
 
         // ---- rules and end reward (gym_env.py:130-141, multiagent_env.py:143-162)
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
             if (done || trunc) rew = __dadd_rn(rew, end_reward);
         } else if (lane < A) {
             if (!((alive_before >> lane) & 1u)) rew = 0.0;
-            else if (e.tl[p.P + lane] > 0) rew = __dadd_rn(rew, end_reward);
+            else if (life_now > 0) rew = __dadd_rn(rew, end_reward);
         }
         if (p.max_steps > 0 && e.ep_steps >= p.max_steps) trunc = true;  // gymnasium TimeLimit
 
@@ -141,10 +156,11 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
                 atomicAdd(p.stats + 2, (unsigned long long)e.ep_steps);
                 atomicAdd(p.stats + 3, (unsigned long long)e.zd);
             }
-            initialize_world(p, e, e.episode + 1);
+            initialize_world(p, base, env, lane, e.episode + 1, e.flags);
+            scalars_from_smem(e);
         }
         if (obs_out) {
-            if (p.obs_scope == ZS_OBS_WORLD) obs_world_patch(p, e, obs_out);
+            if (world_obs) obs_world_patch(p, e, obs_out);
             else encode_surroundings(p, e, obs_out);
         }
         __syncwarp();
@@ -227,7 +243,8 @@ static int validate(const ZsConfig* cfg, const ZsMap* map) {
     if (cfg->initial_zombies < 0 || cfg->minimum_zombies < 0) return fail("negative zombie count");
     int Z = cfg->initial_zombies > cfg->minimum_zombies ? cfg->initial_zombies : cfg->minimum_zombies;
     if (cfg->n_bots + cfg->n_agents + Z > ZS_MAX_SLOTS) return fail("too many things per env (ZS_MAX_SLOTS)");
-    if (map->width < 1 || map->height < 1 || (int64_t)map->width * map->height > 65535) return fail("map size out of range");
+    if (map->width < 1 || map->height < 1 || map->width > 8192 || map->height > 8192 ||
+        (int64_t)map->width * map->height > 65535) return fail("map size out of range");
     if (map->n_statics < 0 || map->n_statics > 30000) return fail("too many statics");
     if (cfg->obs_scope == ZS_OBS_SURROUNDINGS) {
         if (cfg->surroundings_width <= 1 || cfg->surroundings_width % 2 == 0) return fail("surroundings width must be an odd number greater than 1");
@@ -370,6 +387,10 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     p.off_list = take(p.Mp * 2);
     p.off_prev = take(p.Ap * 2);
     p.off_acts = take(p.A * 12);
+    p.off_sl = take(p.Sp * 2);
+    p.off_cq = take(p.Mp * 8);
+    p.off_ats = take(p.Mp * 4);
+    p.off_scal = take(8 * 4);
     p.smem_per_warp = off;
     const int smem = p.smem_per_warp * ZS_WPC;
     if (smem > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }

@@ -15,7 +15,7 @@ __device__ __forceinline__ CellInfo cell_info(const ZsParams& p, const Env& e, i
     else if (g > G_MAX_SLOT) {
         const int i = __ldg(p.cell_static + c);
         ci.label = __ldg(p.static_label + i);
-        ci.life = e.slife[i];
+        ci.life = e.sl[i];
     } else {
         const int s = g - 1;
         ci.life = e.tl[s];
@@ -78,27 +78,30 @@ __device__ __forceinline__ void obs_store_cell(const ZsParams& p, int32_t* obs, 
 // orders the stores of different lanes to the same address (and all of them after pass 1).
 __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e, int32_t* obs) {
     const int lane = e.lane;
-    const bool fresh = e.flags & 1;
+    const bool fresh = e.flags & FL_FRESH;
     __syncwarp();
-    const uint4* sl4 = (const uint4*)e.slife;
-    const uint4* mx4 = (const uint4*)p.static_max;
-    for (int i = lane; i < (p.Sp >> 3); i += 32) {
-        const uint4 a = sl4[i];
-        const uint4 m = __ldg(mx4 + i);
-        if (a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int life = half_of(a, q), mx = half_of(m, q);
-                if (life == mx) continue;
-                CellInfo ci;
-                ci.life = life; ci.weapon = 0; ci.agent = -1;
-                ci.label = __ldg(p.static_label + i * 8 + q);
-                if (life <= 0 && !fresh) { ci.label = 0; ci.life = 0; }  // destroyed: gone from World.things
-                obs_store_cell(p, obs, __ldg(p.static_cell + i * 8 + q), ci);
+    if (e.flags & FL_DMG) {  // launch-lifetime flag: no box/wall differs from its MAX_LIFE otherwise
+        const uint4* mx4 = (const uint4*)p.static_max;
+#pragma unroll 1
+        for (int i = lane; i < (p.Sp >> 3); i += 32) {
+            const uint4 a = ((const uint4*)e.sl)[i];
+            const uint4 m = __ldg(mx4 + i);
+            if (a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w) {
+#pragma unroll 1
+                for (int q = 0; q < 8; ++q) {
+                    const int life = e.sl[i * 8 + q];
+                    if (life == __ldg(p.static_max + i * 8 + q)) continue;
+                    CellInfo ci;
+                    ci.life = life; ci.weapon = 0; ci.agent = -1;
+                    ci.label = __ldg(p.static_label + i * 8 + q);
+                    if (life <= 0 && !fresh) { ci.label = 0; ci.life = 0; }  // destroyed: gone from World.things
+                    obs_store_cell(p, obs, __ldg(p.static_cell + i * 8 + q), ci);
+                }
             }
         }
+        __syncwarp();
     }
-    __syncwarp();
+#pragma unroll 1
     for (int w = lane; w < p.dead_words; w += 32) {
         uint32_t bits = e.dead[w];
         while (bits) {
@@ -110,6 +113,7 @@ __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e,
         }
     }
     __syncwarp();
+#pragma unroll 1
     for (int s = lane; s < p.M; s += 32) {
         if (!(e.tm[s] & 0x80)) continue;
         CellInfo ci;

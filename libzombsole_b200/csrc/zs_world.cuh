@@ -13,45 +13,31 @@ __device__ __forceinline__ void env_bind(const ZsParams& p, Env& e, unsigned cha
     e.act = (unsigned long long*)(base + p.off_act); e.draws = (uint32_t*)(base + p.off_draws);
     e.cand = (uint16_t*)(base + p.off_cand); e.list = (uint16_t*)(base + p.off_list);
     e.prev = (int16_t*)(base + p.off_prev); e.acts = (int32_t*)(base + p.off_acts);
+    e.sl = (int16_t*)(base + p.off_sl); e.cq = (uint2*)(base + p.off_cq); e.ats = (int32_t*)(base + p.off_ats);
+    e.scal = (int32_t*)(base + p.off_scal);
     e.env = env; e.env_global = p.env_base + (uint32_t)env; e.lane = lane;
-    e.slife = p.SLIFE + (size_t)env * p.Sp;
 }
 
-__device__ __forceinline__ void load_scalars(const ZsParams& p, Env& e) {
-    int sc = e.lane < 8 ? p.SCAL[(size_t)e.env * 8 + e.lane] : 0;
+__device__ __forceinline__ void scalars_from_lane(Env& e, int sc) {
     e.t = __shfl_sync(ZS_FULL, sc, ZS_S_T); e.episode = __shfl_sync(ZS_FULL, sc, ZS_S_EPISODE);
     e.deaths = __shfl_sync(ZS_FULL, sc, ZS_S_DEATHS); e.zd = __shfl_sync(ZS_FULL, sc, ZS_S_ZOMBIE_DEATHS);
     e.stampctr = __shfl_sync(ZS_FULL, sc, ZS_S_STAMP_COUNTER); e.flags = __shfl_sync(ZS_FULL, sc, ZS_S_FLAGS);
     e.prev_zd = __shfl_sync(ZS_FULL, sc, ZS_S_PREV_ZOMBIE_DEATHS); e.ep_steps = __shfl_sync(ZS_FULL, sc, ZS_S_EPISODE_STEPS);
 }
-
-__device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
-    const size_t row = (size_t)e.env * p.Mp;
-    for (int s = e.lane; s < p.Mp; s += 32) {
-        e.tx[s] = p.X[row + s]; e.ty[s] = p.Y[row + s]; e.tl[s] = p.LIFE[row + s];
-        e.ts[s] = p.STAMP[row + s]; e.tm[s] = p.META[row + s];
-    }
-    for (int w = e.lane; w < p.dead_words; w += 32) e.dead[w] = p.DEAD[(size_t)e.env * p.dead_words + w];
-    for (int a = e.lane; a < p.Ap; a += 32) e.prev[a] = p.PREV[(size_t)e.env * p.Ap + a];
-    load_scalars(p, e);
+__device__ __forceinline__ int scalar_of_lane(const Env& e) {
+    const int l = e.lane;
+    return l == ZS_S_T ? e.t : l == ZS_S_EPISODE ? e.episode : l == ZS_S_DEATHS ? e.deaths
+         : l == ZS_S_ZOMBIE_DEATHS ? e.zd : l == ZS_S_STAMP_COUNTER ? e.stampctr
+         : l == ZS_S_FLAGS ? e.flags : l == ZS_S_PREV_ZOMBIE_DEATHS ? e.prev_zd : e.ep_steps;
+}
+// hand-off through shared memory around the out-of-line functions (keeps Env in registers)
+__device__ __forceinline__ void scalars_to_smem(Env& e) {
+    if (e.lane < 8) e.scal[e.lane] = scalar_of_lane(e);
     __syncwarp();
 }
-
-__device__ __forceinline__ void store_state(const ZsParams& p, Env& e) {
+__device__ __forceinline__ void scalars_from_smem(Env& e) {
     __syncwarp();
-    const size_t row = (size_t)e.env * p.Mp;
-    for (int s = e.lane; s < p.Mp; s += 32) {
-        p.X[row + s] = e.tx[s]; p.Y[row + s] = e.ty[s]; p.LIFE[row + s] = e.tl[s];
-        p.STAMP[row + s] = e.ts[s]; p.META[row + s] = e.tm[s];
-    }
-    for (int w = e.lane; w < p.dead_words; w += 32) p.DEAD[(size_t)e.env * p.dead_words + w] = e.dead[w];
-    for (int a = e.lane; a < p.Ap; a += 32) p.PREV[(size_t)e.env * p.Ap + a] = e.prev[a];
-    if (e.lane < 8) {
-        int v = e.lane == ZS_S_T ? e.t : e.lane == ZS_S_EPISODE ? e.episode : e.lane == ZS_S_DEATHS ? e.deaths
-              : e.lane == ZS_S_ZOMBIE_DEATHS ? e.zd : e.lane == ZS_S_STAMP_COUNTER ? e.stampctr
-              : e.lane == ZS_S_FLAGS ? e.flags : e.lane == ZS_S_PREV_ZOMBIE_DEATHS ? e.prev_zd : e.ep_steps;
-        p.SCAL[(size_t)e.env * 8 + e.lane] = v;
-    }
+    scalars_from_lane(e, e.lane < 8 ? e.scal[e.lane] : 0);
 }
 
 __device__ __forceinline__ int16_t half_of(const uint4& v, int q) {
@@ -59,40 +45,97 @@ __device__ __forceinline__ int16_t half_of(const uint4& v, int q) {
     return (int16_t)((q & 1) ? (w >> 16) : (w & 0xffffu));
 }
 
-// Rebuild the occupancy grid from the compact state.  `fresh` = first step after a world init:
+__device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
+    const size_t row = (size_t)e.env * p.Mp;
+#pragma unroll 1
+    for (int s = e.lane; s < p.Mp; s += 32) {
+        e.tx[s] = p.X[row + s]; e.ty[s] = p.Y[row + s]; e.tl[s] = p.LIFE[row + s];
+        e.ts[s] = p.STAMP[row + s]; e.tm[s] = p.META[row + s];
+    }
+#pragma unroll 1
+    for (int w = e.lane; w < p.dead_words; w += 32) e.dead[w] = p.DEAD[(size_t)e.env * p.dead_words + w];
+#pragma unroll 1
+    for (int a = e.lane; a < p.Ap; a += 32) e.prev[a] = p.PREV[(size_t)e.env * p.Ap + a];
+    // static lives: staged in shared memory for the launch; note whether any differs from its MAX_LIFE
+    const uint4* sl4 = (const uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
+    const uint4* mx4 = (const uint4*)p.static_max;
+    bool dmg = false;
+#pragma unroll 1
+    for (int i = e.lane; i < (p.Sp >> 3); i += 32) {
+        const uint4 a = sl4[i];
+        const uint4 m = __ldg(mx4 + i);
+        ((uint4*)e.sl)[i] = a;
+        dmg |= a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w;
+    }
+    scalars_from_lane(e, e.lane < 8 ? p.SCAL[(size_t)e.env * 8 + e.lane] : 0);
+    e.flags = (e.flags & FL_FRESH) | (__any_sync(ZS_FULL, dmg) ? FL_DMG : 0);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void store_state(const ZsParams& p, Env& e) {
+    __syncwarp();
+    const size_t row = (size_t)e.env * p.Mp;
+#pragma unroll 1
+    for (int s = e.lane; s < p.Mp; s += 32) {
+        p.X[row + s] = e.tx[s]; p.Y[row + s] = e.ty[s]; p.LIFE[row + s] = e.tl[s];
+        p.STAMP[row + s] = e.ts[s]; p.META[row + s] = e.tm[s];
+    }
+#pragma unroll 1
+    for (int w = e.lane; w < p.dead_words; w += 32) p.DEAD[(size_t)e.env * p.dead_words + w] = e.dead[w];
+#pragma unroll 1
+    for (int a = e.lane; a < p.Ap; a += 32) p.PREV[(size_t)e.env * p.Ap + a] = e.prev[a];
+    if (e.flags & FL_SL_DIRTY) {
+        uint4* sl4 = (uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
+#pragma unroll 1
+        for (int i = e.lane; i < (p.Sp >> 3); i += 32) sl4[i] = ((const uint4*)e.sl)[i];
+    }
+    const int keep = e.flags;
+    e.flags &= FL_FRESH;
+    if (e.lane < 8) p.SCAL[(size_t)e.env * 8 + e.lane] = scalar_of_lane(e);
+    e.flags = keep;
+}
+
+// Rebuild the occupancy grid from the compact state.  FL_FRESH = first step after a world init:
 // boxes/walls whose life is already <= 0 are still in World.things (game.py:154-155) until the
 // first clean_dead_things.
-__device__ __forceinline__ void build_grid(const ZsParams& p, Env& e) {
-    const bool fresh = e.flags & 1;
+__device__ __noinline__ void build_grid(const ZsParams& p, unsigned char* base, int env, int lane, int flags) {
+    Env e;
+    env_bind(p, e, base, env, lane);
+    const bool fresh = flags & FL_FRESH;
     const uint4* tg = (const uint4*)p.tmpl_grid;
     uint4* g4 = (uint4*)e.grid;
-    for (int i = e.lane; i < (p.cells_pad >> 4); i += 32) g4[i] = __ldg(tg + i);
+#pragma unroll 1
+    for (int i = lane; i < (p.cells_pad >> 4); i += 32) g4[i] = __ldg(tg + i);
     __syncwarp();
-    const uint4* sl4 = (const uint4*)e.slife;
-    const uint4* mx4 = (const uint4*)p.static_max;
-    for (int i = e.lane; i < (p.Sp >> 3); i += 32) {
-        uint4 a = sl4[i];
-        uint4 m = __ldg(mx4 + i);
-        if (a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                int life = half_of(a, q), mx = half_of(m, q);
-                if (life != mx) e.grid[__ldg(p.static_cell + i * 8 + q)] = (life <= 0 && !fresh) ? G_EMPTY : G_STATIC_DMG;
+    if (flags & FL_DMG) {
+        const uint4* mx4 = (const uint4*)p.static_max;
+#pragma unroll 1
+        for (int i = lane; i < (p.Sp >> 3); i += 32) {
+            const uint4 a = ((const uint4*)e.sl)[i];
+            const uint4 m = __ldg(mx4 + i);
+            if (a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w) {
+#pragma unroll 1
+                for (int q = 0; q < 8; ++q) {
+                    const int life = e.sl[i * 8 + q], mx = __ldg(p.static_max + i * 8 + q);
+                    if (life != mx) e.grid[__ldg(p.static_cell + i * 8 + q)] = (life <= 0 && !fresh) ? G_EMPTY : G_STATIC_DMG;
+                }
             }
         }
+        __syncwarp();
     }
-    __syncwarp();
-    for (int w = e.lane; w < p.dead_words; w += 32) {
+#pragma unroll 1
+    for (int w = lane; w < p.dead_words; w += 32) {
         uint32_t bits = e.dead[w];
         while (bits) {
-            int b = __ffs(bits) - 1;
+            const int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            int c = w * 32 + b;
+            const int c = w * 32 + b;
             if (e.grid[c] == G_EMPTY) e.grid[c] = G_DEAD;
         }
     }
     __syncwarp();
-    for (int s = e.lane; s < p.M; s += 32)
+#pragma unroll 1
+    for (int s = lane; s < p.M; s += 32)
         if (e.tm[s] & 0x80) e.grid[e.ty[s] * p.W + e.tx[s]] = (uint8_t)(s + 1);
     __syncwarp();
 }
@@ -131,11 +174,24 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     e.t += 1;
     const uint32_t t_word = (uint32_t)(e.t + 1);
 
+    // ---- per-step candidate table: position (a far-away sentinel when not in the world) and stamp
+    unsigned humans = 0;
+#pragma unroll 1
+    for (int s0 = 0; s0 < p.Mp; s0 += 32) {
+        const int s = s0 + lane;
+        if (s < p.Mp) {
+            const bool live = (e.tm[s] & 0x80) != 0;  // padding slots are never in the world
+            e.cq[s] = live ? make_uint2((uint32_t)(uint16_t)e.tx[s] | ((uint32_t)(uint16_t)e.ty[s] << 16), (uint32_t)e.ts[s])
+                           : make_uint2(CQ_ABSENT, 0x7fffffffu);
+            humans |= live && s < NP;
+        }
+    }
+    const bool has_humans = __any_sync(ZS_FULL, humans);
+    __syncwarp();
+
     // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
-    bool hh = false;
-    for (int s = lane; s < NP; s += 32) hh |= (e.tm[s] & 0x80) != 0;
-    const bool has_humans = __any_sync(ZS_FULL, hh);
     bool any_wander = false;
+#pragma unroll 1
     for (int s0 = 0; s0 < p.M; s0 += 32) {
         const int s = s0 + lane;
         const bool live = s < p.M && (e.tm[s] & 0x80);
@@ -149,7 +205,7 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         // closest(self, others) (utils.py:23-31): zombies look at players (things.py:73-82), terminators and
         // attack_closest at zombies (terminator.py:10-14, agent.py:41-47), heal_closest at the other players
         // (agent.py:79-86).  sorted() is stable: ties go to the smaller dict-order stamp.  One uniform loop
-        // over the union of the lanes' candidate ranges; shared-memory reads are warp broadcasts.
+        // over the union of the lanes' candidate ranges; every shared-memory read is a warp broadcast.
         int lo = 0x7fffffff, hi = 0, skip = -1;
         if (live) {
             if (zombie) { if (has_humans) { lo = 0; hi = NP; } }
@@ -157,14 +213,18 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             else if (at == ZS_ACT_HEAL_CLOSEST) { lo = 0; hi = NP; skip = s; }
         }
         const int wlo = __reduce_min_sync(ZS_FULL, lo), whi = __reduce_max_sync(ZS_FULL, hi);
-        unsigned long long best = ~0ull;
-        int tg = -1;
+        const unsigned span = (unsigned)(hi - lo);
+        int bd = 0x7fffffff, bst = 0x7fffffff, tg = -1;
+#pragma unroll 2
         for (int j = wlo; j < whi; ++j) {
-            const bool ok = (e.tm[j] & 0x80) && j >= lo && j < hi && j != skip;
-            const unsigned long long key = ((unsigned long long)(uint32_t)dist2(x, y, e.tx[j], e.ty[j]) << 32) | (uint32_t)e.ts[j];
-            if (ok && key < best) { best = key; tg = j; }
+            const uint2 q = e.cq[j];
+            const int dx = x - (int)(int16_t)(q.x & 0xffffu), dy = y - (int)(int16_t)(q.x >> 16);
+            const int d = dx * dx + dy * dy;
+            const bool in = (unsigned)(j - lo) < span && j != skip;
+            if (in && (d < bd || (d == bd && (int)q.y < bst))) { bd = d; bst = (int)q.y; tg = j; }
         }
-        const int d2 = (int)(best >> 32);
+        if (bd >= CQ_FAR) tg = -1;
+        const int d2 = bd;
         int type = D_IDLE, a = 0, b = 0;
         if (live) {
             const int gx = tg >= 0 ? e.tx[tg] : 0, gy = tg >= 0 ? e.ty[tg] : 0;
@@ -183,14 +243,14 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                 else {
                     // free cells: closest(target, positions), first minimum in adjacency order; boxed in: the
                     // first Box/Wall among the adjacent cells stably sorted by distance to the target (things.py:88-99)
-                    int bd = -1, bdist = 0x7fffffff;
+                    int bdir = -1, bdist = 0x7fffffff;
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
                         const bool cand = freemask ? ((freemask >> d) & 1u) : g_is_static(gs[d]);
-                        if (cand && dd[d] < bdist) { bd = d; bdist = dd[d]; }
+                        if (cand && dd[d] < bdist) { bdir = d; bdist = dd[d]; }
                     }
-                    if (bd >= 0) {
-                        const int cx = x + adj_dx(bd), cy = y + adj_dy(bd);
+                    if (bdir >= 0) {
+                        const int cx = x + adj_dx(bdir), cy = y + adj_dy(bdir);
                         if (freemask) { type = D_MOVE; a = cx; b = cy; }
                         else { type = D_ATTACK; a = p.M + (int)__ldg(p.cell_static + cy * p.W + cx); }
                     }
@@ -198,13 +258,13 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             } else if (!agent) {  // Terminator.next_step (players/terminator.py:9-37)
                 if (tg < 0) { type = D_HEAL; a = s; }
                 else if (d2 > c_range2[e.tm[s] & 15]) {
-                    int bd = 0, bdist = 0x7fffffff;
+                    int bdir = 0, bdist = 0x7fffffff;
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {  // closest(target, adjacent_positions(self)): out-of-bounds cells included
                         const int q = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
-                        if (q < bdist) { bd = d; bdist = q; }
+                        if (q < bdist) { bdir = d; bdist = q; }
                     }
-                    const int bx = x + adj_dx(bd), by = y + adj_dy(bd);
+                    const int bx = x + adj_dx(bdir), by = y + adj_dy(bdir);
                     const int g = grid_at(p, e, bx, by);
                     if (g_is_thing(g)) {
                         type = (g <= G_MAX_SLOT && (g - 1) < NP) ? D_HEAL : D_ATTACK;
@@ -227,13 +287,17 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                 }
             }
         }
-        if (s < p.Mp) { e.dtype[s] = (uint8_t)type; e.da[s] = (int16_t)a; e.db[s] = (int16_t)b; }
+        if (s < p.Mp) {
+            e.dtype[s] = (uint8_t)type; e.da[s] = (int16_t)a; e.db[s] = (int16_t)b;
+            e.ats[s] = (type != D_IDLE && type != D_WANDER) ? e.ts[s] : 0x7fffffff;
+        }
     }
     __syncwarp();
     int nd = 0;
     if (__any_sync(ZS_FULL, any_wander)) {
         // wandering zombies draw random.choice(positions) in dict (= stamp) order (things.py:101-103)
         int mine = 0;
+#pragma unroll 1
         for (int s = lane; s < p.M; s += 32) {
             if (e.dtype[s] != D_WANDER) continue;
             int rank = 0;
@@ -247,18 +311,21 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         }
         nd = __reduce_add_sync(ZS_FULL, mine);
         __syncwarp();
-        for (int s = lane; s < p.M; s += 32) if (e.dtype[s] == D_WANDER) e.dtype[s] = D_MOVE;
+#pragma unroll 1
+        for (int s = lane; s < p.M; s += 32) if (e.dtype[s] == D_WANDER) { e.dtype[s] = D_MOVE; e.ats[s] = e.ts[s]; }
         __syncwarp();
     }
     // actions list in actor (dict) order: position = number of acting things with a smaller stamp.
     // Everything that cannot change before the actor acts is resolved here, in parallel.
     int cnt = 0, n_ah = 0;
+#pragma unroll 1
     for (int s0 = 0; s0 < p.M; s0 += 32) {
         const int s = s0 + lane;
         const int type = s < p.M ? e.dtype[s] : D_IDLE;
         const int st = s < p.M ? e.ts[s] : 0;
         int pos = 0;
-        for (int j = 0; j < p.M; ++j) pos += (e.dtype[j] != D_IDLE && e.ts[j] < st);
+#pragma unroll 4
+        for (int j = 0; j < p.M; ++j) pos += e.ats[j] < st;
         if (type == D_IDLE) continue;
         const int a = e.da[s], b = e.db[s], x = e.tx[s], y = e.ty[s];
         int kind = X_NOP, r2 = 0, dlo = 0, dn = 1;
@@ -286,6 +353,7 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     n_ah = __reduce_add_sync(ZS_FULL, n_ah);
     // ---- draws of this step, generated 4 per lane (counter-based: any k is available directly)
     const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
+#pragma unroll 1
     for (int blk = lane; blk * 4 < n_need; blk += 32) {
         uint32_t o[4];
         philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)blk, p.key0, p.key1, o);
@@ -293,17 +361,20 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     }
     __syncwarp();
     // Fisher-Yates partner of every iteration (random.shuffle: for i = L-1 .. 1: j = randbelow(i + 1))
+#pragma unroll 1
     for (int i = 1 + lane; i < L; i += 32) e.dtype[i] = (uint8_t)below(e.draws[nd + (L - 1 - i)], i + 1);
     __syncwarp();
 
     // ---- random.shuffle + execute_actions: order-dependent by definition, run by lane 0
     int k = nd + (L > 1 ? L - 1 : 0);
     if (lane == 0) {
+#pragma unroll 1
         for (int i = L - 1; i >= 1; --i) {
             const int j = e.dtype[i];
             const unsigned long long tmp = e.act[i]; e.act[i] = e.act[j]; e.act[j] = tmp;
         }
-        int n_touched = 0;
+        int n_touched = 0, stamp = e.stampctr, fl = e.flags, deaths = e.deaths;
+#pragma unroll 1
         for (int i = 0; i < L; ++i) {
             const unsigned long long pk = e.act[i];
             const int actor = (int)(pk & 0xff), kind = (int)((pk >> 8) & 7);
@@ -316,7 +387,7 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                     e.grid[old] = dead_bit(e, old) ? G_DEAD : G_EMPTY;
                     e.grid[c] = (uint8_t)(actor + 1);
                     e.tx[actor] = (int16_t)a; e.ty[actor] = (int16_t)b;
-                    e.ts[actor] = e.stampctr++;  // things[dest] = thing; del things[old]: goes last
+                    e.ts[actor] = stamp++;  // things[dest] = thing; del things[old]: goes last
                 }
                 continue;
             }
@@ -328,44 +399,51 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                 else { const int nl = e.tl[a] + amount; e.tl[a] = (int16_t)(nl < 100 ? nl : 100); }
             } else {
                 const int amount = dlo + below(e.draws[k++], dn);
-                const int cell = __ldg(p.static_cell + a);
                 if (kind == X_ATTACK_S) {
-                    e.slife[a] = (int16_t)(e.slife[a] - amount);
+                    e.sl[a] = (int16_t)(e.sl[a] - amount);
                     e.list[n_touched++] = (uint16_t)a;
                 } else {
                     const int mx = dlo == 1 ? 10 : 200;  // MAX_LIFE // 10 is 1 for a Box, 20 for a Wall
-                    const int nl = e.slife[a] + amount;
-                    e.slife[a] = (int16_t)(nl < mx ? nl : mx);
+                    const int nl = e.sl[a] + amount;
+                    e.sl[a] = (int16_t)(nl < mx ? nl : mx);
                 }
-                e.grid[cell] = G_STATIC_DMG;
+                e.grid[__ldg(p.static_cell + a)] = G_STATIC_DMG;
+                fl |= FL_DMG | FL_SL_DIRTY;
             }
         }
         // clean_dead_things for boxes/walls hit this step (core.py:121-138); the full scan below
         // covers them on the first step of a world
-        if (!(e.flags & 1)) {
+        if (!(fl & FL_FRESH)) {
+#pragma unroll 1
             for (int i = 0; i < n_touched; ++i) {
                 const int si = e.list[i];
                 const int cell = __ldg(p.static_cell + si);
-                if (e.slife[si] <= 0 && g_is_static(e.grid[cell])) { e.grid[cell] = G_EMPTY; e.deaths++; }
+                if (e.sl[si] <= 0 && g_is_static(e.grid[cell])) { e.grid[cell] = G_EMPTY; deaths++; }
             }
         }
+        e.stampctr = stamp; e.flags = fl; e.deaths = deaths;
     }
     k = __shfl_sync(ZS_FULL, k, 0);
     e.stampctr = __shfl_sync(ZS_FULL, e.stampctr, 0);
     e.deaths = __shfl_sync(ZS_FULL, e.deaths, 0);
+    e.flags = __shfl_sync(ZS_FULL, e.flags, 0);
     __syncwarp();
 
     // ---- clean_dead_things (core.py:121-138)
     int nd_all = 0, nd_z = 0;
-    if (e.flags & 1) {  // first step of this world: every box/wall with life <= 0 leaves now
-        for (int i = lane; i < p.S; i += 32) {
-            if (e.slife[i] <= 0) {
-                const int cell = __ldg(p.static_cell + i);
-                if (g_is_static(e.grid[cell])) { e.grid[cell] = G_EMPTY; ++nd_all; }
+    if (e.flags & FL_FRESH) {  // first step of this world: every box/wall with life <= 0 leaves now
+        if (e.flags & FL_DMG) {
+#pragma unroll 1
+            for (int i = lane; i < p.S; i += 32) {
+                if (e.sl[i] <= 0) {
+                    const int cell = __ldg(p.static_cell + i);
+                    if (g_is_static(e.grid[cell])) { e.grid[cell] = G_EMPTY; ++nd_all; }
+                }
             }
         }
-        e.flags &= ~1;
+        e.flags &= ~FL_FRESH;
     }
+#pragma unroll 1
     for (int s = lane; s < p.M; s += 32) {
         if ((e.tm[s] & 0x80) && e.tl[s] <= 0) {
             const int c = e.ty[s] * p.W + e.tx[s];
@@ -386,14 +464,19 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
 // Places the `count` slots listed in e.list[0..count) on shuffled free cells of `spawn` (or of the
 // whole map, x-major, when the map has no such spawn cells).  Only the first `count` Fisher-Yates
 // iterations decide placements (spawns.pop() takes from the end); the rest of the shuffle only
-// advances the draw counter.  Returns the new draw index.
-__device__ __forceinline__ int spawn_in_random(const ZsParams& p, Env& e, uint32_t t_word, int k, int count,
-                                               const uint16_t* spawn, int n_spawn) {
-    const int lane = e.lane;
+// advances the draw counter.  Returns the new draw index.  Cold path: out of line.
+__device__ __noinline__ int spawn_in_random(const ZsParams& p, unsigned char* base, int env, int lane, int episode,
+                                            uint32_t t_word, int k, int count, int which, int stamp0) {
+    Env e;
+    env_bind(p, e, base, env, lane);
+    e.episode = episode;
+    const uint16_t* spawn = which ? p.zs_cells : p.ps_cells;
+    const int n_spawn = which ? p.n_zs : p.n_ps;
     const int n_src = n_spawn > 0 ? n_spawn : p.cells;
     int n = 0;
-    for (int base = 0; base < n_src; base += 32) {
-        const int i = base + lane;
+#pragma unroll 1
+    for (int b0 = 0; b0 < n_src; b0 += 32) {
+        const int i = b0 + lane;
         bool ok = false;
         int c = 0;
         if (i < n_src) {
@@ -407,12 +490,14 @@ __device__ __forceinline__ int spawn_in_random(const ZsParams& p, Env& e, uint32
     }
     __syncwarp();
     const int placed = count < n ? count : n;
+#pragma unroll 1
     for (int it = lane; it < placed; it += 32) {
         const int i = n - 1 - it;
         e.draws[it] = i >= 1 ? (uint32_t)below(draw_at(p, e, t_word, k + it), i + 1) : 0u;
     }
     __syncwarp();
     if (lane == 0) {
+#pragma unroll 1
         for (int it = 0; it < placed; ++it) {
             const int i = n - 1 - it;
             if (i >= 1) { const int j = (int)e.draws[it]; uint16_t tmp = e.cand[i]; e.cand[i] = e.cand[j]; e.cand[j] = tmp; }
@@ -421,23 +506,28 @@ __device__ __forceinline__ int spawn_in_random(const ZsParams& p, Env& e, uint32
             const int y = c / p.W;
             e.tx[s] = (int16_t)(c - y * p.W); e.ty[s] = (int16_t)y;
             e.tm[s] |= 0x80;
-            e.ts[s] = e.stampctr + it;
+            e.ts[s] = stamp0 + it;
             e.grid[c] = (uint8_t)(s + 1);
         }
+        e.scal[ZS_S_STAMP_COUNTER] = stamp0 + placed;
     }
-    e.stampctr += placed;
     __syncwarp();
     return k + (n > 1 ? n - 1 : 0);
 }
 
 // Game.spawn_zombies (game.py:189-194): `count` Zombie() constructions (life draws, things.py:62)
 // followed by spawn_in_random on the zombie spawn cells; free zombie slots are taken in ascending order.
-__device__ __forceinline__ int spawn_zombies(const ZsParams& p, Env& e, uint32_t t_word, int k, int count) {
-    const int lane = e.lane;
+// The new stamp counter is left in e.scal[ZS_S_STAMP_COUNTER].
+__device__ __noinline__ int spawn_zombies(const ZsParams& p, unsigned char* base, int env, int lane, int episode,
+                                          uint32_t t_word, int k, int count, int stamp0) {
+    Env e;
+    env_bind(p, e, base, env, lane);
+    e.episode = episode;
     const int NP = p.P + p.A;
     int n = 0;
-    for (int base = NP; base < p.M; base += 32) {
-        const int s = base + lane;
+#pragma unroll 1
+    for (int b0 = NP; b0 < p.M; b0 += 32) {
+        const int s = b0 + lane;
         const bool free_slot = s < p.M && !(e.tm[s] & 0x80);
         const unsigned m = __ballot_sync(ZS_FULL, free_slot);
         const int pos = n + __popc(m & ((1u << lane) - 1u));
@@ -446,24 +536,30 @@ __device__ __forceinline__ int spawn_zombies(const ZsParams& p, Env& e, uint32_t
     }
     const int made = count < n ? count : n;
     __syncwarp();
+#pragma unroll 1
     for (int i = lane; i < made; i += 32) {
         const int s = e.list[i];
         e.tl[s] = (int16_t)(50 + below(draw_at(p, e, t_word, k + i), 51));
         e.tm[s] = ZS_WEAPON_CLAWS;
     }
     __syncwarp();
-    return spawn_in_random(p, e, t_word, k + count, made, p.zs_cells, p.n_zs);
+    return spawn_in_random(p, base, env, lane, episode, t_word, k + count, made, 1, stamp0);
 }
 
-// Game.__initialize_world__ (game.py:151-169) + reward_tracker.reset (reward.py:26-28).
-// Returns the number of draws consumed.
-__device__ __noinline__ int initialize_world(const ZsParams& p, Env& e, int episode) {
-    const int lane = e.lane;
+// Game.__initialize_world__ (game.py:151-169) + reward_tracker.reset (reward.py:26-28).  Out of line and
+// with its own binding of the env's shared memory, so the hot loop's registers stay registers: the new
+// scalars are left in e.scal (read back with scalars_from_smem).  `flags_in`: the launch-lifetime static
+// damage flags survive a world init (the damage itself does, game.py:154-155).  Returns the draws consumed.
+__device__ __noinline__ int initialize_world(const ZsParams& p, unsigned char* base, int env, int lane, int episode, int flags_in) {
+    Env e;
+    env_bind(p, e, base, env, lane);
     const int NP = p.P + p.A;
+    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH;
     e.episode = episode;
-    e.t = -1; e.deaths = 0; e.zd = 0; e.ep_steps = 0; e.stampctr = 0; e.flags = 1; e.prev_zd = 0;
+#pragma unroll 1
     for (int w = lane; w < p.dead_words; w += 32) e.dead[w] = 0;
     int k = 0;
+#pragma unroll 1
     for (int s = lane; s < p.Mp; s += 32) {
         int w = 0;
         if (s < p.P) w = ZS_WEAPON_SHOTGUN;            // terminator.py:41-42
@@ -474,6 +570,7 @@ __device__ __noinline__ int initialize_world(const ZsParams& p, Env& e, int epis
     }
     __syncwarp();
     // agent_weapon="random": one random.choice per agent, in agent order (weapons.py:43)
+#pragma unroll 1
     for (int a = 0; a < p.A; ++a) {
         if (p.agent_weapons[a] == ZS_WEAPON_RANDOM) {
             const int pick = below(draw_at(p, e, 0u, k), 5);
@@ -483,15 +580,23 @@ __device__ __noinline__ int initialize_world(const ZsParams& p, Env& e, int epis
         }
     }
     __syncwarp();
-    build_grid(p, e);  // every slot is out of the world here: statics (all present) only
+    build_grid(p, base, env, lane, flags);  // every slot is out of the world here: statics (all present) only
+#pragma unroll 1
     for (int s = lane; s < p.P; s += 32) e.list[s] = (uint16_t)s;
+    if (lane == 0) e.scal[ZS_S_STAMP_COUNTER] = 0;
     __syncwarp();
-    k = spawn_in_random(p, e, 0u, k, p.P, p.ps_cells, p.n_ps);
+    k = spawn_in_random(p, base, env, lane, episode, 0u, k, p.P, 0, 0);
+#pragma unroll 1
     for (int a = lane; a < p.A; a += 32) e.list[a] = (uint16_t)(p.P + a);
     __syncwarp();
-    k = spawn_in_random(p, e, 0u, k, p.A, p.ps_cells, p.n_ps);
-    k = spawn_zombies(p, e, 0u, k, p.initial_zombies);
+    k = spawn_in_random(p, base, env, lane, episode, 0u, k, p.A, 0, e.scal[ZS_S_STAMP_COUNTER]);
+    k = spawn_zombies(p, base, env, lane, episode, 0u, k, p.initial_zombies, e.scal[ZS_S_STAMP_COUNTER]);
+#pragma unroll 1
     for (int a = lane; a < p.A; a += 32) e.prev[a] = e.tl[p.P + a];
+    if (lane == 0) {
+        e.scal[ZS_S_T] = -1; e.scal[ZS_S_EPISODE] = episode; e.scal[ZS_S_DEATHS] = 0; e.scal[ZS_S_ZOMBIE_DEATHS] = 0;
+        e.scal[ZS_S_FLAGS] = flags; e.scal[ZS_S_PREV_ZOMBIE_DEATHS] = 0; e.scal[ZS_S_EPISODE_STEPS] = 0;
+    }
     __syncwarp();
     return k;
 }
@@ -501,26 +606,26 @@ __device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, bool& ende
     const int lane = e.lane;
     const int NP = p.P + p.A;
     int alive = 0, ag = 0;
-    for (int s = lane; s < NP; s += 32) {
-        const bool al = e.tl[s] > 0;
-        alive += al;
-        ag += al && s >= p.P;
-    }
-    for (int o = 16; o; o >>= 1) {
-        alive += __shfl_xor_sync(ZS_FULL, alive, o);
-        ag += __shfl_xor_sync(ZS_FULL, ag, o);
+#pragma unroll 1
+    for (int s0 = 0; s0 < NP; s0 += 32) {
+        const int s = s0 + lane;
+        const bool al = s < NP && e.tl[s] > 0;
+        alive += __popc(__ballot_sync(ZS_FULL, al));
+        ag += __popc(__ballot_sync(ZS_FULL, al && s >= p.P));
     }
     agents_alive = ag > 0;                    // rules/rules.py:13-18
     const bool players_alive = alive > 0;     // rules/rules.py:6-11
     won = players_alive;
     if (p.rules == ZS_RULES_EXTERMINATION) {  // extermination.py:12-26
         bool z = false;
+#pragma unroll 1
         for (int s = NP + lane; s < p.M; s += 32) z |= (e.tm[s] & 0x80) && e.tl[s] > 0;
         ended = !players_alive || !__any_sync(ZS_FULL, z);
     } else if (p.rules == ZS_RULES_SURVIVAL) {  // survival.py:5-7
         ended = !players_alive;
     } else if (p.rules == ZS_RULES_SAFEHOUSE) {  // safehouse.py:10-32
         bool out = false;
+#pragma unroll 1
         for (int s = lane; s < NP; s += 32)
             out |= e.tl[s] > 0 && !objective_bit(p, e.ty[s] * p.W + e.tx[s]);
         ended = players_alive ? !__any_sync(ZS_FULL, out) : true;
@@ -541,7 +646,7 @@ __device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, bool& ende
                     seen |= 1ull << s;
                     ++together;
                     const int x = e.tx[s], y = e.ty[s];
-#pragma unroll
+#pragma unroll 1
                     for (int d = 0; d < 4; ++d) {
                         const int g = grid_at(p, e, x + adj_dx(d), y + adj_dy(d));
                         if (g >= 1 && g <= NP && e.tl[g - 1] > 0 && !((seen | pending) >> (g - 1) & 1ull)) pending |= 1ull << (g - 1);
