@@ -111,10 +111,18 @@ def oracle_env(n_envs, seed=0, base=0):
     return orc.OracleEnv(cfg, ENV_KW["map_name"])
 
 
+def host_threads():
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1; ignore it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(budget_s=12.0):
     """The oracle port on all host threads over a bounded sample of the same workload."""
     from oracle import oracle as orc
-    threads = orc.set_threads(0)
+    threads = orc.set_threads(host_threads())
     env = oracle_env(ENVS_PER_GPU)
     env.rollout_synthetic(2, 0)  # warm-up
     t0 = time.perf_counter()
@@ -147,7 +155,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as orc
-    threads = orc.set_threads(0)
+    threads = orc.set_threads(host_threads())
     n = ENVS_PER_GPU
     env = oracle_env(n)
     env.rollout_synthetic(1, 0)
