@@ -243,7 +243,7 @@ static int validate(const ZsConfig* cfg, const ZsMap* map) {
     if (cfg->initial_zombies < 0 || cfg->minimum_zombies < 0) return fail("negative zombie count");
     int Z = cfg->initial_zombies > cfg->minimum_zombies ? cfg->initial_zombies : cfg->minimum_zombies;
     if (cfg->n_bots + cfg->n_agents + Z > ZS_MAX_SLOTS) return fail("too many things per env (ZS_MAX_SLOTS)");
-    if (map->width < 1 || map->height < 1 || map->width > 8192 || map->height > 8192 ||
+    if (map->width < 1 || map->height < 1 || map->width > 2048 || map->height > 2048 ||
         (int64_t)map->width * map->height > 65535) return fail("map size out of range");
     if (map->n_statics < 0 || map->n_statics > 30000) return fail("too many statics");
     if (cfg->obs_scope == ZS_OBS_SURROUNDINGS) {
@@ -391,6 +391,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     p.off_cq = take(p.Mp * 8);
     p.off_ats = take(p.Mp * 4);
     p.off_scal = take(8 * 4);
+    p.off_rk = take(p.Mp); p.off_sor = take(p.Mp); p.off_zb = take((ZS_MAX_BOTS + ZS_MAX_AGENTS) * 4);
     p.smem_per_warp = off;
     const int smem = p.smem_per_warp * ZS_WPC;
     if (smem > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }

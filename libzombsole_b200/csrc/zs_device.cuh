@@ -64,7 +64,7 @@ struct ZsParams {
     unsigned long long* stats;     // [4]
     // ---- shared-memory carve-up (bytes from the warp's base)
     int32_t off_dead, off_tx, off_ty, off_tl, off_ts, off_tm, off_dtype, off_da, off_db, off_act, off_draws,
-        off_cand, off_list, off_prev, off_acts, off_sl, off_cq, off_ats, off_scal;
+        off_cand, off_list, off_prev, off_acts, off_sl, off_cq, off_ats, off_scal, off_rk, off_sor, off_zb;
     int32_t draws_cap, cand_cap;
     int32_t smem_per_warp;
 };
@@ -113,7 +113,10 @@ struct Env {
     unsigned long long* act; uint32_t* draws; uint16_t* cand; uint16_t* list; int16_t* prev; int32_t* acts;
     int16_t* sl;     // static lives, staged for the whole launch
     uint2* cq;       // per step: {x | y << 16 (sentinel when not in the world), dict-order stamp}
-    int32_t* ats;    // per step: stamp of an acting thing, INT_MAX otherwise
+    int32_t* ats;    // per step: closest-player key of a zombie / heal_closest agent
+    uint8_t* rk;     // per step: dict-order rank of a slot (255 when not in the world)
+    uint8_t* sor;    // per step: slot of a rank
+    uint32_t* zb;    // per step: closest-zombie key of a player slot
     int32_t* scal;   // 8 ints: hand-off of the scalars to/from the out-of-line (re)initialisation
     // warp-uniform registers
     int32_t t, episode, deaths, zd, stampctr, flags, prev_zd, ep_steps;
@@ -124,8 +127,7 @@ struct Env {
 #define FL_FRESH 1       // first step of a world: boxes/walls with life <= 0 are still present
 #define FL_DMG 2         // some box/wall has life != MAX_LIFE (else the observation needs no static patches)
 #define FL_SL_DIRTY 4    // static lives changed during this launch: write them back
-#define CQ_ABSENT 0xC180C180u  // x = y = -16000: farther than any real distance (maps are at most 8192 wide)
-#define CQ_FAR 200000000
+
 
 __device__ __forceinline__ uint32_t draw_at(const ZsParams& p, const Env& e, uint32_t t_word, int k) {
     uint32_t o[4];

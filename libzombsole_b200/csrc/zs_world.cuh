@@ -15,6 +15,7 @@ __device__ __forceinline__ void env_bind(const ZsParams& p, Env& e, unsigned cha
     e.prev = (int16_t*)(base + p.off_prev); e.acts = (int32_t*)(base + p.off_acts);
     e.sl = (int16_t*)(base + p.off_sl); e.cq = (uint2*)(base + p.off_cq); e.ats = (int32_t*)(base + p.off_ats);
     e.scal = (int32_t*)(base + p.off_scal);
+    e.rk = base + p.off_rk; e.sor = base + p.off_sor; e.zb = (uint32_t*)(base + p.off_zb);
     e.env = env; e.env_global = p.env_base + (uint32_t)env; e.lane = lane;
 }
 
@@ -174,23 +175,79 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     e.t += 1;
     const uint32_t t_word = (uint32_t)(e.t + 1);
 
-    // ---- per-step candidate table: position (a far-away sentinel when not in the world) and stamp
-    unsigned humans = 0;
+    // ---- per-step tables: packed position + stamp of every slot, which players need their closest zombie
+    bool humans = false;
+    unsigned needz0 = 0, needz1 = 0;  // players (slots < NP <= 64) that look for the closest zombie
 #pragma unroll 1
     for (int s0 = 0; s0 < p.Mp; s0 += 32) {
         const int s = s0 + lane;
+        bool live = false, needz = false;
         if (s < p.Mp) {
-            const bool live = (e.tm[s] & 0x80) != 0;  // padding slots are never in the world
-            e.cq[s] = live ? make_uint2((uint32_t)(uint16_t)e.tx[s] | ((uint32_t)(uint16_t)e.ty[s] << 16), (uint32_t)e.ts[s])
-                           : make_uint2(CQ_ABSENT, 0x7fffffffu);
-            humans |= live && s < NP;
+            live = (e.tm[s] & 0x80) != 0;  // padding slots are never in the world
+            e.cq[s] = make_uint2((uint32_t)(uint16_t)e.tx[s] | ((uint32_t)(uint16_t)e.ty[s] << 16),
+                                 live ? (uint32_t)e.ts[s] : 0x7fffffffu);
+            if (live && s < NP) {
+                humans = true;
+                // terminators always (terminator.py:10-14), agents for attack_closest (agent.py:41-47)
+                needz = s < p.P || e.acts[3 * (s - p.P)] == ZS_ACT_ATTACK_CLOSEST;
+            }
         }
+        if (s0 < NP) {
+            const unsigned m = __ballot_sync(ZS_FULL, needz);
+            if (s0 == 0) needz0 = m; else needz1 = m;
+        }
+        if (s < NP) e.zb[s] = 0xffffffffu;
     }
     const bool has_humans = __any_sync(ZS_FULL, humans);
+    __syncwarp();
+    // ---- dict-order rank of every thing in the world = number of things with a smaller stamp.  It breaks
+    // distance ties (sorted() is stable, utils.py:23-31) and orders the actors (core.py:83-90).
+#pragma unroll 1
+    for (int s0 = 0; s0 < p.Mp; s0 += 32) {
+        const int s = s0 + lane;
+        const int st = s < p.Mp ? (int)e.cq[s].y : 0x7fffffff;
+        int r = 0;
+#pragma unroll 4
+        for (int j = 0; j < p.Mp; ++j) r += (int)e.cq[j].y < st;
+        if (s < p.Mp) {
+            const bool live = st != 0x7fffffff;
+            e.rk[s] = live ? (uint8_t)r : (uint8_t)255;
+            if (live) e.sor[r] = (uint8_t)s;
+        }
+    }
+    __syncwarp();
+    // ---- closest(self, others) (utils.py:23-31) for everybody from ONE pass over the (thing, player) distances:
+    // a zombie (things.py:73-82) or a heal_closest agent (agent.py:79-86) takes the minimum over the players in
+    // its own lane; a player's closest zombie (terminator.py:10-14, agent.py:41-47) is the minimum of the same
+    // distances across the zombie lanes (redux.sync).  Key = (d^2 << 8) | dict rank: ties go to the earlier thing.
+#pragma unroll 1
+    for (int s0 = 0; s0 < p.M; s0 += 32) {
+        const int s = s0 + lane;
+        const bool live = s < p.M && (e.tm[s] & 0x80);
+        const bool zombie = s >= NP;
+        const int x = live ? e.tx[s] : 0, y = live ? e.ty[s] : 0;
+        const uint32_t myrank = live ? e.rk[s] : 255u;
+        const bool wantp = live && (zombie ? has_humans : (s >= p.P && e.acts[3 * (s - p.P)] == ZS_ACT_HEAL_CLOSEST));
+        uint32_t bestp = 0xffffffffu;
+#pragma unroll 1
+        for (int q = 0; q < NP; ++q) {
+            const uint2 c = e.cq[q];
+            if (c.y == 0x7fffffffu) continue;  // player q is not in the world (warp-uniform)
+            const int dx = x - (int)(int16_t)(c.x & 0xffffu), dy = y - (int)(int16_t)(c.x >> 16);
+            const uint32_t d = (uint32_t)(dx * dx + dy * dy) << 8;
+            if (wantp && q != s) bestp = min(bestp, d | (uint32_t)e.rk[q]);
+            if (((q < 32 ? needz0 : needz1) >> (q & 31)) & 1u) {
+                const uint32_t m = __reduce_min_sync(ZS_FULL, (live && zombie) ? (d | myrank) : 0xffffffffu);
+                if (lane == 0 && m < e.zb[q]) e.zb[q] = m;
+            }
+        }
+        if (s < p.Mp) e.ats[s] = (int)bestp;
+    }
     __syncwarp();
 
     // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
     bool any_wander = false;
+    int n_idle = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < p.M; s0 += 32) {
         const int s = s0 + lane;
@@ -202,41 +259,23 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             at = e.acts[3 * (s - p.P)]; adx = e.acts[3 * (s - p.P) + 1]; ady = e.acts[3 * (s - p.P) + 2];
             if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; adx = 0; ady = 0; }  // multiagent_env.py:129-131
         }
-        // closest(self, others) (utils.py:23-31): zombies look at players (things.py:73-82), terminators and
-        // attack_closest at zombies (terminator.py:10-14, agent.py:41-47), heal_closest at the other players
-        // (agent.py:79-86).  sorted() is stable: ties go to the smaller dict-order stamp.  One uniform loop
-        // over the union of the lanes' candidate ranges; every shared-memory read is a warp broadcast.
-        int lo = 0x7fffffff, hi = 0, skip = -1;
-        if (live) {
-            if (zombie) { if (has_humans) { lo = 0; hi = NP; } }
-            else if (!agent || at == ZS_ACT_ATTACK_CLOSEST) { lo = NP; hi = p.M; }
-            else if (at == ZS_ACT_HEAL_CLOSEST) { lo = 0; hi = NP; skip = s; }
-        }
-        const int wlo = __reduce_min_sync(ZS_FULL, lo), whi = __reduce_max_sync(ZS_FULL, hi);
-        const unsigned span = (unsigned)(hi - lo);
-        int bd = 0x7fffffff, bst = 0x7fffffff, tg = -1;
-#pragma unroll 2
-        for (int j = wlo; j < whi; ++j) {
-            const uint2 q = e.cq[j];
-            const int dx = x - (int)(int16_t)(q.x & 0xffffu), dy = y - (int)(int16_t)(q.x >> 16);
-            const int d = dx * dx + dy * dy;
-            const bool in = (unsigned)(j - lo) < span && j != skip;
-            if (in && (d < bd || (d == bd && (int)q.y < bst))) { bd = d; bst = (int)q.y; tg = j; }
-        }
-        if (bd >= CQ_FAR) tg = -1;
-        const int d2 = bd;
+        uint32_t key = 0xffffffffu;
+        if (live) key = (zombie || at == ZS_ACT_HEAL_CLOSEST) ? (uint32_t)e.ats[s] : e.zb[s];
+        const int tg = key == 0xffffffffu ? -1 : (int)e.sor[key & 255u];
+        const int d2 = (int)(key >> 8);
         int type = D_IDLE, a = 0, b = 0;
         if (live) {
             const int gx = tg >= 0 ? e.tx[tg] : 0, gy = tg >= 0 ? e.ty[tg] : 0;
-            if (zombie) {  // Zombie.next_step (things.py:70-105)
-                unsigned freemask = 0, gs[4];
-                int dd[4];
+            // the four adjacent cells (utils.py:34-44): what is on them and how far they are from the target
+            unsigned freemask = 0, gs[4];
+            int dd[4];
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {  // possible_moves: no bounds check (utils.py:47-52)
-                    gs[d] = grid_at(p, e, x + adj_dx(d), y + adj_dy(d));
-                    dd[d] = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
-                    if (!g_is_thing(gs[d])) freemask |= 1u << d;
-                }
+            for (int d = 0; d < 4; ++d) {  // no bounds check: cells outside the map hold nothing (utils.py:47-52)
+                gs[d] = grid_at(p, e, x + adj_dx(d), y + adj_dy(d));
+                dd[d] = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
+                if (!g_is_thing(gs[d])) freemask |= 1u << d;
+            }
+            if (zombie) {  // Zombie.next_step (things.py:70-105)
                 if (!has_humans) {
                     if (freemask) { type = D_WANDER; a = (int)freemask; any_wander = true; }
                 } else if (d2 <= 2) { type = D_ATTACK; a = tg; }  // distance < 1.5 (things.py:83)
@@ -258,14 +297,11 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             } else if (!agent) {  // Terminator.next_step (players/terminator.py:9-37)
                 if (tg < 0) { type = D_HEAL; a = s; }
                 else if (d2 > c_range2[e.tm[s] & 15]) {
-                    int bdir = 0, bdist = 0x7fffffff;
+                    int bdir = 0, bdist = 0x7fffffff, g = 0;
 #pragma unroll
-                    for (int d = 0; d < 4; ++d) {  // closest(target, adjacent_positions(self)): out-of-bounds cells included
-                        const int q = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
-                        if (q < bdist) { bdir = d; bdist = q; }
-                    }
+                    for (int d = 0; d < 4; ++d)  // closest(target, adjacent_positions(self)): out-of-bounds cells included
+                        if (dd[d] < bdist) { bdir = d; bdist = dd[d]; g = (int)gs[d]; }
                     const int bx = x + adj_dx(bdir), by = y + adj_dy(bdir);
-                    const int g = grid_at(p, e, bx, by);
                     if (g_is_thing(g)) {
                         type = (g <= G_MAX_SLOT && (g - 1) < NP) ? D_HEAL : D_ATTACK;
                         a = target_of_cell(p, g, by * p.W + bx);
@@ -286,12 +322,11 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                     }
                 }
             }
+            n_idle += type == D_IDLE;
         }
-        if (s < p.Mp) {
-            e.dtype[s] = (uint8_t)type; e.da[s] = (int16_t)a; e.db[s] = (int16_t)b;
-            e.ats[s] = (type != D_IDLE && type != D_WANDER) ? e.ts[s] : 0x7fffffff;
-        }
+        if (s < p.Mp) { e.dtype[s] = (uint8_t)type; e.da[s] = (int16_t)a; e.db[s] = (int16_t)b; }
     }
+    n_idle = __reduce_add_sync(ZS_FULL, n_idle);
     __syncwarp();
     int nd = 0;
     if (__any_sync(ZS_FULL, any_wander)) {
@@ -312,20 +347,23 @@ __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         nd = __reduce_add_sync(ZS_FULL, mine);
         __syncwarp();
 #pragma unroll 1
-        for (int s = lane; s < p.M; s += 32) if (e.dtype[s] == D_WANDER) { e.dtype[s] = D_MOVE; e.ats[s] = e.ts[s]; }
+        for (int s = lane; s < p.M; s += 32) if (e.dtype[s] == D_WANDER) e.dtype[s] = D_MOVE;
         __syncwarp();
     }
-    // actions list in actor (dict) order: position = number of acting things with a smaller stamp.
+    // actions list in actor (dict) order (core.py:83-90): the position of an acting thing is its dict rank minus
+    // the idle things before it (idle things are rare: usually the rank is the position).
     // Everything that cannot change before the actor acts is resolved here, in parallel.
     int cnt = 0, n_ah = 0;
 #pragma unroll 1
     for (int s0 = 0; s0 < p.M; s0 += 32) {
         const int s = s0 + lane;
-        const int type = s < p.M ? e.dtype[s] : D_IDLE;
-        const int st = s < p.M ? e.ts[s] : 0;
-        int pos = 0;
-#pragma unroll 4
-        for (int j = 0; j < p.M; ++j) pos += e.ats[j] < st;
+        const int type = (s < p.M && (e.tm[s] & 0x80)) ? e.dtype[s] : D_IDLE;
+        int pos = s < p.M ? e.rk[s] : 0;
+        if (n_idle) {
+            const int mine = pos;
+#pragma unroll 1
+            for (int j = 0; j < p.M; ++j) pos -= ((e.tm[j] & 0x80) && e.dtype[j] == D_IDLE && e.rk[j] < mine);
+        }
         if (type == D_IDLE) continue;
         const int a = e.da[s], b = e.db[s], x = e.tx[s], y = e.ty[s];
         int kind = X_NOP, r2 = 0, dlo = 0, dn = 1;
