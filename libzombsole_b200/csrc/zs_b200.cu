@@ -16,11 +16,8 @@
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_ENCODE = 2 };
 
 __device__ __forceinline__ int synthetic_action(const ZsParams& p, uint32_t env_global, uint32_t step_index, int agent) {
-    uint32_t o[4];
-    philox4x32_10(env_global, step_index, 0u, (uint32_t)(agent >> 2), p.key0, p.key1 ^ 0xAC710115u, o);
-    const int w = agent & 3;
-    const uint32_t u = w == 0 ? o[0] : w == 1 ? o[1] : w == 2 ? o[2] : o[3];
-    return below(u, p.n_discrete);
+    const uint4 o = philox4x32_10(env_global, step_index, 0u, (uint32_t)(agent >> 2), p.key0, p.key1 ^ 0xAC710115u);
+    return below(word_of(o, agent & 3), p.n_discrete);
 }
 
 // discrete id -> (type, dx, dy): ZombsoleGymEnvDiscreteAction.game_actions (gym_env.py:328-351),
@@ -33,120 +30,148 @@ __device__ __forceinline__ void discrete_to_action(const ZsParams& p, int id, in
     else type = id == 4 ? ZS_ACT_ATTACK_CLOSEST : id == 5 ? ZS_ACT_HEAL : ZS_ACT_HEAL_CLOSEST;
 }
 
-template <int MODE>
+template <int MODE, int MPC, int G>
 __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int env = blockIdx.x * ZS_WPC + wid;
-    if (env >= p.N) return;
-    unsigned char* base = smem + (size_t)wid * p.smem_per_warp;
+    ZS_CONSTS;
+    constexpr int EPW = 32 / G;  // envs per warp
+    const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     Env e;
-    env_bind(p, e, base, env, lane);
+    e.gl = wlane & (G - 1);
+    e.gshift = wlane & ~(G - 1);
+    e.gm = G == 32 ? 0xffffffffu : (0xffffu << e.gshift);
+    const int slot = wid * EPW + (wlane / G);
+    const int env = blockIdx.x * (ZS_WPC * EPW) + slot;
+    if (env >= p.N) return;
+    e.b = (uint32_t)slot * (uint32_t)p.smem_per_env;
+    e.env = env; e.env_global = p.env_base + (uint32_t)env;
+    const int lane = e.gl;
+    ZS_VIEWS;
 
     if (MODE == MODE_RESET) {
         if (io.env_mask && !io.env_mask[env]) return;
         // slots keep their last position/life until re-placed; bring them in so the store is complete
-        load_state(p, e);
-        const int k = initialize_world(p, base, env, lane, e.episode + 1, e.flags);
-        scalars_from_smem(e);
+        load_state<MPC, G>(p, e);
+        const int k = initialize_world<MPC, G>(p, id_of(e), e.episode + 1, e.flags);
+        scalars_from_smem<MPC, G>(p, e);
         if (io.draws && lane == 0) io.draws[env] = k;
-        if (io.obs) encode_obs(p, e, io.obs + (size_t)env * p.obs_elems);
-        store_state(p, e);
+        if (io.obs) encode_obs<MPC, G>(p, e, io.obs + (size_t)env * p.obs_elems);
+        store_state<MPC, G>(p, e);
         return;
     }
-    load_state(p, e);
-    build_grid(p, base, env, lane, e.flags);
+    load_state<MPC, G>(p, e);
+    build_grid<MPC, G>(p, id_of(e), e.flags);
     if (MODE == MODE_ENCODE) {
-        encode_obs(p, e, io.obs + (size_t)env * p.obs_elems);
+        encode_obs<MPC, G>(p, e, io.obs + (size_t)env * p.obs_elems);
         return;
     }
 
     const int A = p.A, NP = p.P + p.A;
     const int R = p.obs_per_agent ? A : 1;
     const bool world_obs = p.obs_scope == ZS_OBS_WORLD;
-    // this lane's agent action for the coming step, fetched one step ahead (Agent.set_action, agent.py:22-25)
-    int at = ZS_ACT_NONE, adx = 0, ady = 0;
+    // agent actions for the coming step, fetched one step ahead (Agent.set_action, agent.py:22-25);
+    // agent a is handled by lanes a, a + G, ... of the group
+    constexpr int AR = ZS_MAX_AGENTS / G > 0 ? ZS_MAX_AGENTS / G : 1;  // agents per lane (1 or 2)
+    int at[AR], adx[AR], ady[AR];
     auto fetch_action = [&](int step) {
-        if (lane >= A) return;
-        const size_t sn = (size_t)step * p.N + env;
-        if (io.actions == nullptr) discrete_to_action(p, synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), lane), at, adx, ady);
-        else if (io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, io.actions[sn * A + lane], at, adx, ady);
-        else { const int32_t* q = io.actions + (sn * A + lane) * 3; at = q[0]; adx = q[1]; ady = q[2]; }
+#pragma unroll
+        for (int r = 0; r < AR; ++r) {
+            const int a = lane + r * G;
+            at[r] = ZS_ACT_NONE; adx[r] = 0; ady[r] = 0;
+            if (a >= A) continue;
+            const size_t sn = (size_t)step * p.N + env;
+            if (io.actions == nullptr) discrete_to_action(p, synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), a), at[r], adx[r], ady[r]);
+            else if (io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, io.actions[sn * A + a], at[r], adx[r], ady[r]);
+            else { const int32_t* q = io.actions + (sn * A + a) * 3; at[r] = q[0]; adx[r] = q[1]; ady[r] = q[2]; }
+        }
     };
     fetch_action(0);
-    int slot = 0;
+    int oslot = 0;
 #pragma unroll 1
     for (int step = 0; step < io.n_steps; ++step) {
         const size_t sn = (size_t)step * p.N + env;
         int32_t* obs_out = nullptr;
         if (io.obs) {
-            obs_out = io.obs + ((size_t)slot * p.N + env) * p.obs_elems;
-            if (++slot >= io.obs_slots) slot = 0;
+            obs_out = io.obs + ((size_t)oslot * p.N + env) * p.obs_elems;
+            if (++oslot >= io.obs_slots) oslot = 0;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
-            if (world_obs) obs_world_template(p, e, obs_out);
+            if (world_obs) obs_world_template<MPC, G>(p, e, obs_out);
         }
-        if (lane < A) { e.acts[3 * lane] = at; e.acts[3 * lane + 1] = adx; e.acts[3 * lane + 2] = ady; }
         // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
-        const unsigned alive_before = __ballot_sync(ZS_FULL, lane < A && e.tl[p.P + (lane < A ? lane : 0)] > 0);
+        unsigned alive_before = 0;
+        int life_before[AR];
+#pragma unroll
+        for (int r = 0; r < AR; ++r) {
+            const int a = lane + r * G;
+            if (a < A) { ACTS(3 * a) = at[r]; ACTS(3 * a + 1) = adx[r]; ACTS(3 * a + 2) = ady[r]; }
+            alive_before |= gballot<G>(e, a < A && TL(p.P + (a < A ? a : 0)) > 0) << (r * G);
+            life_before[r] = a < A ? PREVL(a) : 0;
+        }
         const int zd_before = e.prev_zd;
-        const int life_before = lane < A ? e.prev[lane] : 0;
-        __syncwarp();
+        gsync<G>(e);
         if (step + 1 < io.n_steps) fetch_action(step + 1);
 
-        int k = world_step(p, e);
+        int k = world_step<MPC, G>(p, e);
         e.ep_steps += 1;
 
         // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order.
-        // Lane a holds agent a's reward; a tracker whose inputs did not change yields exactly +0.0.
-        const int life_now = lane < A ? e.tl[p.P + lane] : 0;
-        double rew = 0.0;
-        if (!p.obs_per_agent) {
-            const int sum_prev = __reduce_add_sync(ZS_FULL, life_before), sum_new = __reduce_add_sync(ZS_FULL, life_now);
-            if (sum_prev != sum_new || zd_before != e.zd)
-                rew = __dsub_rn(total_reward(e.zd, sum_new), total_reward(zd_before, sum_prev));
-        } else if (lane < A && (life_before != life_now || zd_before != e.zd)) {
-            rew = __dsub_rn(total_reward(e.zd, life_now), total_reward(zd_before, life_before));
+        // A tracker whose inputs did not change yields exactly +0.0.
+        int life_now[AR];
+        double rew[AR];
+        int sum_prev = 0, sum_new = 0;
+#pragma unroll
+        for (int r = 0; r < AR; ++r) {
+            const int a = lane + r * G;
+            life_now[r] = a < A ? TL(p.P + a) : 0;
+            rew[r] = 0.0;
+            if (!p.obs_per_agent) { sum_prev += gadd<G>(e, life_before[r]); sum_new += gadd<G>(e, life_now[r]); }
+            else if (a < A && (life_before[r] != life_now[r] || zd_before != e.zd))
+                rew[r] = __dsub_rn(total_reward(e.zd, life_now[r]), total_reward(zd_before, life_before[r]));
+            if (a < A) PREVL(a) = (int16_t)life_now[r];
         }
-        if (lane < A) e.prev[lane] = (int16_t)life_now;
+        if (!p.obs_per_agent && (sum_prev != sum_new || zd_before != e.zd))
+            rew[0] = __dsub_rn(total_reward(e.zd, sum_new), total_reward(zd_before, sum_prev));
         e.prev_zd = e.zd;
-        __syncwarp();
+        gsync<G>(e);
 
         // ---- Game.spawn_zombies_to_maintain_minimum (game.py:196-201)
         if (p.minimum_zombies > 0) {
             int zc = 0;
 #pragma unroll 1
-            for (int s0 = NP; s0 < p.M; s0 += 32) zc += __popc(__ballot_sync(ZS_FULL, s0 + lane < p.M && (e.tm[s0 + lane] & 0x80)));
+            for (int s0 = NP; s0 < p.M; s0 += G) zc += __popc(gballot<G>(e, s0 + lane < p.M && (TM(s0 + lane) & 0x80)));
             if (zc < p.minimum_zombies) {
-                k = spawn_zombies(p, base, env, lane, e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.stampctr);
-                e.stampctr = e.scal[ZS_S_STAMP_COUNTER];
+                k = spawn_zombies<MPC, G>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive);
+                e.nlive = SCALW(ZS_S_STAMP_COUNTER);
             }
         }
 
         // ---- rules and end reward (gym_env.py:130-141, multiagent_env.py:143-162)
         bool ended, won, agents_alive;
-        rules_eval(p, e, ended, won, agents_alive);
+        rules_eval<MPC, G>(p, e, ended, won, agents_alive);
         bool done = false, trunc = false;
         double end_reward = 0.0;
         if (ended) { done = true; end_reward = won ? 10.0 : -10.0; }
         else if (!agents_alive) { trunc = true; end_reward = -10.0; }
         if (!p.obs_per_agent) {
-            if (done || trunc) rew = __dadd_rn(rew, end_reward);
-        } else if (lane < A) {
-            if (!((alive_before >> lane) & 1u)) rew = 0.0;
-            else if (life_now > 0) rew = __dadd_rn(rew, end_reward);
+            if (done || trunc) rew[0] = __dadd_rn(rew[0], end_reward);
+            if (io.reward && lane == 0) io.reward[sn] = rew[0];
+        } else {
+#pragma unroll
+            for (int r = 0; r < AR; ++r) {
+                const int a = lane + r * G;
+                if (a >= A) continue;
+                if (!((alive_before >> a) & 1u)) rew[r] = 0.0;
+                else if (life_now[r] > 0) rew[r] = __dadd_rn(rew[r], end_reward);
+                if (io.reward) io.reward[sn * R + a] = rew[r];
+                if (io.agent_mask) io.agent_mask[sn * A + a] = (alive_before >> a) & 1u;
+            }
         }
         if (p.max_steps > 0 && e.ep_steps >= p.max_steps) trunc = true;  // gymnasium TimeLimit
-
-        if (io.reward) {
-            if (!p.obs_per_agent) { if (lane == 0) io.reward[sn] = rew; }
-            else if (lane < A) io.reward[sn * R + lane] = rew;
-        }
         if (lane == 0) {
             if (io.terminated) io.terminated[sn] = done;
             if (io.truncated) io.truncated[sn] = trunc;
             if (io.draws) io.draws[sn] = k;
         }
-        if (io.agent_mask && lane < A) io.agent_mask[sn * A + lane] = (alive_before >> lane) & 1u;
+        if (!p.obs_per_agent && io.agent_mask && lane < A) io.agent_mask[sn * A + lane] = (alive_before >> lane) & 1u;
 
         // ---- same-step auto-reset
         if ((done || trunc) && (p.auto_reset || io.force_auto_reset)) {
@@ -156,16 +181,16 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
                 atomicAdd(p.stats + 2, (unsigned long long)e.ep_steps);
                 atomicAdd(p.stats + 3, (unsigned long long)e.zd);
             }
-            initialize_world(p, base, env, lane, e.episode + 1, e.flags);
-            scalars_from_smem(e);
+            initialize_world<MPC, G>(p, id_of(e), e.episode + 1, e.flags);
+            scalars_from_smem<MPC, G>(p, e);
         }
         if (obs_out) {
-            if (world_obs) obs_world_patch(p, e, obs_out);
-            else encode_surroundings(p, e, obs_out);
+            if (world_obs) obs_world_patch<MPC, G>(p, e, obs_out);
+            else encode_surroundings<MPC, G>(p, e, obs_out);
         }
-        __syncwarp();
+        gsync<G>(e);
     }
-    store_state(p, e);
+    store_state<MPC, G>(p, e);
 }
 
 __global__ void zs_init_static_life_kernel(const __grid_constant__ ZsParams p) {
@@ -216,6 +241,9 @@ struct ZsHandle {
     int64_t launches;
     int64_t bound_bytes;
     int sm_count;
+    int envs_per_cta;
+    int lanes_per_env;
+    int smem_bytes;
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -284,6 +312,36 @@ extern "C" __attribute__((visibility("default"))) int zs_layout(const ZsConfig* 
     out->obs_count = cfg->obs_per_agent ? cfg->n_agents : 1;
     out->obs_elems_per_env = (int64_t)out->obs_count * out->obs_channels * out->obs_height * out->obs_width;
     out->n_discrete_actions = cfg->obs_per_agent ? 7 : 6;
+    return 0;
+}
+
+template <int MODE>
+static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
+    const dim3 grid((h->p.N + h->envs_per_cta - 1) / h->envs_per_cta), block(ZS_WPC * 32);
+    switch (h->p.mpc) {
+        case 16:
+            if (h->lanes_per_env == 16) zs_sim_kernel<MODE, 16, 16><<<grid, block, h->smem_bytes, st>>>(h->p, io);
+            else zs_sim_kernel<MODE, 16, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io);
+            break;
+        case 32: zs_sim_kernel<MODE, 32, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io); break;
+        case 128: zs_sim_kernel<MODE, 128, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io); break;
+        default: zs_sim_kernel<MODE, 256, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io); break;
+    }
+}
+template <int MPC, int G>
+static cudaError_t set_smem_attr_for(int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e;
+}
+static int set_smem_attr(int mpc, int lanes, int bytes) {
+    cudaError_t e;
+    if (mpc == 16) e = lanes == 16 ? set_smem_attr_for<16, 16>(bytes) : set_smem_attr_for<16, 32>(bytes);
+    else if (mpc == 32) e = set_smem_attr_for<32, 32>(bytes);
+    else if (mpc == 128) e = set_smem_attr_for<128, 32>(bytes);
+    else e = set_smem_attr_for<256, 32>(bytes);
+    CU(e);
     return 0;
 }
 
@@ -371,33 +429,31 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     p.stats = (unsigned long long*)st;
     if (rc) { zs_destroy(h); return rc; }
 
-    // ---- shared-memory carve-up per warp
-    int off = p.cells_pad;
+    // ---- shared memory per env: EnvS<MPC> (compile-time layout) + run-time sized tail (grid, dead bits, static lives, candidates)
+    p.mpc = p.Mp <= 16 ? 16 : p.Mp <= 32 ? 32 : p.Mp <= 128 ? 128 : 256;
+    const int struct_bytes = p.mpc == 16 ? (int)sizeof(EnvS<16>) : p.mpc == 32 ? (int)sizeof(EnvS<32>)
+                           : p.mpc == 128 ? (int)sizeof(EnvS<128>) : (int)sizeof(EnvS<256>);
+    int off = p.cells_pad;  // the grid starts right behind the struct
     auto take = [&](int bytes) { int o = off; off = round_up(off + bytes, 16); return o; };
     p.off_dead = take(p.dead_words * 4);
-    p.off_tx = take(p.Mp * 2); p.off_ty = take(p.Mp * 2); p.off_tl = take(p.Mp * 2); p.off_ts = take(p.Mp * 4); p.off_tm = take(p.Mp);
-    p.off_dtype = take(p.Mp); p.off_da = take(p.Mp * 2); p.off_db = take(p.Mp * 2); p.off_act = take(p.Mp * 8);
-    p.draws_cap = round_up(3 * p.M + 4, 4);
-    p.off_draws = take(p.draws_cap * 4);
+    p.off_sl = take(p.Sp * 2);
     int cand = 1;
     if (p.P + p.A > 0) cand = p.n_ps > 0 ? p.n_ps : cells;
     if (p.Z > 0) { int zc = p.n_zs > 0 ? p.n_zs : cells; if (zc > cand) cand = zc; }
     p.cand_cap = cand;
     p.off_cand = take(cand * 2);
-    p.off_list = take(p.Mp * 2);
-    p.off_prev = take(p.Ap * 2);
-    p.off_acts = take(p.A * 12);
-    p.off_sl = take(p.Sp * 2);
-    p.off_cq = take(p.Mp * 8);
-    p.off_ats = take(p.Mp * 4);
-    p.off_scal = take(8 * 4);
-    p.off_rk = take(p.Mp); p.off_sor = take(p.Mp); p.off_zb = take((ZS_MAX_BOTS + ZS_MAX_AGENTS) * 4);
-    p.smem_per_warp = off;
-    const int smem = p.smem_per_warp * ZS_WPC;
-    if (smem > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
-    CU(cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CU(cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    p.smem_per_env = round_up(struct_bytes + off, 16);
+    // lanes per env: a half warp when an env has at most 16 slots AND the batch does not fit the chip as
+    // one full-warp wave (148 SMs x 28 resident warps); small batches are latency-bound and want the lanes
+    h->lanes_per_env = (p.mpc == 16 && p.N > prop.multiProcessorCount * ZS_MIN_CTAS * ZS_WPC) ? 16 : 32;
+    if (const char* force = getenv("ZS_LANES_PER_ENV")) {
+        const int v = atoi(force);
+        if ((v == 16 && p.mpc == 16) || v == 32) h->lanes_per_env = v;
+    }
+    h->envs_per_cta = ZS_WPC * (32 / h->lanes_per_env);
+    h->smem_bytes = p.smem_per_env * h->envs_per_cta;
+    if (h->smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
+    if (int rc2 = set_smem_attr(p.mpc, h->lanes_per_env, h->smem_bytes)) { zs_destroy(h); return rc2; }
     *out = h;
     return 0;
 }
@@ -436,7 +492,6 @@ static int launched(ZsHandle* h) {
     h->launches++;
     return 0;
 }
-static dim3 sim_grid(const ZsHandle* h) { return dim3((h->p.N + ZS_WPC - 1) / ZS_WPC); }
 
 extern "C" __attribute__((visibility("default"))) int zs_init_static_life(ZsHandle* h, void* stream) {
     if (int rc = check_bound(h)) return rc;
@@ -449,7 +504,7 @@ extern "C" __attribute__((visibility("default"))) int zs_reset(ZsHandle* h, cons
     ZsIO io;
     memset(&io, 0, sizeof(io));
     io.env_mask = env_mask_dev; io.obs = obs_dev; io.obs_slots = 1; io.draws = draws_dev;
-    zs_sim_kernel<MODE_RESET><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    launch_sim<MODE_RESET>(h, io, (cudaStream_t)stream);
     return launched(h);
 }
 
@@ -463,7 +518,7 @@ extern "C" __attribute__((visibility("default"))) int zs_step(ZsHandle* h, const
     io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1; io.reward = reward_dev;
     io.terminated = terminated_dev; io.truncated = truncated_dev; io.agent_mask = agent_mask_dev; io.draws = draws_dev;
     io.n_steps = 1;
-    zs_sim_kernel<MODE_STEP><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    launch_sim<MODE_STEP>(h, io, (cudaStream_t)stream);
     return launched(h);
 }
 
@@ -473,7 +528,7 @@ extern "C" __attribute__((visibility("default"))) int zs_encode_obs(ZsHandle* h,
     ZsIO io;
     memset(&io, 0, sizeof(io));
     io.obs = obs_dev; io.obs_slots = 1;
-    zs_sim_kernel<MODE_ENCODE><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    launch_sim<MODE_ENCODE>(h, io, (cudaStream_t)stream);
     return launched(h);
 }
 
@@ -489,7 +544,7 @@ extern "C" __attribute__((visibility("default"))) int zs_rollout(ZsHandle* h, in
     io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = obs_slots; io.reward = reward_dev;
     io.terminated = terminated_dev; io.truncated = truncated_dev; io.n_steps = n_steps; io.first_step = first_step_index;
     io.force_auto_reset = 1;
-    zs_sim_kernel<MODE_STEP><<<sim_grid(h), ZS_WPC * 32, h->p.smem_per_warp * ZS_WPC, (cudaStream_t)stream>>>(h->p, io);
+    launch_sim<MODE_STEP>(h, io, (cudaStream_t)stream);
     return launched(h);
 }
 

@@ -1,30 +1,32 @@
 // zs_device.cuh — device-side data model and helpers of the batched zombsole simulator (sm_100a).
 //
-// Execution model: ONE WARP PER ENVIRONMENT, ZS_WPC environments per CTA.  The world of an
-// environment lives in shared memory while its warp works on it:
-//   * an occupancy grid, one byte per map cell (0 empty, 1..250 mobile slot+1, 253/255 box or wall,
-//     254 dead-body decoration) — the shared-memory-staged stand-in for the reference's
-//     position-keyed dict World.things (zombsole/core.py:15) and World.decoration (core.py:16);
-//   * the mobile things as structure-of-arrays (x, y, life, dict-order stamp, meta).
-// Phases that are parallel in the reference's semantics (every actor decides against the
-// pre-step world; observation cells are independent) are spread over the 32 lanes; the phases
-// that the reference defines sequentially (shuffle, execute_actions) are run by lane 0 on
-// shared memory.  All per-thing and per-cell loops are lane-strided so the same code serves 13
-// things on bridge and 101 on the maze.
+// Execution model: ONE LANE GROUP PER ENVIRONMENT.  A group is a full warp (G = 32) or, when an
+// env has at most 16 mobile slots (bridge: 13), a HALF warp (G = 16, two envs per warp, every sync /
+// vote / reduce carries the group's member mask).  The world of an env lives in shared memory while
+// its group works on it:
+//   * EnvS<MPC>: the mobile things as structure-of-arrays (packed x/y, life, dict-order rank, meta)
+//     and the per-step scratch, in a struct templated on the slot capacity MPC so that every field has
+//     a COMPILE-TIME offset (LDS [base + imm]);
+//   * after it, at run-time offsets: the occupancy grid, one byte per map cell (0 empty, 1..250 mobile
+//     slot+1, 253/255 box or wall, 254 dead-body decoration) — the shared-memory-staged stand-in for
+//     the reference's position-keyed dicts World.things / World.decoration (zombsole/core.py:15-16) —
+//     the dead-body bitmap, the static lives and the spawn candidate list.
+// Phases that are parallel in the reference's semantics (every actor decides against the pre-step
+// world; observation cells are independent) are spread over the group's lanes; the phases that the
+// reference defines sequentially (execute_actions) are run by the group's lane 0 on shared memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/zs_b200.h"
 
-#define ZS_WPC 4              // warps (= environments) per CTA
-#define ZS_MIN_CTAS 7         // 7 CTAs x 4 warps = 28 envs resident per SM: 4,096 envs fit the 148 SMs in one wave
-#define ZS_FULL 0xffffffffu
+#define ZS_WPC 4              // warps per CTA
+#define ZS_MIN_CTAS 7         // 7 CTAs x 4 warps resident per SM: 4,096 full-warp envs fit the 148 SMs in one wave
 
 // occupancy-grid byte codes
 #define G_EMPTY 0
 #define G_MAX_SLOT 250        // 1..250: mobile slot + 1
-#define G_STATIC_DMG 253      // box/wall present, life != MAX_LIFE (observation takes the per-cell path)
+#define G_STATIC_DMG 253      // box/wall present, life != MAX_LIFE
 #define G_DEAD 254            // DeadBody decoration and no thing
 #define G_STATIC 255          // pristine box/wall present
 
@@ -34,6 +36,10 @@
 #define D_ATTACK 2
 #define D_HEAL 3
 #define D_WANDER 4            // zombie with no humans: destination drawn in dict order (things.py:101-103)
+
+#define RK_NONE 255           // rank of a slot that is not in the world
+#define ZS_DMG_CAP 24         // damaged boxes/walls tracked individually; more than that -> full scan
+#define ZS_NP_MAX (ZS_MAX_BOTS + ZS_MAX_AGENTS)
 
 struct ZsParams {
     // ---- configuration
@@ -62,11 +68,11 @@ struct ZsParams {
     int16_t* X; int16_t* Y; int16_t* LIFE; int32_t* STAMP; uint8_t* META;
     int16_t* PREV; int16_t* SLIFE; uint32_t* DEAD; int32_t* SCAL;
     unsigned long long* stats;     // [4]
-    // ---- shared-memory carve-up (bytes from the warp's base)
-    int32_t off_dead, off_tx, off_ty, off_tl, off_ts, off_tm, off_dtype, off_da, off_db, off_act, off_draws,
-        off_cand, off_list, off_prev, off_acts, off_sl, off_cq, off_ats, off_scal, off_rk, off_sor, off_zb;
-    int32_t draws_cap, cand_cap;
-    int32_t smem_per_warp;
+    // ---- shared memory: run-time sized tail behind EnvS<MPC> (byte offsets from the end of the struct)
+    int32_t off_dead, off_sl, off_cand;
+    int32_t cand_cap;
+    int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
+    int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
 };
 
 struct ZsIO {
@@ -91,49 +97,109 @@ __constant__ int16_t c_dmg_lo[16] = {0, 5, 0, 0, 0, 0, 0, 0, 0, 0, 5, 75, 10, 25
 __constant__ int16_t c_dmg_n[16] = {1, 6, 1, 1, 1, 1, 1, 1, 1, 1, 6, 26, 41, 51, 26, 1};  // hi - lo + 1
 
 // ---------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t out[4]) {
+__device__ __noinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         c0 = hi1 ^ c1 ^ k0; c1 = lo1;
         c2 = hi0 ^ c3 ^ k1; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    return make_uint4(c0, c1, c2, c3);
 }
+__device__ __forceinline__ uint32_t word_of(const uint4& o, int w) { return w == 0 ? o.x : w == 1 ? o.y : w == 2 ? o.z : o.w; }
 
-// The environment a warp is working on.
+// ---------------------------------------------------------------- shared-memory image of one env
+extern __shared__ __align__(16) unsigned char zs_smem[];
+
+template <int MPC>
+struct alignas(16) EnvS {
+    unsigned long long act[MPC];            // the step's action list (packed, see pack_action)
+    uint32_t txy[MPC];                      // x | y << 16 (int16 each)
+    uint32_t bk[MPC];                       // per step: closest-player key of a zombie / heal_closest agent
+    uint32_t draws[3 * MPC + 16];           // per step: the draws, 4 per Philox block
+    uint32_t zb[ZS_NP_MAX];                 // per step: closest-zombie key of a player slot
+    int32_t scal[8];                        // scalar hand-off around out-of-line functions
+    int32_t acts[3 * ZS_MAX_AGENTS];        // agent actions of the step (type, dx, dy)
+    uint32_t masks[2 * ((MPC + 31) / 32) + 2];  // rank bit-masks: stayers, then movers
+    int16_t tl[MPC];                        // life
+    int16_t da[MPC];
+    int16_t db[MPC];
+    uint16_t list[MPC];
+    int16_t prev[ZS_MAX_AGENTS];            // reward tracker's agents_life
+    uint16_t dmg[ZS_DMG_CAP + 8];           // dmg[0] = count, dmg[1..] = damaged static indices
+    uint8_t tm[MPC];                        // bit7 in world, bits0-3 weapon code
+    uint8_t rk[MPC];                        // dict-order rank among the things in the world (RK_NONE if absent)
+    uint8_t sor[MPC];                       // slot of a rank
+    uint8_t mvq[MPC];                       // order of this step's successful moves, RK_NONE if none
+    uint8_t dtype[MPC];
+};
+
+// The env a lane group is working on (warp-uniform within the group).
 struct Env {
-    // shared memory views
-    uint8_t* grid; uint32_t* dead;
-    int16_t* tx; int16_t* ty; int16_t* tl; int32_t* ts; uint8_t* tm;
-    uint8_t* dtype; int16_t* da; int16_t* db;
-    unsigned long long* act; uint32_t* draws; uint16_t* cand; uint16_t* list; int16_t* prev; int32_t* acts;
-    int16_t* sl;     // static lives, staged for the whole launch
-    uint2* cq;       // per step: {x | y << 16 (sentinel when not in the world), dict-order stamp}
-    int32_t* ats;    // per step: closest-player key of a zombie / heal_closest agent
-    uint8_t* rk;     // per step: dict-order rank of a slot (255 when not in the world)
-    uint8_t* sor;    // per step: slot of a rank
-    uint32_t* zb;    // per step: closest-zombie key of a player slot
-    int32_t* scal;   // 8 ints: hand-off of the scalars to/from the out-of-line (re)initialisation
-    // warp-uniform registers
-    int32_t t, episode, deaths, zd, stampctr, flags, prev_zd, ep_steps;
+    uint32_t b;       // byte offset of this env's EnvS in zs_smem
+    int32_t t, episode, deaths, zd, nlive, flags, prev_zd, ep_steps;
     int32_t env; uint32_t env_global;
-    int32_t lane;
+    int32_t gl;       // lane within the group
+    uint32_t gm;      // member mask of the group
+    int32_t gshift;   // first lane of the group within the warp
 };
 // Env::flags: bit0 is state (ZS_S_FLAGS); the others live for one launch only
 #define FL_FRESH 1       // first step of a world: boxes/walls with life <= 0 are still present
 #define FL_DMG 2         // some box/wall has life != MAX_LIFE (else the observation needs no static patches)
 #define FL_SL_DIRTY 4    // static lives changed during this launch: write them back
+#define FL_DMG_OVER 8    // more than ZS_DMG_CAP damaged boxes/walls: scan instead of using the list
 
+// Bind the shared-memory views of `e` in the current scope (S: the struct; GRIDP/DEADP/SLP/CANDP: the tail).
+#define ZS_VIEWS                                                                                   \
+    EnvS<MPC>& S = *reinterpret_cast<EnvS<MPC>*>(zs_smem + e.b);                                     \
+    uint8_t* const GRIDP = zs_smem + e.b + sizeof(EnvS<MPC>);                                        \
+    uint32_t* const DEADP = reinterpret_cast<uint32_t*>(GRIDP + p.off_dead);                         \
+    int16_t* const SLP = reinterpret_cast<int16_t*>(GRIDP + p.off_sl);                               \
+    uint16_t* const CANDP = reinterpret_cast<uint16_t*>(GRIDP + p.off_cand);                         \
+    (void)S; (void)GRIDP; (void)DEADP; (void)SLP; (void)CANDP
+#define GRID(i) GRIDP[i]
+#define DEADW(i) DEADP[i]
+#define SL(i) SLP[i]
+#define CAND(i) CANDP[i]
+#define TXY(i) S.txy[i]
+#define TL(i) S.tl[i]
+#define TM(i) S.tm[i]
+#define RK(i) S.rk[i]
+#define SOR(i) S.sor[i]
+#define MVQ(i) S.mvq[i]
+#define DTYPE(i) S.dtype[i]
+#define DA(i) S.da[i]
+#define DB(i) S.db[i]
+#define ACT(i) S.act[i]
+#define DRAWS(i) S.draws[i]
+#define LIST(i) S.list[i]
+#define PREVL(i) S.prev[i]
+#define ACTS(i) S.acts[i]
+#define BK(i) S.bk[i]
+#define ZB(i) S.zb[i]
+#define SCALW(i) S.scal[i]
+#define MASKW(i) S.masks[i]
+#define DMG(i) S.dmg[i]
+
+// ---------------------------------------------------------------- lane-group primitives
+template <int G> __device__ __forceinline__ void gsync(const Env& e) { __syncwarp(e.gm); }
+template <int G> __device__ __forceinline__ unsigned gballot(const Env& e, bool pred) {
+    const unsigned m = __ballot_sync(e.gm, pred);
+    return G == 32 ? m : ((m >> e.gshift) & ((1u << (G & 31)) - 1u));
+}
+template <int G> __device__ __forceinline__ bool gany(const Env& e, bool pred) { return __any_sync(e.gm, pred); }
+template <int G> __device__ __forceinline__ int gbcast(const Env& e, int v, int src) { return __shfl_sync(e.gm, v, src, G); }
+template <int G> __device__ __forceinline__ int gadd(const Env& e, int v) { return __reduce_add_sync(e.gm, v); }
+template <int G> __device__ __forceinline__ uint32_t gminu(const Env& e, uint32_t v) { return __reduce_min_sync(e.gm, v); }
+
+__device__ __forceinline__ int xy_x(uint32_t xy) { return (int)(int16_t)(xy & 0xffffu); }
+__device__ __forceinline__ int xy_y(uint32_t xy) { return (int)xy >> 16; }
+__device__ __forceinline__ uint32_t xy_pack(int x, int y) { return (uint32_t)(uint16_t)x | ((uint32_t)y << 16); }
 
 __device__ __forceinline__ uint32_t draw_at(const ZsParams& p, const Env& e, uint32_t t_word, int k) {
-    uint32_t o[4];
-    philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)(k >> 2), p.key0, p.key1, o);
-    int w = k & 3;
-    return w == 0 ? o[0] : w == 1 ? o[1] : w == 2 ? o[2] : o[3];
+    return word_of(philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)(k >> 2), p.key0, p.key1), k & 3);
 }
 __device__ __forceinline__ int below(uint32_t u, int n) { return (int)__umulhi(u, (uint32_t)n); }
 
@@ -141,15 +207,14 @@ __device__ __forceinline__ bool g_is_thing(int g) { return g != G_EMPTY && g != 
 __device__ __forceinline__ bool g_is_static(int g) { return g == G_STATIC || g == G_STATIC_DMG; }
 
 // World.things.get((x, y)) as a grid byte; positions outside the map hold nothing
-__device__ __forceinline__ int grid_at(const ZsParams& p, const Env& e, int x, int y) {
+__device__ __forceinline__ int grid_at(const ZsParams& p, const uint8_t* GRIDP, int x, int y) {
     if ((unsigned)x >= (unsigned)p.W || (unsigned)y >= (unsigned)p.H) return G_EMPTY;
-    return e.grid[y * p.W + x];
+    return GRIDP[y * p.W + x];
 }
 __device__ __forceinline__ int dist2(int x1, int y1, int x2, int y2) {
-    int dx = x1 - x2, dy = y1 - y2;
+    const int dx = x1 - x2, dy = y1 - y2;
     return dx * dx + dy * dy;
 }
-__device__ __forceinline__ bool dead_bit(const Env& e, int c) { return (e.dead[c >> 5] >> (c & 31)) & 1u; }
 __device__ __forceinline__ bool objective_bit(const ZsParams& p, int c) {
     return (__ldg(p.objective_bits + (c >> 5)) >> (c & 31)) & 1u;
 }

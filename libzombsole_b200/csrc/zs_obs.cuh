@@ -3,11 +3,12 @@
 // World scope: template stream + ordered patches (obs_world_template / obs_world_patch below).
 // Surroundings scope: per-cell encoding of the agent-centred window from the occupancy grid.
 #pragma once
-#include "zs_device.cuh"
+#include "zs_world.cuh"
 
 struct CellInfo { int label, life, weapon, agent; };
 
-__device__ __forceinline__ CellInfo cell_info(const ZsParams& p, const Env& e, int c, int g) {
+ZS_TPL __device__ __forceinline__ CellInfo cell_info(const ZsParams& p, const Env& e, int c, int g) {
+    ZS_VIEWS;
     CellInfo ci;
     ci.life = 0; ci.weapon = 0; ci.agent = -1;
     if (g == G_EMPTY) ci.label = objective_bit(p, c) ? ZS_LABEL_OBJECTIVE : 0;
@@ -15,11 +16,11 @@ __device__ __forceinline__ CellInfo cell_info(const ZsParams& p, const Env& e, i
     else if (g > G_MAX_SLOT) {
         const int i = __ldg(p.cell_static + c);
         ci.label = __ldg(p.static_label + i);
-        ci.life = e.sl[i];
+        ci.life = SL(i);
     } else {
         const int s = g - 1;
-        ci.life = e.tl[s];
-        ci.weapon = e.tm[s] & 15;
+        ci.life = TL(s);
+        ci.weapon = TM(s) & 15;
         ci.label = s < p.P ? ZS_LABEL_PLAYER : s < p.P + p.A ? ZS_LABEL_AGENT : ZS_LABEL_ZOMBIE;
         ci.agent = s - p.P;
     }
@@ -41,8 +42,9 @@ __device__ __forceinline__ int channel_label(const ZsParams& p, const CellInfo& 
 // observation row with 128-bit loads/stores — 512 contiguous bytes per warp instruction — and no
 // per-cell work.  The stores are fire-and-forget, so the step kernel issues them BEFORE the world
 // transition and lets them drain underneath the latency-bound game logic.
-__device__ __forceinline__ void obs_world_template(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
-    const int lane = e.lane;
+ZS_TPL __device__ __forceinline__ void obs_world_template(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
+    ZS_CONSTS;
+    const int lane = e.gl;
     const int cells = p.cells;
     const bool channels = p.obs_enc == ZS_OBS_CHANNELS;
     if ((cells & 3) == 0) {
@@ -50,10 +52,10 @@ __device__ __forceinline__ void obs_world_template(const ZsParams& p, const Env&
         const uint4* to4 = (const uint4*)p.tmpl_obs;
         uint4* o4 = (uint4*)obs;
 #pragma unroll 4
-        for (int i = lane; i < n4; i += 32) __stcs(o4 + i, __ldg(to4 + i));
+        for (int i = lane; i < n4; i += G) __stcs(o4 + i, __ldg(to4 + i));
         if (channels) {
 #pragma unroll 4
-            for (int i = lane; i < n4; i += 32) {
+            for (int i = lane; i < n4; i += G) {
                 __stcs(o4 + n4 + i, __ldg(to4 + n4 + i));
                 __stcs(o4 + 2 * n4 + i, make_uint4(0, 0, 0, 0));
             }
@@ -61,7 +63,8 @@ __device__ __forceinline__ void obs_world_template(const ZsParams& p, const Env&
         return;
     }
     // maps whose cell count is not a multiple of 4 (an env's row is then not 16-byte aligned)
-    for (int c = lane; c < cells; c += 32) {
+#pragma unroll 1
+    for (int c = lane; c < cells; c += G) {
         __stcs(obs + c, __ldg(p.tmpl_obs + c));
         if (channels) { __stcs(obs + cells + c, __ldg(p.tmpl_obs + cells + c)); __stcs(obs + 2 * cells + c, 0); }
     }
@@ -76,34 +79,30 @@ __device__ __forceinline__ void obs_store_cell(const ZsParams& p, int32_t* obs, 
 // layering order of the reference (decorations under things, observation.py:41-42): damaged or destroyed
 // boxes/walls, then dead bodies, then the mobile things.  Each layer is separated by __syncwarp(), which
 // orders the stores of different lanes to the same address (and all of them after pass 1).
-__device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e, int32_t* obs) {
-    const int lane = e.lane;
+ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e, int32_t* obs) {
+    ZS_CONSTS; ZS_VIEWS;
+    const int lane = e.gl;
     const bool fresh = e.flags & FL_FRESH;
-    __syncwarp();
-    if (e.flags & FL_DMG) {  // launch-lifetime flag: no box/wall differs from its MAX_LIFE otherwise
-        const uint4* mx4 = (const uint4*)p.static_max;
+    gsync<G>(e);
+    if (e.flags & FL_DMG) {  // launch-lifetime: the boxes/walls whose life differs from MAX_LIFE (a short list)
+        const bool over = e.flags & FL_DMG_OVER;
+        const int n_list = over ? p.S : (int)DMG(0);
 #pragma unroll 1
-        for (int i = lane; i < (p.Sp >> 3); i += 32) {
-            const uint4 a = ((const uint4*)e.sl)[i];
-            const uint4 m = __ldg(mx4 + i);
-            if (a.x != m.x || a.y != m.y || a.z != m.z || a.w != m.w) {
-#pragma unroll 1
-                for (int q = 0; q < 8; ++q) {
-                    const int life = e.sl[i * 8 + q];
-                    if (life == __ldg(p.static_max + i * 8 + q)) continue;
-                    CellInfo ci;
-                    ci.life = life; ci.weapon = 0; ci.agent = -1;
-                    ci.label = __ldg(p.static_label + i * 8 + q);
-                    if (life <= 0 && !fresh) { ci.label = 0; ci.life = 0; }  // destroyed: gone from World.things
-                    obs_store_cell(p, obs, __ldg(p.static_cell + i * 8 + q), ci);
-                }
-            }
+        for (int i = lane; i < n_list; i += G) {
+            const int si = over ? i : (int)DMG(1 + i);
+            const int life = SL(si);
+            if (over && life == __ldg(p.static_max + si)) continue;
+            CellInfo ci;
+            ci.life = life; ci.weapon = 0; ci.agent = -1;
+            ci.label = __ldg(p.static_label + si);
+            if (life <= 0 && !fresh) { ci.label = 0; ci.life = 0; }  // destroyed: gone from World.things
+            obs_store_cell(p, obs, __ldg(p.static_cell + si), ci);
         }
-        __syncwarp();
+        gsync<G>(e);
     }
 #pragma unroll 1
-    for (int w = lane; w < p.dead_words; w += 32) {
-        uint32_t bits = e.dead[w];
+    for (int w = lane; w < p.dead_words; w += G) {
+        uint32_t bits = DEADW(w);
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
@@ -112,26 +111,32 @@ __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e,
             obs_store_cell(p, obs, w * 32 + b, ci);
         }
     }
-    __syncwarp();
+    gsync<G>(e);
 #pragma unroll 1
-    for (int s = lane; s < p.M; s += 32) {
-        if (!(e.tm[s] & 0x80)) continue;
+    for (int s = lane; s < p.M; s += G) {
+        const int m = TM(s);
+        if (!(m & 0x80)) continue;
         CellInfo ci;
-        ci.life = e.tl[s]; ci.weapon = e.tm[s] & 15; ci.agent = s - p.P;
+        ci.life = TL(s); ci.weapon = m & 15; ci.agent = s - p.P;
         ci.label = s < p.P ? ZS_LABEL_PLAYER : s < p.P + p.A ? ZS_LABEL_AGENT : ZS_LABEL_ZOMBIE;
-        obs_store_cell(p, obs, e.ty[s] * p.W + e.tx[s], ci);
+        const uint32_t xy = TXY(s);
+        obs_store_cell(p, obs, xy_y(xy) * p.W + xy_x(xy), ci);
     }
 }
 
 // surroundings window (observation.py:99-119): rows = y, columns = x, centred on the agent's
 // (possibly stale, if dead) position; out-of-bounds cells are a fresh Wall (observation.py:43-44,64-65)
-__device__ __forceinline__ void encode_surroundings(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
-    const int lane = e.lane;
+ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
+    ZS_CONSTS; ZS_VIEWS;
+    const int lane = e.gl;
     const int w = p.sw, half = p.sw >> 1, ww = p.sw * p.sw;
+#pragma unroll 1
     for (int a = 0; a < p.obs_count; ++a) {
-        const int ax = e.tx[p.P + a] - half, ay = e.ty[p.P + a] - half;
+        const uint32_t axy = TXY(p.P + a);
+        const int ax = xy_x(axy) - half, ay = xy_y(axy) - half;
         int32_t* o = obs + (size_t)a * p.obs_C * ww;
-        for (int i = lane; i < ww; i += 32) {
+#pragma unroll 1
+        for (int i = lane; i < ww; i += G) {
             const int r = i / w, c = i - r * w;
             const int x = ax + c, y = ay + r;
             CellInfo ci;
@@ -139,7 +144,7 @@ __device__ __forceinline__ void encode_surroundings(const ZsParams& p, const Env
                 ci.label = ZS_LABEL_WALL; ci.life = 200; ci.weapon = 0; ci.agent = -1;
             } else {
                 const int cell = y * p.W + x;
-                ci = cell_info(p, e, cell, e.grid[cell]);
+                ci = cell_info<MPC, G>(p, e, cell, GRID(cell));
             }
             if (p.obs_enc == ZS_OBS_SIMPLE) __stcs(o + i, encode_simple(ci));
             else {
@@ -151,7 +156,7 @@ __device__ __forceinline__ void encode_surroundings(const ZsParams& p, const Env
     }
 }
 
-__device__ __forceinline__ void encode_obs(const ZsParams& p, const Env& e, int32_t* obs) {
-    if (p.obs_scope == ZS_OBS_WORLD) { obs_world_template(p, e, obs); obs_world_patch(p, e, obs); }
-    else encode_surroundings(p, e, obs);
+ZS_TPL __device__ __forceinline__ void encode_obs(const ZsParams& p, const Env& e, int32_t* obs) {
+    if (p.obs_scope == ZS_OBS_WORLD) { obs_world_template<MPC, G>(p, e, obs); obs_world_patch<MPC, G>(p, e, obs); }
+    else encode_surroundings<MPC, G>(p, e, obs);
 }
