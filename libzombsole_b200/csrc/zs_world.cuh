@@ -180,24 +180,27 @@ __device__ __forceinline__ int target_of_cell(const ZsParams& p, int g, int cell
     return g <= G_MAX_SLOT ? g - 1 : p.M + (int)__ldg(p.cell_static + cell);
 }
 
-// A decided action, packed so that the sequential execute loop touches as little as possible:
-//   bits 0-7 actor | 8-10 kind | 11-26 a | 27-42 b | 43-49 range^2 | 50-56 lo | 57-62 n
-// kind: X_NOP (an action that can no longer have an effect but still takes part in the shuffle),
-// X_MOVE (a, b = destination, already known to be in bounds and one step away; bits 11-42 are the packed
-// x/y word), X_ATTACK_M / X_HEAL_M (a = mobile target slot; range is checked against current positions
-// at execute time), X_ATTACK_S / X_HEAL_S (a = static index, already known to be in range: neither end
-// can move before the actor acts).  lo/n: the draw is lo + randbelow(n).
+// A decided action, packed into one 64-bit word so that the sequential execute loop touches as little as
+// possible; everything that cannot change before the actor acts is resolved when the word is built.
+//   bits 0-2 kind, then per kind:
+//   X_NOP       an action that can no longer have an effect but still takes part in the shuffle
+//   X_MOVE      3-10 actor | 11 restore (dead body under the actor) | 16-31 destination cell | 32-47 current cell;
+//               the destination is already known to be in bounds and one step away; its packed x/y is in BK(actor)
+//   X_ATTACK_M / X_HEAL_M   3-10 mobile target slot | 11-17 range^2 | 18-24 lo | 25-30 n | 32-63 the actor's packed
+//               x/y (it cannot move before it acts); the range is checked against the target's CURRENT position
+//   X_ATTACK_S / X_HEAL_S   3-10 unused | 18-24 lo | 25-30 n | 32-47 static index; already known to be in range
+//   The draw of an attack / heal is lo + randbelow(n).
 #define X_NOP 0
 #define X_MOVE 1
 #define X_ATTACK_M 2
 #define X_HEAL_M 3
 #define X_ATTACK_S 4
 #define X_HEAL_S 5
-__device__ __forceinline__ unsigned long long pack_action(int actor, int kind, int a, int b, int r2, int lo, int n) {
-    return (unsigned long long)(uint32_t)actor | ((unsigned long long)(uint32_t)kind << 8) |
-           ((unsigned long long)(uint16_t)(int16_t)a << 11) | ((unsigned long long)(uint16_t)(int16_t)b << 27) |
-           ((unsigned long long)(uint32_t)r2 << 43) | ((unsigned long long)(uint32_t)lo << 50) |
-           ((unsigned long long)(uint32_t)n << 57);
+__device__ __forceinline__ unsigned long long pack_move(int actor, int restore, int c, int old) {
+    return (unsigned long long)(X_MOVE | (actor << 3) | (restore << 11) | (c << 16)) | ((unsigned long long)(uint32_t)old << 32);
+}
+__device__ __forceinline__ unsigned long long pack_hit(int kind, int target, int r2, int lo, int n, uint32_t hi) {
+    return (unsigned long long)(uint32_t)(kind | (target << 3) | (r2 << 11) | (lo << 18) | (n << 25)) | ((unsigned long long)hi << 32);
 }
 
 // number of set bits below `bit` in the rank bit-mask starting at word `word0`
@@ -383,6 +386,8 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     // the idle things before it (idle things are rare: usually the rank is the position).
     // Everything that cannot change before the actor acts is resolved here, in parallel.
     int cnt = 0, n_ah = 0;
+    unsigned long long my_word = X_NOP;  // ONE: this lane's action stays in registers until its shuffled position is known
+    int my_pos = -1;
 #pragma unroll 1
     for (int s0 = 0; s0 < (ONE ? 1 : (p.M)); s0 += G) {
         const int s = s0 + lane;
@@ -393,30 +398,36 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
 #pragma unroll 1
             for (int j = 0; j < p.M; ++j) pos -= (RK(j) < mine && DTYPE(j) == D_IDLE);
         }
-        if (type == D_IDLE) continue;
-        const int a = DA(s), b = DB(s);
-        const uint32_t xy = TXY(s);
-        const int x = xy_x(xy), y = xy_y(xy);
-        int kind = X_NOP, r2 = 0, dlo = 0, dn = 1;
-        if (type == D_MOVE) {  // in bounds and at most one step (core.py:149-153); occupancy is checked when it runs
-            if ((unsigned)a < (unsigned)p.W && (unsigned)b < (unsigned)p.H && dist2(x, y, a, b) <= 1) kind = X_MOVE;
-        } else {
-            const bool is_static = a >= p.M;
-            int mx = 100;
-            if (type == D_ATTACK) { const int w = TM(s) & 15; r2 = c_range2[w]; dlo = c_dmg_lo[w]; dn = c_dmg_n[w]; }
-            else {  // heal: randint(MAX_LIFE // 10, MAX_LIFE // 4) of the target's class, range 3 (core.py:194-198)
-                if (is_static) mx = max_life_of_label(__ldg(p.static_label + (a - p.M)));
-                r2 = 9; dlo = mx / 10; dn = mx / 4 - mx / 10 + 1;
+        unsigned long long word = X_NOP;
+        bool acting = type != D_IDLE;
+        if (acting) {
+            const int a = DA(s), b = DB(s);
+            const uint32_t xy = TXY(s);
+            const int x = xy_x(xy), y = xy_y(xy);
+            if (type == D_MOVE) {  // in bounds and at most one step (core.py:149-153); occupancy is checked when it runs
+                if ((unsigned)a < (unsigned)p.W && (unsigned)b < (unsigned)p.H && dist2(x, y, a, b) <= 1) {
+                    const int old = y * p.W + x;
+                    word = pack_move(s, (DEADW(old >> 5) >> (old & 31)) & 1u, b * p.W + a, old);
+                    BK(s) = xy_pack(a, b);
+                }
+            } else {
+                const bool is_static = a >= p.M;
+                int mx = 100, r2, dlo, dn;
+                if (type == D_ATTACK) { const int w = TM(s) & 15; r2 = c_range2[w]; dlo = c_dmg_lo[w]; dn = c_dmg_n[w]; }
+                else {  // heal: randint(MAX_LIFE // 10, MAX_LIFE // 4) of the target's class, range 3 (core.py:194-198)
+                    if (is_static) mx = max_life_of_label(__ldg(p.static_label + (a - p.M)));
+                    r2 = 9; dlo = mx / 10; dn = mx / 4 - mx / 10 + 1;
+                }
+                if (is_static) {
+                    const int cell = __ldg(p.static_cell + (a - p.M));
+                    const int gy = cell / p.W, gx = cell - gy * p.W;
+                    if (dist2(x, y, gx, gy) <= r2) { word = pack_hit(type == D_ATTACK ? X_ATTACK_S : X_HEAL_S, 0, 0, dlo, dn, (uint32_t)(a - p.M)); ++n_ah; }
+                } else { word = pack_hit(type == D_ATTACK ? X_ATTACK_M : X_HEAL_M, a, r2, dlo, dn, xy); ++n_ah; }
             }
-            if (is_static) {
-                const int cell = __ldg(p.static_cell + (a - p.M));
-                const int gy = cell / p.W, gx = cell - gy * p.W;
-                if (dist2(x, y, gx, gy) <= r2) kind = type == D_ATTACK ? X_ATTACK_S : X_HEAL_S;
-            } else kind = type == D_ATTACK ? X_ATTACK_M : X_HEAL_M;
+            ++cnt;
         }
-        ACT(pos) = pack_action(s, kind, kind >= X_ATTACK_S ? a - p.M : a, b, r2, dlo, dn);
-        ++cnt;
-        n_ah += kind >= X_ATTACK_M;
+        if (ONE) { my_word = word; my_pos = acting ? pos : -1; }
+        else if (acting) ACT(pos) = word;
     }
     const int L = gadd<G>(e, cnt);
     n_ah = gadd<G>(e, n_ah);
@@ -431,43 +442,57 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     for (int i = 1 + e.gl; i < L; i += G) DTYPE(i) = (uint8_t)below(DRAWS(nd + (L - 1 - i)), i + 1);
     gsync<G>(e);
 
-    // ---- random.shuffle + execute_actions: order-dependent by definition, run by lane 0
-    int k = nd + (L > 1 ? L - 1 : 0);
-    int nmv = 0;
-    if (lane == 0) {
+    // ---- random.shuffle (core.py:76).  The Fisher-Yates swaps are a fixed sequence once the partners are known,
+    // so every lane follows its own action through them in registers (if pos == i: pos = j; elif pos == j: pos = i)
+    // and stores it at its final position; with more actions than lanes, lane 0 swaps in shared memory.
+    if (ONE) {
 #pragma unroll 1
         for (int i = L - 1; i >= 1; --i) {
             const int j = DTYPE(i);
-            const unsigned long long tmp = ACT(i); ACT(i) = ACT(j); ACT(j) = tmp;
+            my_pos = my_pos == i ? j : (my_pos == j ? i : my_pos);
+        }
+        if (my_pos >= 0) ACT(my_pos) = my_word;
+        gsync<G>(e);
+    }
+    // ---- execute_actions (core.py:103-119): order-dependent by definition, run by the group's lane 0
+    int k = nd + (L > 1 ? L - 1 : 0);
+    int nmv = 0;
+    if (lane == 0) {
+        if (!ONE) {
+#pragma unroll 1
+            for (int i = L - 1; i >= 1; --i) {
+                const int j = DTYPE(i);
+                const unsigned long long tmp = ACT(i); ACT(i) = ACT(j); ACT(j) = tmp;
+            }
         }
         int n_touched = 0, fl = e.flags, deaths = e.deaths;
 #pragma unroll 1
         for (int i = 0; i < L; ++i) {
             const unsigned long long pk = ACT(i);
-            const int actor = (int)(pk & 0xff), kind = (int)((pk >> 8) & 7);
+            const uint32_t lo32 = (uint32_t)pk, hi32 = (uint32_t)(pk >> 32);
+            const int kind = lo32 & 7;
             if (kind == X_NOP) continue;
             if (kind == X_MOVE) {  // World.thing_move (core.py:140-166)
-                const uint32_t dxy = (uint32_t)(pk >> 11);
-                const int c = xy_y(dxy) * p.W + xy_x(dxy);
+                const int c = lo32 >> 16;
                 if (!g_is_thing(GRID(c))) {
-                    const uint32_t oxy = TXY(actor);
-                    const int old = xy_y(oxy) * p.W + xy_x(oxy);
-                    GRID(old) = ((DEADW(old >> 5) >> (old & 31)) & 1u) ? G_DEAD : G_EMPTY;
+                    const int actor = (lo32 >> 3) & 0xff;
+                    GRID(hi32 & 0xffffu) = (lo32 & 0x800u) ? G_DEAD : G_EMPTY;
                     GRID(c) = (uint8_t)(actor + 1);
-                    TXY(actor) = dxy;
+                    TXY(actor) = BK(actor);
                     MVQ(actor) = (uint8_t)nmv++;  // things[dest] = thing; del things[old]: goes last in the dict
                 }
                 continue;
             }
-            const int a = (int16_t)(pk >> 11);
-            const int r2 = (int)((pk >> 43) & 127), dlo = (int)((pk >> 50) & 127), dn = (int)((pk >> 57) & 63);
+            const int dlo = (lo32 >> 18) & 127, dn = (lo32 >> 25) & 63;
             if (kind <= X_HEAL_M) {  // mobile target: distance between CURRENT positions (core.py:176,194)
-                const uint32_t axy = TXY(actor), gxy = TXY(a);
-                if (dist2(xy_x(axy), xy_y(axy), xy_x(gxy), xy_y(gxy)) > r2) continue;
+                const int a = (lo32 >> 3) & 0xff;
+                const uint32_t gxy = TXY(a);
+                if (dist2(xy_x(hi32), xy_y(hi32), xy_x(gxy), xy_y(gxy)) > (int)((lo32 >> 11) & 127)) continue;
                 const int amount = dlo + below(DRAWS(k++), dn);
                 if (kind == X_ATTACK_M) TL(a) = (int16_t)(TL(a) - amount);
                 else { const int nl = TL(a) + amount; TL(a) = (int16_t)(nl < 100 ? nl : 100); }
             } else {
+                const int a = hi32 & 0xffffu;
                 const int amount = dlo + below(DRAWS(k++), dn);
                 if (kind == X_ATTACK_S) {
                     SL(a) = (int16_t)(SL(a) - amount);
