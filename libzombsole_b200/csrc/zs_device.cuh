@@ -53,6 +53,7 @@ struct ZsParams {
     int32_t n_ps, n_zs;
     int64_t obs_elems;
     uint8_t agent_weapons[ZS_MAX_AGENTS];
+    uint8_t bot_kinds[ZS_MAX_BOTS];
     int32_t agent_obs_ids[ZS_MAX_AGENTS];
     // ---- map tables (device, read-only)
     const int16_t* cell_static;    // [cells] static index or -1

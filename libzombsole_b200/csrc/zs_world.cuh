@@ -223,7 +223,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     const uint32_t t_word = (uint32_t)(e.t + 1);
 
     // ---- which players are in the world, and which of them look for their closest zombie
-    // (terminators always, terminator.py:10-14; agents for attack_closest, agent.py:41-47)
+    // (terminators and snipers always, terminator.py:10-14, sniper.py:10-16; agents for attack_closest, agent.py:41-47)
     bool humans = false;
     unsigned needz0 = 0, needz1 = 0;  // slots < NP <= 64
 #pragma unroll 1
@@ -232,7 +232,8 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         bool needz = false;
         if (s < NP && (TM(s) & 0x80)) {
             humans = true;
-            needz = s < p.P || ACTS(3 * (s - p.P)) == ZS_ACT_ATTACK_CLOSEST;
+            needz = s < p.P ? (p.bot_kinds[s] == ZS_KIND_TERMINATOR || p.bot_kinds[s] == ZS_KIND_SNIPER)
+                            : ACTS(3 * (s - p.P)) == ZS_ACT_ATTACK_CLOSEST;
         }
         const unsigned m = gballot<G>(e, needz);
         if (s0 == 0) needz0 = m; else needz1 = m;
@@ -323,6 +324,12 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                             else { type = D_ATTACK; a = p.M + (int)__ldg(p.cell_static + cy * p.W + cx); }
                         }
                     }
+                } else if (p.bot_kinds[s] == ZS_KIND_SNIPER) {  // Sniper.next_step (players/sniper.py:9-19)
+                    if (tg >= 0) { type = D_ATTACK; a = tg; }
+                } else if (p.bot_kinds[s] == ZS_KIND_TROLL) {   // Troll.next_step (players/troll.py:10-12)
+                    type = D_HEAL; a = s;
+                } else if (p.bot_kinds[s] == ZS_KIND_HAMSTER) { // Hamster.next_step (players/hamster.py:10-14)
+                    if (freemask) { type = D_WANDER; a = (int)freemask; any_wander = true; }
                 } else {  // Terminator.next_step (players/terminator.py:9-37)
                     if (tg < 0) { type = D_HEAL; a = s; }
                     else if (d2 > c_range2[TM(s) & 15]) {
@@ -360,14 +367,14 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     gsync<G>(e);
     int nd = 0;
     if (gany<G>(e, any_wander)) {
-        // wandering zombies draw random.choice(positions) in dict order (things.py:101-103)
+        // wandering zombies and hamsters draw random.choice(positions) in dict order (things.py:101-103, hamster.py:12-14)
         int mine = 0;
 #pragma unroll 1
         for (int s = e.gl; s < p.M; s += G) {
             if (DTYPE(s) != D_WANDER) continue;
             int rank = 0;
 #pragma unroll 1
-            for (int j = NP; j < p.M; ++j) rank += (DTYPE(j) == D_WANDER && RK(j) < RK(s));
+            for (int j = 0; j < p.M; ++j) rank += (DTYPE(j) == D_WANDER && RK(j) < RK(s));
             const unsigned fm = (unsigned)DA(s);
             int pick = below(draw_at(p, e, t_word, rank), __popc(fm));
             int d = 0;
@@ -709,7 +716,7 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
 #pragma unroll 1
     for (int s = e.gl; s < p.Mp; s += G) {
         int w = 0;
-        if (s < p.P) w = ZS_WEAPON_SHOTGUN;            // terminator.py:41-42
+        if (s < p.P) w = p.bot_kinds[s] == ZS_KIND_SNIPER ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN;  // sniper.py:23-24, terminator.py:41-42
         else if (s < NP) w = p.agent_weapons[s - p.P];
         else w = ZS_WEAPON_CLAWS;
         TM(s) = (uint8_t)(w == ZS_WEAPON_RANDOM ? 15 : w);
@@ -717,6 +724,17 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
         if (s < NP) TL(s) = 100;
     }
     gsync<G>(e);
+    // trolls and hamsters are created without a weapon: Player.__init__ draws random.choice([Gun, Shotgun, Rifle,
+    // Knife, Axe]) (things.py:115-116), in player_names order, before the agents are created (game.py:157-165)
+#pragma unroll 1
+    for (int b = 0; b < p.P; ++b) {
+        if (p.bot_kinds[b] == ZS_KIND_TROLL || p.bot_kinds[b] == ZS_KIND_HAMSTER) {
+            const int pick = below(draw_at(p, e, 0u, k), 5);
+            ++k;
+            if (lane == 0) TM(b) = (uint8_t)(pick == 0 ? ZS_WEAPON_GUN : pick == 1 ? ZS_WEAPON_SHOTGUN
+                                             : pick == 2 ? ZS_WEAPON_RIFLE : pick == 3 ? ZS_WEAPON_KNIFE : ZS_WEAPON_AXE);
+        }
+    }
     // agent_weapon="random": one random.choice per agent, in agent order (weapons.py:43)
 #pragma unroll 1
     for (int a = 0; a < p.A; ++a) {

@@ -57,7 +57,7 @@ ZSO_EXPORT void zso_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint
 }
 
 /* ------------------------------------------------------------------ types */
-enum { T_BOX = 0, T_WALL, T_ZOMBIE, T_TERMINATOR, T_AGENT };
+enum { T_BOX = 0, T_WALL, T_ZOMBIE, T_TERMINATOR, T_AGENT, T_SNIPER, T_TROLL, T_HAMSTER };
 enum { A_MOVE = 1, A_ATTACK = 2, A_HEAL = 3 };
 
 typedef struct Thing {
@@ -134,7 +134,7 @@ static int max_life(int type) {
     /* things.py:12,47,57,109 */
     switch (type) { case T_BOX: return 10; case T_WALL: return 200; default: return 100; }
 }
-static int is_player(int type) { return type == T_TERMINATOR || type == T_AGENT; }
+static int is_player(int type) { return type == T_TERMINATOR || type >= T_AGENT; }
 static int is_fighter(int type) { return type >= T_ZOMBIE; }
 
 /* ------------------------------------------------------------------ draws */
@@ -275,6 +275,30 @@ static int terminator_next_step(const ZsoHandle* h, Env* e, int self, Action* ou
     out->type = A_ATTACK; out->target = target; return 1;
 }
 
+/* Sniper.next_step (players/sniper.py:9-19): shoot the closest zombie wherever it is, idle without zombies */
+static int sniper_next_step(const ZsoHandle* h, Env* e, int self, Action* out) {
+    out->actor = self;
+    int target = closest_of_type(h, e, self, 0, 1, 0);
+    if (target < 0) return 0;
+    out->type = A_ATTACK; out->target = target; return 1;
+}
+/* Troll.next_step (players/troll.py:10-12) */
+static int troll_next_step(int self, Action* out) {
+    out->actor = self; out->type = A_HEAL; out->target = self; return 1;
+}
+/* Hamster.next_step (players/hamster.py:10-14): random.choice(possible_moves) */
+static int hamster_next_step(const ZsoHandle* h, Env* e, int self, Action* out) {
+    const Thing* me = &e->things[self];
+    int px[4], py[4], npos = 0;
+    for (int a = 0; a < 4; ++a) {
+        int x = me->x + ADJ_DX[a], y = me->y + ADJ_DY[a];
+        if (thing_at(h, e, x, y) < 0) { px[npos] = x; py[npos] = y; ++npos; }
+    }
+    if (!npos) return 0;
+    int i = (int)randbelow(h, e, (uint32_t)npos);
+    out->actor = self; out->type = A_MOVE; out->dx = px[i]; out->dy = py[i]; return 1;
+}
+
 /* Agent.next_step (players/agent.py:28-96) */
 static int agent_next_step(const ZsoHandle* h, Env* e, int self, const int32_t act[3], Action* out) {
     const Thing* me = &e->things[self];
@@ -411,10 +435,22 @@ static void initialize_world(const ZsoHandle* h, Env* e, int env_local, int epis
     for (int c = 0; c < h->cells; ++c) { e->grid[c] = -1; e->deco[c] = h->objective[c] ? ZS_LABEL_OBJECTIVE : 0; }
     for (int i = 0; i < h->S; ++i) world_insert(h, e, i); /* same objects: life persists (game.py:154-155) */
     int32_t ids[ZS_MAX_SLOTS];
-    /* bots (create_player; terminator always carries a Shotgun, terminator.py:41-42) */
+    /* bots (create_player, game.py:157-159): terminator carries a Shotgun (terminator.py:41-42), sniper a Rifle
+       (sniper.py:23-24); troll and hamster are created without a weapon and Player.__init__ draws
+       random.choice([Gun, Shotgun, Rifle, Knife, Axe]) (things.py:115-116) */
     for (int b = 0; b < h->P; ++b) {
         Thing* t = &e->things[h->S + b];
-        t->type = T_TERMINATOR; t->weapon = ZS_WEAPON_SHOTGUN; t->life = 100; t->in_world = 0;
+        t->life = 100; t->in_world = 0;
+        switch (h->cfg.bot_kinds[b]) {
+            case ZS_KIND_SNIPER: t->type = T_SNIPER; t->weapon = ZS_WEAPON_RIFLE; break;
+            case ZS_KIND_TROLL: case ZS_KIND_HAMSTER: {
+                static const uint8_t choices[5] = { ZS_WEAPON_GUN, ZS_WEAPON_SHOTGUN, ZS_WEAPON_RIFLE, ZS_WEAPON_KNIFE, ZS_WEAPON_AXE };
+                t->type = h->cfg.bot_kinds[b] == ZS_KIND_TROLL ? T_TROLL : T_HAMSTER;
+                t->weapon = choices[randbelow(h, e, 5)];
+                break;
+            }
+            default: t->type = T_TERMINATOR; t->weapon = ZS_WEAPON_SHOTGUN; break;
+        }
         ids[b] = h->S + b;
     }
     /* agents (create_agent -> WeaponFactory, weapons.py:28-45); "random" draws here */
@@ -454,8 +490,8 @@ static void cell_codes(const ZsoHandle* h, const Env* e, int x, int y, int* labe
             case T_BOX: *label = ZS_LABEL_BOX; break;
             case T_WALL: *label = ZS_LABEL_WALL; break;
             case T_ZOMBIE: *label = ZS_LABEL_ZOMBIE; break;
-            case T_TERMINATOR: *label = ZS_LABEL_PLAYER; break;
-            default: *label = ZS_LABEL_AGENT; *agent_index = t->agent_index; break;
+            case T_AGENT: *label = ZS_LABEL_AGENT; *agent_index = t->agent_index; break;
+            default: *label = ZS_LABEL_PLAYER; break;
         }
         return;
     }
@@ -593,6 +629,9 @@ static void env_step(ZsoHandle* h, Env* e, int env_local, const int32_t* actions
         switch (e->things[id].type) {
             case T_ZOMBIE: ok = zombie_next_step(h, e, id, &act); break;
             case T_TERMINATOR: ok = terminator_next_step(h, e, id, &act); break;
+            case T_SNIPER: ok = sniper_next_step(h, e, id, &act); break;
+            case T_TROLL: ok = troll_next_step(id, &act); break;
+            case T_HAMSTER: ok = hamster_next_step(h, e, id, &act); break;
             default: ok = agent_next_step(h, e, id, acts[e->things[id].agent_index], &act); break;
         }
         if (ok) e->actions[n_act++] = act;

@@ -42,6 +42,8 @@ PLAN = {
     "multi_fort_32p": (1, 40, 0),
     "survival_minz": (2, 100, 40),
     "minz_allcells": (2, 80, 0),
+    "bots_mixed": (2, 60, 0),
+    "bots_hamsters": (2, 100, 0),
 }
 
 

@@ -49,6 +49,13 @@ CONFIGS = {
     "survival_minz": dict(kind="single", rules_name="survival", player_names=["terminator"], map_name="arduino",
                           agent_ids=[0], agent_weapons="random", initial_zombies=5, minimum_zombies=8,
                           observation_scope="world", observation_position_encoding="simple"),
+    # the other scripted players: sniper, troll, hamster (random default weapons, decide-phase draws)
+    "bots_mixed": dict(kind="single", rules_name="extermination", player_names=["sniper", "troll", "hamster", "terminator"],
+                       map_name="fort", agent_ids=[0], agent_weapons="gun", initial_zombies=25, minimum_zombies=0,
+                       observation_scope="surroundings:15", observation_position_encoding="channels"),
+    "bots_hamsters": dict(kind="multi", rules_name="survival", player_names=["hamster", "hamster", "sniper"],
+                          map_name="hallway", agent_ids=["0", "1"], agent_weapons="knife", initial_zombies=6,
+                          minimum_zombies=4, surroundings_width=11),
     "minz_allcells": dict(kind="multi", rules_name="extermination", player_names=[], map_name="village_for_evacuation",
                           agent_ids=["0", "1"], agent_weapons="random", initial_zombies=4, minimum_zombies=6,
                           surroundings_width=21),
