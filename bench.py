@@ -45,6 +45,16 @@ ENV_KW = dict(rules_name="extermination", player_names=["terminator", "terminato
 FALLBACK_HBM_GBS = 6650.0
 
 
+def ncu_traffic_per_env_step():
+    """DRAM bytes per env-step of the step kernel from the committed ncu --set full capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_env_step"]), d["capture"]
+    except Exception:
+        return None, None
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -284,6 +294,7 @@ def run_ours(args, rank, world, local_rank):
         total_envs = N * world
         value = total_envs * K / (fused_ms * 1e-3)
         achieved = value * B_ALG / world / 1e9
+        traffic_per, traffic_src = ncu_traffic_per_env_step()
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": fused_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -298,7 +309,8 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": N * 4, "d2h_bytes_per_step": obs_bytes + N * 8 + 2 * N,
                     "api": "ZombsoleVectorEnv.step(pinned host actions) + obs/reward/flags copied to pinned host"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "zs_sim_kernel<MODE_STEP>",
+                         "traffic": None if traffic_per is None else traffic_per * N * K,
+                         "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "zs_sim_kernel<MODE_STEP>",
                          "algorithmic_bytes_per_env_step": B_ALG,
                          "launch_ms": fused_ms, "env_steps_per_launch": N * K},
             "gpu_launches": launches,
