@@ -56,6 +56,10 @@ CONFIGS = {
     "bots_hamsters": dict(kind="multi", rules_name="survival", player_names=["hamster", "hamster", "sniper"],
                           map_name="hallway", agent_ids=["0", "1"], agent_weapons="knife", initial_zombies=6,
                           minimum_zombies=4, surroundings_width=11),
+    # slot capacity 256: 8 agents + 2 bots + 236 zombies on the biggest stock map with zombie spawns
+    "fort_max_slots": dict(kind="multi", rules_name="extermination", player_names=["terminator", "sniper"], map_name="fort",
+                           agent_ids=[str(i) for i in range(8)], agent_weapons=["shotgun", "axe"], initial_zombies=236,
+                           minimum_zombies=0, surroundings_width=7),
     "minz_allcells": dict(kind="multi", rules_name="extermination", player_names=[], map_name="village_for_evacuation",
                           agent_ids=["0", "1"], agent_weapons="random", initial_zombies=4, minimum_zombies=6,
                           surroundings_width=21),

@@ -78,7 +78,7 @@ CASES = [
     ("gym_v0_alone", 64, 80, 0), ("gym_surroundings", 32, 60, 0), ("surroundings_channels", 32, 80, 0),
     ("c3_city_evac", 32, 120, 0), ("village_evac_mixed", 16, 100, 0), ("c4_maze_safehouse", 8, 40, 0),
     ("safehouse_small", 32, 120, 0), ("multi_boxed_2p", 64, 80, 0), ("multi_fort_32p", 4, 30, 0),
-    ("survival_minz", 32, 120, 25), ("minz_allcells", 16, 80, 0), ("bots_mixed", 16, 60, 0), ("bots_hamsters", 32, 120, 0),
+    ("survival_minz", 32, 120, 25), ("minz_allcells", 16, 80, 0), ("bots_mixed", 16, 60, 0), ("bots_hamsters", 32, 120, 0), ("fort_max_slots", 3, 25, 0),
 ]
 
 
