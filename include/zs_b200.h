@@ -111,7 +111,8 @@ enum {
     ZS_F_X = 0,          /* int16 [N, slot_pitch]   */
     ZS_F_Y,              /* int16 [N, slot_pitch]   */
     ZS_F_LIFE,           /* int16 [N, slot_pitch]   */
-    ZS_F_STAMP,          /* int32 [N, slot_pitch]   dict-order stamp (smaller = earlier in World.things) */
+    ZS_F_STAMP,          /* int32 [N, slot_pitch]   dict-order stamp: any values whose ORDER among the slots in the world is
+                            the World.things iteration order (smaller = earlier); the library writes ranks 0..n-1 */
     ZS_F_META,           /* uint8 [N, slot_pitch]   bit7 = in World.things, bits0-3 = weapon code */
     ZS_F_PREV_LIFE,      /* int16 [N, agent_pitch]  reward tracker's agents_life (reward.py:21,27,33) */
     ZS_F_STATIC_LIFE,    /* int16 [N, static_pitch] persists across resets (game.py:154-155) */
@@ -124,7 +125,7 @@ enum {
     ZS_S_EPISODE,        /* world initialisations so far (0 = constructor) */
     ZS_S_DEATHS,         /* World.deaths */
     ZS_S_ZOMBIE_DEATHS,  /* World.zombie_deaths */
-    ZS_S_STAMP_COUNTER,  /* next dict-order stamp */
+    ZS_S_STAMP_COUNTER,  /* number of mobile things in World.things (= the next dict-order rank) */
     ZS_S_FLAGS,          /* bit0: fresh world (statics with life<=0 still present until the first clean) */
     ZS_S_PREV_ZOMBIE_DEATHS, /* reward tracker's zombie_deaths (reward.py:22,28,34) */
     ZS_S_EPISODE_STEPS,  /* steps since the last world init (TimeLimit) */
