@@ -41,6 +41,15 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
     e.gm = G == 32 ? 0xffffffffu : (0xffffu << e.gshift);
     const int slot = wid * EPW + (wlane / G);
     const int env = blockIdx.x * (ZS_WPC * EPW) + slot;
+    if (p.tmpl_smem_off >= 0) {
+        // stage the pristine observation planes once per CTA: the source of the per-step TMA bulk copies
+        uint4* dst = reinterpret_cast<uint4*>(zs_smem + p.tmpl_smem_off);
+        const uint4* src = reinterpret_cast<const uint4*>(p.tmpl_obs);
+        const int n4 = p.cells >> 2, nsrc = (p.tmpl_planes > 1 ? 2 : 1) * n4;
+        for (int i = threadIdx.x; i < p.tmpl_planes * n4; i += blockDim.x) dst[i] = i < nsrc ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        __syncthreads();
+    }
     if (env >= p.N) return;
     e.b = (uint32_t)slot * (uint32_t)p.smem_per_env;
     e.env = env; e.env_global = p.env_base + (uint32_t)env;
@@ -318,15 +327,18 @@ extern "C" __attribute__((visibility("default"))) int zs_layout(const ZsConfig* 
 
 template <int MODE>
 static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
-    const dim3 grid((h->p.N + h->envs_per_cta - 1) / h->envs_per_cta), block(ZS_WPC * 32);
-    switch (h->p.mpc) {
+    // staging the observation template for the TMA pays off when a launch runs several steps
+    ZsParams pp = h->p;
+    if (MODE != MODE_STEP || io.n_steps < 4) pp.tmpl_smem_off = -1;
+    const dim3 grid((pp.N + h->envs_per_cta - 1) / h->envs_per_cta), block(ZS_WPC * 32);
+    switch (pp.mpc) {
         case 16:
-            if (h->lanes_per_env == 16) zs_sim_kernel<MODE, 16, 16><<<grid, block, h->smem_bytes, st>>>(h->p, io);
-            else zs_sim_kernel<MODE, 16, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io);
+            if (h->lanes_per_env == 16) zs_sim_kernel<MODE, 16, 16><<<grid, block, h->smem_bytes, st>>>(pp, io);
+            else zs_sim_kernel<MODE, 16, 32><<<grid, block, h->smem_bytes, st>>>(pp, io);
             break;
-        case 32: zs_sim_kernel<MODE, 32, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io); break;
-        case 128: zs_sim_kernel<MODE, 128, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io); break;
-        default: zs_sim_kernel<MODE, 256, 32><<<grid, block, h->smem_bytes, st>>>(h->p, io); break;
+        case 32: zs_sim_kernel<MODE, 32, 32><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
+        case 128: zs_sim_kernel<MODE, 128, 32><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
+        default: zs_sim_kernel<MODE, 256, 32><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
     }
 }
 template <int MPC, int G>
@@ -454,6 +466,16 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     }
     h->envs_per_cta = ZS_WPC * (32 / h->lanes_per_env);
     h->smem_bytes = p.smem_per_env * h->envs_per_cta;
+    p.tmpl_smem_off = -1; p.tmpl_planes = 0;
+    if (p.obs_scope == ZS_OBS_WORLD && (p.cells & 3) == 0) {
+        const int planes = p.obs_enc == ZS_OBS_CHANNELS ? 3 : 1;
+        const int bytes = planes * p.cells * 4;
+        // keep at least 6 CTAs per SM resident
+        if ((h->smem_bytes + bytes + 1024) * 6 <= (int)prop.sharedMemPerMultiprocessor && !getenv("ZS_NO_TMA")) {
+            p.tmpl_smem_off = h->smem_bytes; p.tmpl_planes = planes;
+            h->smem_bytes += bytes;
+        }
+    }
     if (h->smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
     if (int rc2 = set_smem_attr(p.mpc, h->lanes_per_env, h->smem_bytes)) { zs_destroy(h); return rc2; }
     *out = h;

@@ -73,6 +73,8 @@ struct ZsParams {
     int32_t off_dead, off_sl, off_cand;
     int32_t cand_cap;
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
+    int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
+    int32_t tmpl_planes;           // planes staged there: 1 (simple) or 3 (channels: label, life, zeros)
     int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
 };
 
@@ -120,15 +122,15 @@ struct alignas(16) EnvS {
     uint32_t txy[MPC];                      // x | y << 16 (int16 each)
     uint32_t bk[MPC];                       // per step: closest-player key of a zombie / heal_closest agent
     uint32_t draws[3 * MPC + 16];           // per step: the draws, 4 per Philox block
-    uint32_t zb[ZS_NP_MAX];                 // per step: closest-zombie key of a player slot
+    uint32_t zb[MPC < ZS_NP_MAX ? MPC : ZS_NP_MAX];  // per step: closest-zombie key of a player slot
     int32_t scal[8];                        // scalar hand-off around out-of-line functions
-    int32_t acts[3 * ZS_MAX_AGENTS];        // agent actions of the step (type, dx, dy)
+    int32_t acts[3 * (MPC < ZS_MAX_AGENTS ? MPC : ZS_MAX_AGENTS) + 1];  // agent actions of the step (type, dx, dy)
     uint32_t masks[2 * ((MPC + 31) / 32) + 2];  // rank bit-masks: stayers, then movers
     int16_t tl[MPC];                        // life
     int16_t da[MPC];
     int16_t db[MPC];
     uint16_t list[MPC];
-    int16_t prev[ZS_MAX_AGENTS];            // reward tracker's agents_life
+    int16_t prev[MPC < ZS_MAX_AGENTS ? MPC : ZS_MAX_AGENTS];  // reward tracker's agents_life
     uint16_t dmg[ZS_DMG_CAP + 8];           // dmg[0] = count, dmg[1..] = damaged static indices
     uint8_t tm[MPC];                        // bit7 in world, bits0-3 weapon code
     uint8_t rk[MPC];                        // dict-order rank among the things in the world (RK_NONE if absent)
@@ -183,6 +185,15 @@ struct Env {
 #define SCALW(i) S.scal[i]
 #define MASKW(i) S.masks[i]
 #define DMG(i) S.dmg[i]
+
+// ---------------------------------------------------------------- TMA bulk copies (shared -> global)
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------- lane-group primitives
 template <int G> __device__ __forceinline__ void gsync(const Env& e) { __syncwarp(e.gm); }

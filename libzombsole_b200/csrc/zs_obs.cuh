@@ -38,15 +38,27 @@ __device__ __forceinline__ int channel_label(const ZsParams& p, const CellInfo& 
 }
 
 // World scope, pass 1: the observation of the pristine static layer (boxes, walls, objectives) is the
-// same for every env and every step, so it is streamed from the L1-resident template to the env's
-// observation row with 128-bit loads/stores — 512 contiguous bytes per warp instruction — and no
-// per-cell work.  The stores are fire-and-forget, so the step kernel issues them BEFORE the world
-// transition and lets them drain underneath the latency-bound game logic.
+// same for every env and every step.  It is staged once per CTA in shared memory and copied to the env's
+// observation row by the TMA (cp.async.bulk shared -> global, one instruction per plane per step); when the
+// row is not 16-byte aligned (cell count not a multiple of 4) or the template does not fit, it is streamed
+// from the L1-resident template with 128-bit loads/stores instead.  Either way it is issued BEFORE the
+// world transition and drains underneath the latency-bound game logic.
 ZS_TPL __device__ __forceinline__ void obs_world_template(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
     ZS_CONSTS;
     const int lane = e.gl;
     const int cells = p.cells;
     const bool channels = p.obs_enc == ZS_OBS_CHANNELS;
+    if (p.tmpl_smem_off >= 0) {
+        // TMA: the group's lane 0 issues one bulk copy per plane from the CTA-shared template to the env's row —
+        // no per-lane loads/stores at all.  obs_world_patch waits for the group before it patches cells.
+        if (lane == 0) {
+            const unsigned char* t = zs_smem + p.tmpl_smem_off;
+            const uint32_t plane = (uint32_t)cells * 4u;
+            for (int c = 0; c < p.tmpl_planes; ++c) bulk_store(obs + (size_t)c * cells, t + (size_t)c * plane, plane);
+            bulk_commit();
+        }
+        return;
+    }
     if ((cells & 3) == 0) {
         const int n4 = cells >> 2;
         const uint4* to4 = (const uint4*)p.tmpl_obs;
@@ -83,6 +95,7 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const 
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl;
     const bool fresh = e.flags & FL_FRESH;
+    if (p.tmpl_smem_off >= 0 && lane == 0) bulk_wait_all();  // pass 1 (TMA) has landed before any cell is patched
     gsync<G>(e);
     if (e.flags & FL_DMG) {  // launch-lifetime: the boxes/walls whose life differs from MAX_LIFE (a short list)
         const bool over = e.flags & FL_DMG_OVER;
