@@ -539,6 +539,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
 
     // ---- clean_dead_things (core.py:121-138)
     int nd_all = 0, nd_z = 0;
+    const bool fresh_scan = (e.flags & FL_FRESH) && (e.flags & FL_DMG);
     if (e.flags & FL_FRESH) {  // first step of this world: every box/wall with life <= 0 leaves now
         if (e.flags & FL_DMG) {
             const bool over = e.flags & FL_DMG_OVER;
@@ -554,7 +555,44 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         }
         e.flags &= ~FL_FRESH;
     }
-        for (int w = e.gl; w < 2 * rw; w += G) MASKW(w) = 0u;
+    if constexpr (ONE) {
+        // every slot has its own lane: deaths, dead bodies and the new dict order in one pass.  Survivors that
+        // did not move keep their relative order, the movers follow in move order (re-inserted at the end,
+        // core.py:158-159); the two rank bit-masks come from redux.sync.or.
+        const int s = lane;
+        const int r = s < p.M ? RK(s) : RK_NONE;
+        const bool was = r != RK_NONE;
+        const bool dead = was && TL(s) <= 0;
+        if (dead) {
+            const uint32_t xy = TXY(s);
+            const int c = xy_y(xy) * p.W + xy_x(xy);
+            GRID(c) = G_DEAD;                         // DeadBody overwrites any decoration (core.py:30-31,126-128)
+            atomicOr(&DEADW(c >> 5), 1u << (c & 31));
+            TM(s) &= 0x7f;
+        }
+        const unsigned dead_m = gballot<G>(e, dead);
+        e.deaths += __popc(dead_m) + (fresh_scan ? gadd<G>(e, nd_all) : 0);
+        e.zd += __popc(dead_m >> NP);
+        if (nmv > 0 || dead_m) {
+            const int q = was ? MVQ(s) : RK_NONE;
+            const bool alive = was && !dead;
+            const unsigned stay_m = __reduce_or_sync(e.gm, (alive && q == RK_NONE) ? (1u << r) : 0u);
+            const unsigned move_m = __reduce_or_sync(e.gm, (alive && q != RK_NONE) ? (1u << q) : 0u);
+            if (was) {
+                int nr = RK_NONE;
+                if (alive) {
+                    nr = q == RK_NONE ? __popc(stay_m & ((1u << r) - 1u)) : __popc(stay_m) + __popc(move_m & ((1u << q) - 1u));
+                    SOR(nr) = (uint8_t)s;
+                }
+                RK(s) = (uint8_t)nr;
+                MVQ(s) = RK_NONE;
+            }
+            e.nlive = __popc(stay_m) + __popc(move_m);
+        }
+        gsync<G>(e);
+        return k;
+    } else {
+    for (int w = e.gl; w < 2 * rw; w += G) MASKW(w) = 0u;
     gsync<G>(e);
 #pragma unroll 1
     for (int s = e.gl; s < p.M; s += G) {
@@ -585,7 +623,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         for (int w = 0; w < rw; ++w) stayers += __popc(MASKW(w));
         int nl = 0;
 #pragma unroll 1
-        for (int s0 = 0; s0 < (ONE ? 1 : (p.M)); s0 += G) {
+        for (int s0 = 0; s0 < p.M; s0 += G) {
             const int s = s0 + lane;
             int r = s < p.M ? RK(s) : RK_NONE;
             if (r != RK_NONE) {
@@ -604,6 +642,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         gsync<G>(e);
     }
     return k;
+    }
 }
 
 // ---------------------------------------------------------------- World.spawn_in_random (core.py:40-66)
