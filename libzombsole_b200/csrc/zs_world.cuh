@@ -9,9 +9,6 @@
 #define ZS_CONSTS                                   \
     constexpr bool ONE = MPC <= G;                  \
     (void)ONE
-// lane-strided loop over n items / round loop over the slots (a single pass when ONE)
-#define FOR_LANES(i, n) _Pragma("unroll 1") for (int i = e.gl; i < (n); i += G)
-#define FOR_ROUNDS(s0, n) _Pragma("unroll 1") for (int s0 = 0; s0 < (ONE ? 1 : (n)); s0 += G)
 
 // identity of a lane group, passed by value to the out-of-line functions (keeps the caller's Env in registers)
 struct GrpId { uint32_t b; int32_t env; int32_t gl; uint32_t gm; int32_t gshift; };
