@@ -60,6 +60,10 @@ CONFIGS = {
     "fort_max_slots": dict(kind="multi", rules_name="extermination", player_names=["terminator", "sniper"], map_name="fort",
                            agent_ids=[str(i) for i in range(8)], agent_weapons=["shotgun", "axe"], initial_zombies=236,
                            minimum_zombies=0, surroundings_width=7),
+    # edge: no zombies at all (extermination ends on the first step; every episode is one step long)
+    "no_zombies": dict(kind="single", rules_name="extermination", player_names=["terminator"], map_name="hallway",
+                       agent_ids=[0], agent_weapons="axe", initial_zombies=0, minimum_zombies=0,
+                       observation_scope="world", observation_position_encoding="channels"),
     "minz_allcells": dict(kind="multi", rules_name="extermination", player_names=[], map_name="village_for_evacuation",
                           agent_ids=["0", "1"], agent_weapons="random", initial_zombies=4, minimum_zombies=6,
                           surroundings_width=21),

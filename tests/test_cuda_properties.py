@@ -101,6 +101,24 @@ def test_fused_rollout_equals_single_steps(name, N):
         e.close()
 
 
+@pytest.mark.parametrize("name,N,mes", [("c1_bridge_ext", 1024, 7), ("gym_v0_alone", 777, 3), ("multi_boxed_2p", 300, 5)])
+def test_time_limit_inside_fused_rollout_matches_oracle(name, N, mes):
+    """gymnasium's TimeLimit (max_episode_steps) truncates and re-initialises inside one fused launch."""
+    from oracle import oracle as orc
+    K = 40
+    eng, cfg, m = engine(name, N, seed=(1 << 40) + 17, base=9, mes=mes)
+    obs = eng.new_obs()
+    rew, term, trunc = eng.new_outputs(K)
+    eng.rollout(K, 3, None, abi.ACTIONS_DISCRETE, obs, rew, term, trunc)
+    ref = orc.OracleEnv(cfg, m)
+    o, r, te, tr = ref.rollout_synthetic(K, 3)
+    assert np.array_equal(obs.cpu().numpy().reshape(N, -1), o)
+    assert np.array_equal(rew.cpu().numpy().view(np.uint64).reshape(r.shape), r.view(np.uint64))
+    assert np.array_equal(term.cpu().numpy(), te) and np.array_equal(trunc.cpu().numpy(), tr)
+    assert tr.sum() >= N * (K // mes) // 2  # truncations did happen
+    eng.close()
+
+
 def test_shard_independence():
     """Env g evolves identically whether it is env g of one batch or env 0 of a shard based at g."""
     K = 40
