@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
             life_before[r] = a < A ? PREVL(a) : 0;
         }
         const int zd_before = e.prev_zd;
+        const int life_prev0 = PREVL(0);
         gsync<G>(e);
         if (step + 1 < io.n_steps) fetch_action(step + 1);
 
@@ -132,13 +133,18 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
             const int a = lane + r * G;
             life_now[r] = a < A ? TL(p.P + a) : 0;
             rew[r] = 0.0;
-            if (!p.obs_per_agent) { sum_prev += gadd<G>(e, life_before[r]); sum_new += gadd<G>(e, life_now[r]); }
-            else if (a < A && (life_before[r] != life_now[r] || zd_before != e.zd))
+            if (!p.obs_per_agent) {
+                if (A > 1) { sum_prev += gadd<G>(e, life_before[r]); sum_new += gadd<G>(e, life_now[r]); }
+            } else if (a < A && (life_before[r] != life_now[r] || zd_before != e.zd))
                 rew[r] = __dsub_rn(total_reward(e.zd, life_now[r]), total_reward(zd_before, life_before[r]));
-            if (a < A) PREVL(a) = (int16_t)life_now[r];
         }
-        if (!p.obs_per_agent && (sum_prev != sum_new || zd_before != e.zd))
-            rew[0] = __dsub_rn(total_reward(e.zd, sum_new), total_reward(zd_before, sum_prev));
+        if (!p.obs_per_agent) {
+            if (A == 1) { sum_prev = life_prev0; sum_new = TL(p.P); }  // one agent: every lane reads the same two words
+            if (sum_prev != sum_new || zd_before != e.zd)
+                rew[0] = __dsub_rn(total_reward(e.zd, sum_new), total_reward(zd_before, sum_prev));
+        }
+#pragma unroll
+        for (int r = 0; r < AR; ++r) { const int a = lane + r * G; if (a < A) PREVL(a) = (int16_t)life_now[r]; }
         e.prev_zd = e.zd;
         gsync<G>(e);
 
