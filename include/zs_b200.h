@@ -218,6 +218,10 @@ int zs_episode_stats(ZsHandle* h, int64_t* out_dev, int32_t reset, void* stream)
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches). */
 int64_t zs_launch_count(const ZsHandle* h);
 
+/* Lanes of a warp that work on one env on this handle: 32, or 16 (two envs per warp) for worlds of at
+ * most 16 things in batches larger than one resident wave (diagnostics / tests). */
+int32_t zs_lanes_per_env(const ZsHandle* h);
+
 #ifdef __cplusplus
 }
 #endif

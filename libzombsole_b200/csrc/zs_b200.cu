@@ -33,6 +33,8 @@ __device__ __forceinline__ void discrete_to_action(const ZsParams& p, int id, in
 template <int MODE, int MPC, int G>
 __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     ZS_CONSTS;
+    // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
+    constexpr bool CV = MODE == MODE_STEP;
     constexpr int EPW = 32 / G;  // envs per warp
     const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     Env e;
@@ -59,18 +61,18 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
     if (MODE == MODE_RESET) {
         if (io.env_mask && !io.env_mask[env]) return;
         // slots keep their last position/life until re-placed; bring them in so the store is complete
-        load_state<MPC, G>(p, e);
-        const int k = initialize_world<MPC, G>(p, id_of(e), e.episode + 1, e.flags);
-        scalars_from_smem<MPC, G>(p, e);
+        load_state<MPC, G, CV>(p, e);
+        const int k = initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
+        scalars_from_smem<MPC, G, CV>(p, e);
         if (io.draws && lane == 0) io.draws[env] = k;
-        if (io.obs) encode_obs<MPC, G>(p, e, io.obs + (size_t)env * p.obs_elems);
-        store_state<MPC, G>(p, e);
+        if (io.obs) encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
+        store_state<MPC, G, CV>(p, e);
         return;
     }
-    load_state<MPC, G>(p, e);
-    build_grid<MPC, G>(p, id_of(e), e.flags);
+    load_state<MPC, G, CV>(p, e);
+    build_grid<MPC, G, false>(p, id_of(e), e.flags);
     if (MODE == MODE_ENCODE) {
-        encode_obs<MPC, G>(p, e, io.obs + (size_t)env * p.obs_elems);
+        encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
         return;
     }
 
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
             obs_out = io.obs + ((size_t)oslot * p.N + env) * p.obs_elems;
             if (++oslot >= io.obs_slots) oslot = 0;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
-            if (world_obs) obs_world_template<MPC, G>(p, e, obs_out);
+            if (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
         }
         // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
         unsigned alive_before = 0;
@@ -112,15 +114,17 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
         for (int r = 0; r < AR; ++r) {
             const int a = lane + r * G;
             if (a < A) { ACTS(3 * a) = at[r]; ACTS(3 * a + 1) = adx[r]; ACTS(3 * a + 2) = ady[r]; }
-            alive_before |= gballot<G>(e, a < A && TL(p.P + (a < A ? a : 0)) > 0) << (r * G);
+            alive_before |= gballot<G, CV>(e, a < A && TL(p.P + (a < A ? a : 0)) > 0) << (r * G);
             life_before[r] = a < A ? PREVL(a) : 0;
         }
         const int zd_before = e.prev_zd;
         const int life_prev0 = PREVL(0);
-        gsync<G>(e);
+        gsync<G, CV>(e);
         if (step + 1 < io.n_steps) fetch_action(step + 1);
 
-        int k = world_step<MPC, G>(p, e);
+        int k;
+        if constexpr (ONE) k = world_step_one<MPC, G, CV>(p, e);
+        else k = world_step<MPC, G, CV>(p, e);
         e.ep_steps += 1;
 
         // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order.
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
             life_now[r] = a < A ? TL(p.P + a) : 0;
             rew[r] = 0.0;
             if (!p.obs_per_agent) {
-                if (A > 1) { sum_prev += gadd<G>(e, life_before[r]); sum_new += gadd<G>(e, life_now[r]); }
+                if (A > 1) { sum_prev += gadd<G, CV>(e, life_before[r]); sum_new += gadd<G, CV>(e, life_now[r]); }
             } else if (a < A && (life_before[r] != life_now[r] || zd_before != e.zd))
                 rew[r] = __dsub_rn(total_reward(e.zd, life_now[r]), total_reward(zd_before, life_before[r]));
         }
@@ -146,22 +150,22 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
 #pragma unroll
         for (int r = 0; r < AR; ++r) { const int a = lane + r * G; if (a < A) PREVL(a) = (int16_t)life_now[r]; }
         e.prev_zd = e.zd;
-        gsync<G>(e);
+        gsync<G, CV>(e);
 
         // ---- Game.spawn_zombies_to_maintain_minimum (game.py:196-201)
         if (p.minimum_zombies > 0) {
             int zc = 0;
 #pragma unroll 1
-            for (int s0 = NP; s0 < p.M; s0 += G) zc += __popc(gballot<G>(e, s0 + lane < p.M && (TM(s0 + lane) & 0x80)));
+            for (int s0 = NP; s0 < p.M; s0 += G) zc += __popc(gballot<G, CV>(e, s0 + lane < p.M && (TM(s0 + lane) & 0x80)));
             if (zc < p.minimum_zombies) {
-                k = spawn_zombies<MPC, G>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive);
+                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive);
                 e.nlive = SCALW(ZS_S_STAMP_COUNTER);
             }
         }
 
         // ---- rules and end reward (gym_env.py:130-141, multiagent_env.py:143-162)
         bool ended, won, agents_alive;
-        rules_eval<MPC, G>(p, e, ended, won, agents_alive);
+        rules_eval<MPC, G, CV>(p, e, ended, won, agents_alive);
         bool done = false, trunc = false;
         double end_reward = 0.0;
         if (ended) { done = true; end_reward = won ? 10.0 : -10.0; }
@@ -196,16 +200,17 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
                 atomicAdd(p.stats + 2, (unsigned long long)e.ep_steps);
                 atomicAdd(p.stats + 3, (unsigned long long)e.zd);
             }
-            initialize_world<MPC, G>(p, id_of(e), e.episode + 1, e.flags);
-            scalars_from_smem<MPC, G>(p, e);
+            // rare, and possibly only one env of the warp: the divergent flavour
+            initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
+            scalars_from_smem<MPC, G, false>(p, e);
         }
         if (obs_out) {
-            if (world_obs) obs_world_patch<MPC, G>(p, e, obs_out);
-            else encode_surroundings<MPC, G>(p, e, obs_out);
+            if (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
+            else encode_surroundings<MPC, G, CV>(p, e, obs_out);
         }
-        gsync<G>(e);
+        gsync<G, CV>(e);
     }
-    store_state<MPC, G>(p, e);
+    store_state<MPC, G, CV>(p, e);
 }
 
 __global__ void zs_init_static_life_kernel(const __grid_constant__ ZsParams p) {
@@ -465,10 +470,11 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     p.smem_per_env = round_up(struct_bytes + off, 16);
     // lanes per env: a half warp when an env has at most 16 slots AND the batch does not fit the chip as
     // one full-warp wave (148 SMs x 28 resident warps); small batches are latency-bound and want the lanes
-    h->lanes_per_env = (p.mpc == 16 && p.N > prop.multiProcessorCount * ZS_MIN_CTAS * ZS_WPC) ? 16 : 32;
+    // (two envs per warp run in lock-step: an odd env count would leave half a warp without an env)
+    h->lanes_per_env = (p.mpc == 16 && p.N % 2 == 0 && p.N > prop.multiProcessorCount * ZS_MIN_CTAS * ZS_WPC) ? 16 : 32;
     if (const char* force = getenv("ZS_LANES_PER_ENV")) {
         const int v = atoi(force);
-        if ((v == 16 && p.mpc == 16) || v == 32) h->lanes_per_env = v;
+        if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) h->lanes_per_env = v;
     }
     h->envs_per_cta = ZS_WPC * (32 / h->lanes_per_env);
     h->smem_bytes = p.smem_per_env * h->envs_per_cta;
@@ -596,3 +602,4 @@ extern "C" __attribute__((visibility("default"))) int zs_episode_stats(ZsHandle*
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t zs_launch_count(const ZsHandle* h) { return h ? h->launches : 0; }
+extern "C" __attribute__((visibility("default"))) int32_t zs_lanes_per_env(const ZsHandle* h) { return h ? h->lanes_per_env : 0; }

@@ -196,15 +196,55 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------- lane-group primitives
-template <int G> __device__ __forceinline__ void gsync(const Env& e) { __syncwarp(e.gm); }
-template <int G> __device__ __forceinline__ unsigned gballot(const Env& e, bool pred) {
-    const unsigned m = __ballot_sync(e.gm, pred);
+// G = lanes per env.  With G == 16 a *.sync primitive on the half warp's own member mask costs a convergence
+// check (MATCH.ANY + REDUX + VOTEU + branch) in front of every use, which made two envs per warp slower than one.
+// CV = true ("converged") instead promises that BOTH halves of the warp reach every primitive together: the
+// primitives run on the full mask and are segmented by hand (ballot bits shifted to the half, reductions done
+// per half or on values shifted into the half's own 16 bits, shuffles with width 16).  Every branch of the hot
+// loop that contains a primitive is therefore taken on a WARP-level condition (wany) and predicated per env
+// inside.  CV = false is the divergent flavour (member mask e.gm): the rare out-of-line paths (world init, respawn,
+// sequential execute) that one env of a warp may take alone, and the reset / encode kernels.
+template <int G, bool CV> __device__ __forceinline__ unsigned gmask(const Env& e) { return (G == 32 || CV) ? 0xffffffffu : e.gm; }
+template <int G, bool CV> __device__ __forceinline__ void gsync(const Env& e) { __syncwarp(gmask<G, CV>(e)); }
+template <int G, bool CV> __device__ __forceinline__ unsigned gballot(const Env& e, bool pred) {
+    const unsigned m = __ballot_sync(gmask<G, CV>(e), pred);
     return G == 32 ? m : ((m >> e.gshift) & ((1u << (G & 31)) - 1u));
 }
-template <int G> __device__ __forceinline__ bool gany(const Env& e, bool pred) { return __any_sync(e.gm, pred); }
-template <int G> __device__ __forceinline__ int gbcast(const Env& e, int v, int src) { return __shfl_sync(e.gm, v, src, G); }
-template <int G> __device__ __forceinline__ int gadd(const Env& e, int v) { return __reduce_add_sync(e.gm, v); }
-template <int G> __device__ __forceinline__ uint32_t gminu(const Env& e, uint32_t v) { return __reduce_min_sync(e.gm, v); }
+// any over the env's lanes
+template <int G, bool CV> __device__ __forceinline__ bool gany(const Env& e, bool pred) {
+    if (G == 32 || !CV) return __any_sync(gmask<G, CV>(e), pred);
+    return gballot<G, CV>(e, pred) != 0u;
+}
+// any over everybody who has to take a branch together: the whole warp when converged, else the env's lanes
+template <int G, bool CV> __device__ __forceinline__ bool wany(const Env& e, bool pred) { return __any_sync(gmask<G, CV>(e), pred); }
+template <int G, bool CV> __device__ __forceinline__ int gbcast(const Env& e, int v, int src) { return __shfl_sync(gmask<G, CV>(e), v, src, G); }
+template <int G, bool CV> __device__ __forceinline__ int gadd(const Env& e, int v) {
+    if (G == 32 || !CV) return __reduce_add_sync(gmask<G, CV>(e), v);
+    const int lo = __reduce_add_sync(0xffffffffu, e.gshift ? 0 : v), hi = __reduce_add_sync(0xffffffffu, e.gshift ? v : 0);
+    return e.gshift ? hi : lo;
+}
+template <int G, bool CV> __device__ __forceinline__ uint32_t gminu(const Env& e, uint32_t v) {
+    if (G == 32 || !CV) return __reduce_min_sync(gmask<G, CV>(e), v);
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, e.gshift ? 0xffffffffu : v), hi = __reduce_min_sync(0xffffffffu, e.gshift ? v : 0xffffffffu);
+    return e.gshift ? hi : lo;
+}
+// OR of bit-masks whose set bits are all below G (rank / position masks): one reduction serves both halves
+template <int G, bool CV> __device__ __forceinline__ unsigned gor_bits(const Env& e, unsigned v) {
+    if (G == 32 || !CV) return __reduce_or_sync(gmask<G, CV>(e), v);
+    return (__reduce_or_sync(0xffffffffu, v << e.gshift) >> e.gshift) & ((1u << (G & 31)) - 1u);
+}
+// lanes of the env holding the same value (value < 2^20), as a mask of group lanes
+template <int G, bool CV> __device__ __forceinline__ unsigned gmatch(const Env& e, uint32_t v) {
+    if (G == 32) return __match_any_sync(0xffffffffu, v);
+    if (!CV) return __match_any_sync(e.gm, v) >> e.gshift;
+    return (__match_any_sync(0xffffffffu, v | ((uint32_t)e.gshift << 20)) >> e.gshift) & ((1u << (G & 31)) - 1u);
+}
+// the larger of a value that is uniform within each env, over the envs that share control flow
+template <int G, bool CV> __device__ __forceinline__ int wmax(const Env& e, int v) {
+    if (G == 32 || !CV) return v;
+    const int o = __shfl_xor_sync(0xffffffffu, v, 16);
+    return v > o ? v : o;
+}
 
 __device__ __forceinline__ int xy_x(uint32_t xy) { return (int)(int16_t)(xy & 0xffffu); }
 __device__ __forceinline__ int xy_y(uint32_t xy) { return (int)xy >> 16; }

@@ -96,7 +96,7 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const 
     const int lane = e.gl;
     const bool fresh = e.flags & FL_FRESH;
     if (p.tmpl_smem_off >= 0 && lane == 0) bulk_wait_all();  // pass 1 (TMA) has landed before any cell is patched
-    gsync<G>(e);
+    gsync<G, CV>(e);
     if (e.flags & FL_DMG) {  // launch-lifetime: the boxes/walls whose life differs from MAX_LIFE (a short list)
         const bool over = e.flags & FL_DMG_OVER;
         const int n_list = over ? p.S : (int)DMG(0);
@@ -111,8 +111,8 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const 
             if (life <= 0 && !fresh) { ci.label = 0; ci.life = 0; }  // destroyed: gone from World.things
             obs_store_cell(p, obs, __ldg(p.static_cell + si), ci);
         }
-        gsync<G>(e);
     }
+    gsync<G, CV>(e);
 #pragma unroll 1
     for (int w = lane; w < p.dead_words; w += G) {
         uint32_t bits = DEADW(w);
@@ -124,7 +124,7 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const 
             obs_store_cell(p, obs, w * 32 + b, ci);
         }
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
 #pragma unroll 1
     for (int s = lane; s < p.M; s += G) {
         const int m = TM(s);
@@ -157,7 +157,7 @@ ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, co
                 ci.label = ZS_LABEL_WALL; ci.life = 200; ci.weapon = 0; ci.agent = -1;
             } else {
                 const int cell = y * p.W + x;
-                ci = cell_info<MPC, G>(p, e, cell, GRID(cell));
+                ci = cell_info<MPC, G, CV>(p, e, cell, GRID(cell));
             }
             if (p.obs_enc == ZS_OBS_SIMPLE) __stcs(o + i, encode_simple(ci));
             else {
@@ -170,6 +170,6 @@ ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, co
 }
 
 ZS_TPL __device__ __forceinline__ void encode_obs(const ZsParams& p, const Env& e, int32_t* obs) {
-    if (p.obs_scope == ZS_OBS_WORLD) { obs_world_template<MPC, G>(p, e, obs); obs_world_patch<MPC, G>(p, e, obs); }
-    else encode_surroundings<MPC, G>(p, e, obs);
+    if (p.obs_scope == ZS_OBS_WORLD) { obs_world_template<MPC, G, CV>(p, e, obs); obs_world_patch<MPC, G, CV>(p, e, obs); }
+    else encode_surroundings<MPC, G, CV>(p, e, obs);
 }

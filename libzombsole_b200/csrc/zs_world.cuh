@@ -1,11 +1,11 @@
 // zs_world.cuh — the world transition, rules, rewards and world (re)initialisation, one lane group per env.
 // Reference line numbers are relative to the reference tree (jvstinian/libzombsole v0.13.2).
-// Everything is templated on the slot capacity MPC (16, 32, 128, 256) and the lanes per env G (32, or 16 for
-// MPC == 16 and large batches); ONE = "every slot has its own lane" (no round loops).
+// Everything is templated on the slot capacity MPC (16, 32, 128, 256), the lanes per env G (32, or 16 for
+// MPC == 16) and CV (see zs_device.cuh: full-mask warp primitives); ONE = "every slot has its own lane".
 #pragma once
 #include "zs_device.cuh"
 
-#define ZS_TPL template <int MPC, int G>
+#define ZS_TPL template <int MPC, int G, bool CV>
 #define ZS_CONSTS                                   \
     constexpr bool ONE = MPC <= G;                  \
     (void)ONE
@@ -20,11 +20,11 @@ __device__ __forceinline__ Env env_of(const ZsParams& p, const GrpId& id) {
 }
 __device__ __forceinline__ GrpId id_of(const Env& e) { GrpId id; id.b = e.b; id.env = e.env; id.gl = e.gl; id.gm = e.gm; id.gshift = e.gshift; return id; }
 
-template <int G> __device__ __forceinline__ void scalars_from_lane(Env& e, int sc) {
-    e.t = gbcast<G>(e, sc, ZS_S_T); e.episode = gbcast<G>(e, sc, ZS_S_EPISODE);
-    e.deaths = gbcast<G>(e, sc, ZS_S_DEATHS); e.zd = gbcast<G>(e, sc, ZS_S_ZOMBIE_DEATHS);
-    e.nlive = gbcast<G>(e, sc, ZS_S_STAMP_COUNTER); e.flags = gbcast<G>(e, sc, ZS_S_FLAGS);
-    e.prev_zd = gbcast<G>(e, sc, ZS_S_PREV_ZOMBIE_DEATHS); e.ep_steps = gbcast<G>(e, sc, ZS_S_EPISODE_STEPS);
+template <int G, bool CV> __device__ __forceinline__ void scalars_from_lane(Env& e, int sc) {
+    e.t = gbcast<G, CV>(e, sc, ZS_S_T); e.episode = gbcast<G, CV>(e, sc, ZS_S_EPISODE);
+    e.deaths = gbcast<G, CV>(e, sc, ZS_S_DEATHS); e.zd = gbcast<G, CV>(e, sc, ZS_S_ZOMBIE_DEATHS);
+    e.nlive = gbcast<G, CV>(e, sc, ZS_S_STAMP_COUNTER); e.flags = gbcast<G, CV>(e, sc, ZS_S_FLAGS);
+    e.prev_zd = gbcast<G, CV>(e, sc, ZS_S_PREV_ZOMBIE_DEATHS); e.ep_steps = gbcast<G, CV>(e, sc, ZS_S_EPISODE_STEPS);
 }
 __device__ __forceinline__ int scalar_of_lane(const Env& e) {
     const int l = e.gl;
@@ -35,8 +35,8 @@ __device__ __forceinline__ int scalar_of_lane(const Env& e) {
 // hand-off through shared memory around the out-of-line functions
 ZS_TPL __device__ __forceinline__ void scalars_from_smem(const ZsParams& p, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
-    gsync<G>(e);
-    scalars_from_lane<G>(e, e.gl < 8 ? SCALW(e.gl) : 0);
+    gsync<G, CV>(e);
+    scalars_from_lane<G, CV>(e, e.gl < 8 ? SCALW(e.gl) : 0);
 }
 
 // Dict-order ranks from arbitrary order-preserving stamps (state import / start of a launch): the rank of
@@ -61,9 +61,9 @@ ZS_TPL __device__ __noinline__ int ranks_from_stamps(const ZsParams& p, GrpId id
             MVQ(s) = RK_NONE;
             if (live) SOR(r) = (uint8_t)s;
         }
-        n += __popc(gballot<G>(e, live));
+        n += __popc(gballot<G, CV>(e, live));
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
     return n;
 }
 
@@ -78,13 +78,13 @@ ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId
     for (int i0 = 0; i0 < p.Sp; i0 += G) {
         const int i = i0 + lane;
         const bool dmg = i < p.Sp && SL(i) != __ldg(p.static_max + i);
-        const unsigned m = gballot<G>(e, dmg);
+        const unsigned m = gballot<G, CV>(e, dmg);
         const int pos = n + __popc(m & ((1u << e.gl) - 1u));
         if (dmg && pos < ZS_DMG_CAP) DMG(1 + pos) = (uint16_t)i;
         n += __popc(m);
     }
     if (lane == 0) DMG(0) = (uint16_t)(n < ZS_DMG_CAP ? n : ZS_DMG_CAP);
-    gsync<G>(e);
+    gsync<G, CV>(e);
     return n == 0 ? 0 : (n <= ZS_DMG_CAP ? FL_DMG : (FL_DMG | FL_DMG_OVER));
 }
 
@@ -103,15 +103,15 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
     const uint4* sl4 = (const uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
 #pragma unroll 1
     for (int i = e.gl; i < (p.Sp >> 3); i += G) reinterpret_cast<uint4*>(SLP)[i] = sl4[i];
-    scalars_from_lane<G>(e, e.gl < 8 ? p.SCAL[(size_t)e.env * 8 + e.gl] : 0);
-    gsync<G>(e);
-    e.nlive = ranks_from_stamps<MPC, G>(p, id_of(e));
-    e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G>(p, id_of(e));
+    scalars_from_lane<G, CV>(e, e.gl < 8 ? p.SCAL[(size_t)e.env * 8 + e.gl] : 0);
+    gsync<G, CV>(e);
+    e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e));
+    e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e));
 }
 
 ZS_TPL __device__ __forceinline__ void store_state(const ZsParams& p, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
-    gsync<G>(e);
+    gsync<G, CV>(e);
     const size_t row = (size_t)e.env * p.Mp;
 #pragma unroll 1
     for (int s = e.gl; s < p.Mp; s += G) {
@@ -145,14 +145,14 @@ ZS_TPL __device__ __noinline__ void build_grid(const ZsParams& p, GrpId id, int 
     const uint4* tg = (const uint4*)p.tmpl_grid;
 #pragma unroll 1
     for (int i = e.gl; i < (p.cells_pad >> 4); i += G) reinterpret_cast<uint4*>(GRIDP)[i] = __ldg(tg + i);
-    gsync<G>(e);
+    gsync<G, CV>(e);
     if (flags & FL_DMG) {
 #pragma unroll 1
         for (int i = e.gl; i < p.S; i += G) {
             const int life = SL(i);
             if (life != __ldg(p.static_max + i)) GRID(__ldg(p.static_cell + i)) = (life <= 0 && !fresh) ? G_EMPTY : G_STATIC_DMG;
         }
-        gsync<G>(e);
+        gsync<G, CV>(e);
     }
 #pragma unroll 1
     for (int w = e.gl; w < p.dead_words; w += G) {
@@ -164,11 +164,11 @@ ZS_TPL __device__ __noinline__ void build_grid(const ZsParams& p, GrpId id, int 
             if (GRID(c) == G_EMPTY) GRID(c) = G_DEAD;
         }
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
 #pragma unroll 1
     for (int s = e.gl; s < p.M; s += G)
         if (TM(s) & 0x80) { const uint32_t xy = TXY(s); GRID(xy_y(xy) * p.W + xy_x(xy)) = (uint8_t)(s + 1); }
-    gsync<G>(e);
+    gsync<G, CV>(e);
 }
 
 // ---------------------------------------------------------------- decide phase
@@ -210,7 +210,7 @@ ZS_TPL __device__ __forceinline__ int prefix_popc(const ZsParams& p, const Env& 
 }
 
 // ---------------------------------------------------------------- World.step (core.py:72-78)
-// Returns the number of draws consumed so far in this step's draw cell.
+// General version: more slots than lanes (round loops over the slots).  Returns the draws consumed so far in this step.
 ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl;
@@ -224,7 +224,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     bool humans = false;
     unsigned needz0 = 0, needz1 = 0;  // slots < NP <= 64
 #pragma unroll 1
-    for (int s0 = 0; s0 < (ONE ? 1 : (NP)); s0 += G) {
+    for (int s0 = 0; s0 < NP; s0 += G) {
         const int s = s0 + lane;
         bool needz = false;
         if (s < NP && (TM(s) & 0x80)) {
@@ -232,18 +232,18 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             needz = s < p.P ? (p.bot_kinds[s] == ZS_KIND_TERMINATOR || p.bot_kinds[s] == ZS_KIND_SNIPER)
                             : ACTS(3 * (s - p.P)) == ZS_ACT_ATTACK_CLOSEST;
         }
-        const unsigned m = gballot<G>(e, needz);
+        const unsigned m = gballot<G, CV>(e, needz);
         if (s0 == 0) needz0 = m; else needz1 = m;
         if (s < NP) ZB(s) = 0xffffffffu;
     }
-    const bool has_humans = gany<G>(e, humans);
-    gsync<G>(e);
+    const bool has_humans = gany<G, CV>(e, humans);
+    gsync<G, CV>(e);
     // ---- closest(self, others) (utils.py:23-31) for everybody from ONE pass over the (thing, player) distances:
     // a zombie (things.py:73-82) or a heal_closest agent (agent.py:79-86) takes the minimum over the players in
     // its own lane; a player's closest zombie is the minimum of the same distances across the zombie lanes
     // (redux.sync).  Key = (d^2 << 8) | dict rank: sorted() is stable, so ties go to the earlier thing.
 #pragma unroll 1
-    for (int s0 = 0; s0 < (ONE ? 1 : (p.M)); s0 += G) {
+    for (int s0 = 0; s0 < p.M; s0 += G) {
         const int s = s0 + lane;
         const uint32_t myrank = s < p.M ? RK(s) : RK_NONE;
         const bool live = myrank != RK_NONE;
@@ -261,19 +261,19 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             const uint32_t d = (uint32_t)dist2(x, y, xy_x(qxy), xy_y(qxy)) << 8;
             if (wantp && q != s) bestp = min(bestp, d | rq);
             if (((q < 32 ? needz0 : needz1) >> (q & 31)) & 1u) {
-                const uint32_t m = gminu<G>(e, d | zkey);
+                const uint32_t m = gminu<G, CV>(e, d | zkey);
                 if (lane == 0 && m < ZB(q)) ZB(q) = m;
             }
         }
         if (s < p.Mp) BK(s) = bestp;
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
 
     // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
     bool any_wander = false;
     int n_idle = 0;
 #pragma unroll 1
-    for (int s0 = 0; s0 < (ONE ? 1 : (p.M)); s0 += G) {
+    for (int s0 = 0; s0 < p.M; s0 += G) {
         const int s = s0 + lane;
         const bool live = s < p.M && RK(s) != RK_NONE;
         const uint32_t xy = live ? TXY(s) : 0u;
@@ -360,10 +360,10 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         }
         if (s < p.Mp) { DTYPE(s) = (uint8_t)type; DA(s) = (int16_t)a; DB(s) = (int16_t)b; }
     }
-    n_idle = gadd<G>(e, n_idle);
-    gsync<G>(e);
+    n_idle = gadd<G, CV>(e, n_idle);
+    gsync<G, CV>(e);
     int nd = 0;
-    if (gany<G>(e, any_wander)) {
+    if (gany<G, CV>(e, any_wander)) {
         // wandering zombies and hamsters draw random.choice(positions) in dict order (things.py:101-103, hamster.py:12-14)
         int mine = 0;
 #pragma unroll 1
@@ -380,20 +380,18 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             DA(s) = (int16_t)(xy_x(xy) + adj_dx(d)); DB(s) = (int16_t)(xy_y(xy) + adj_dy(d));
             ++mine;
         }
-        nd = gadd<G>(e, mine);
-        gsync<G>(e);
+        nd = gadd<G, CV>(e, mine);
+        gsync<G, CV>(e);
 #pragma unroll 1
         for (int s = e.gl; s < p.M; s += G) if (DTYPE(s) == D_WANDER) DTYPE(s) = D_MOVE;
-        gsync<G>(e);
+        gsync<G, CV>(e);
     }
     // actions list in actor (dict) order (core.py:83-90): the position of an acting thing is its dict rank minus
     // the idle things before it (idle things are rare: usually the rank is the position).
     // Everything that cannot change before the actor acts is resolved here, in parallel.
     int cnt = 0, n_ah = 0;
-    unsigned long long my_word = X_NOP;  // ONE: this lane's action stays in registers until its shuffled position is known
-    int my_pos = -1;
 #pragma unroll 1
-    for (int s0 = 0; s0 < (ONE ? 1 : (p.M)); s0 += G) {
+    for (int s0 = 0; s0 < p.M; s0 += G) {
         const int s = s0 + lane;
         const int type = s < p.M ? DTYPE(s) : D_IDLE;  // D_IDLE for everything that is not in the world
         int pos = s < p.M ? RK(s) : 0;
@@ -430,44 +428,30 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             }
             ++cnt;
         }
-        if (ONE) { my_word = word; my_pos = acting ? pos : -1; }
-        else if (acting) ACT(pos) = word;
+        if (acting) ACT(pos) = word;
     }
-    const int L = gadd<G>(e, cnt);
-    n_ah = gadd<G>(e, n_ah);
+    const int L = gadd<G, CV>(e, cnt);
+    n_ah = gadd<G, CV>(e, n_ah);
     // ---- draws of this step, generated 4 per lane (counter-based: any k is available directly)
     const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
 #pragma unroll 1
     for (int blk = lane; blk * 4 < n_need; blk += G)
         reinterpret_cast<uint4*>(S.draws)[blk] = philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)blk, p.key0, p.key1);
-    gsync<G>(e);
+    gsync<G, CV>(e);
     // Fisher-Yates partner of every iteration (random.shuffle: for i = L-1 .. 1: j = randbelow(i + 1))
 #pragma unroll 1
     for (int i = 1 + e.gl; i < L; i += G) DTYPE(i) = (uint8_t)below(DRAWS(nd + (L - 1 - i)), i + 1);
-    gsync<G>(e);
+    gsync<G, CV>(e);
 
-    // ---- random.shuffle (core.py:76).  The Fisher-Yates swaps are a fixed sequence once the partners are known,
-    // so every lane follows its own action through them in registers (if pos == i: pos = j; elif pos == j: pos = i)
-    // and stores it at its final position; with more actions than lanes, lane 0 swaps in shared memory.
-    if (ONE) {
-#pragma unroll 1
-        for (int i = L - 1; i >= 1; --i) {
-            const int j = DTYPE(i);
-            my_pos = my_pos == i ? j : (my_pos == j ? i : my_pos);
-        }
-        if (my_pos >= 0) ACT(my_pos) = my_word;
-        gsync<G>(e);
-    }
-    // ---- execute_actions (core.py:103-119): order-dependent by definition, run by the group's lane 0
+    // ---- random.shuffle (core.py:76) and execute_actions (core.py:103-119): order-dependent by definition, run by
+    // the group's lane 0 on shared memory
     int k = nd + (L > 1 ? L - 1 : 0);
     int nmv = 0;
     if (lane == 0) {
-        if (!ONE) {
 #pragma unroll 1
-            for (int i = L - 1; i >= 1; --i) {
-                const int j = DTYPE(i);
-                const unsigned long long tmp = ACT(i); ACT(i) = ACT(j); ACT(j) = tmp;
-            }
+        for (int i = L - 1; i >= 1; --i) {
+            const int j = DTYPE(i);
+            const unsigned long long tmp = ACT(i); ACT(i) = ACT(j); ACT(j) = tmp;
         }
         int n_touched = 0, fl = e.flags, deaths = e.deaths;
 #pragma unroll 1
@@ -528,11 +512,11 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         }
         e.flags = fl; e.deaths = deaths;
     }
-    k = gbcast<G>(e, k, 0);
-    nmv = gbcast<G>(e, nmv, 0);
-    e.deaths = gbcast<G>(e, e.deaths, 0);
-    e.flags = gbcast<G>(e, e.flags, 0);
-    gsync<G>(e);
+    k = gbcast<G, CV>(e, k, 0);
+    nmv = gbcast<G, CV>(e, nmv, 0);
+    e.deaths = gbcast<G, CV>(e, e.deaths, 0);
+    e.flags = gbcast<G, CV>(e, e.flags, 0);
+    gsync<G, CV>(e);
 
     // ---- clean_dead_things (core.py:121-138)
     int nd_all = 0, nd_z = 0;
@@ -552,45 +536,8 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         }
         e.flags &= ~FL_FRESH;
     }
-    if constexpr (ONE) {
-        // every slot has its own lane: deaths, dead bodies and the new dict order in one pass.  Survivors that
-        // did not move keep their relative order, the movers follow in move order (re-inserted at the end,
-        // core.py:158-159); the two rank bit-masks come from redux.sync.or.
-        const int s = lane;
-        const int r = s < p.M ? RK(s) : RK_NONE;
-        const bool was = r != RK_NONE;
-        const bool dead = was && TL(s) <= 0;
-        if (dead) {
-            const uint32_t xy = TXY(s);
-            const int c = xy_y(xy) * p.W + xy_x(xy);
-            GRID(c) = G_DEAD;                         // DeadBody overwrites any decoration (core.py:30-31,126-128)
-            atomicOr(&DEADW(c >> 5), 1u << (c & 31));
-            TM(s) &= 0x7f;
-        }
-        const unsigned dead_m = gballot<G>(e, dead);
-        e.deaths += __popc(dead_m) + (fresh_scan ? gadd<G>(e, nd_all) : 0);
-        e.zd += __popc(dead_m >> NP);
-        if (nmv > 0 || dead_m) {
-            const int q = was ? MVQ(s) : RK_NONE;
-            const bool alive = was && !dead;
-            const unsigned stay_m = __reduce_or_sync(e.gm, (alive && q == RK_NONE) ? (1u << r) : 0u);
-            const unsigned move_m = __reduce_or_sync(e.gm, (alive && q != RK_NONE) ? (1u << q) : 0u);
-            if (was) {
-                int nr = RK_NONE;
-                if (alive) {
-                    nr = q == RK_NONE ? __popc(stay_m & ((1u << r) - 1u)) : __popc(stay_m) + __popc(move_m & ((1u << q) - 1u));
-                    SOR(nr) = (uint8_t)s;
-                }
-                RK(s) = (uint8_t)nr;
-                MVQ(s) = RK_NONE;
-            }
-            e.nlive = __popc(stay_m) + __popc(move_m);
-        }
-        gsync<G>(e);
-        return k;
-    } else {
     for (int w = e.gl; w < 2 * rw; w += G) MASKW(w) = 0u;
-    gsync<G>(e);
+    gsync<G, CV>(e);
 #pragma unroll 1
     for (int s = e.gl; s < p.M; s += G) {
         const int r = RK(s);
@@ -609,10 +556,10 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             else atomicOr(&MASKW(rw + (q >> 5)), 1u << (q & 31));
         }
     }
-    nd_all = gadd<G>(e, nd_all);
+    nd_all = gadd<G, CV>(e, nd_all);
     e.deaths += nd_all;
-    e.zd += gadd<G>(e, nd_z);
-    gsync<G>(e);
+    e.zd += gadd<G, CV>(e, nd_z);
+    gsync<G, CV>(e);
     // ---- new dict order: World.things after the moves (re-inserted at the end, core.py:158-159) and the deletions
     if (nmv > 0 || nd_all > 0) {
         int stayers = 0;
@@ -627,19 +574,439 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                 if (!(TM(s) & 0x80)) r = RK_NONE;
                 else {
                     const int q = MVQ(s);
-                    r = q == RK_NONE ? prefix_popc<MPC, G>(p, e, 0, r) : stayers + prefix_popc<MPC, G>(p, e, rw, q);
+                    r = q == RK_NONE ? prefix_popc<MPC, G, CV>(p, e, 0, r) : stayers + prefix_popc<MPC, G, CV>(p, e, rw, q);
                     SOR(r) = (uint8_t)s;
                 }
                 RK(s) = (uint8_t)r;
                 MVQ(s) = RK_NONE;
             }
-            nl += __popc(gballot<G>(e, r != RK_NONE));
+            nl += __popc(gballot<G, CV>(e, r != RK_NONE));
         }
         e.nlive = nl;
-        gsync<G>(e);
+        gsync<G, CV>(e);
     }
     return k;
+}
+
+// ---------------------------------------------------------------- World.step when every slot has its own lane
+// (MPC <= G).  Same semantics as world_step above, organised for short dependent chains and no divergence
+// between the two envs of a warp in half-warp mode:
+//   * SLOT SPACE (lane = slot): everything an actor decides stays in registers; closest-zombie keys land in the
+//     player's own lane straight from redux.sync.min; wander / idle bookkeeping uses rank bit-masks from redux.sync.or.
+//   * the Fisher-Yates partners are exchanged with shuffles, every lane follows its own action to its position.
+//   * POSITION SPACE (lane = position in the shuffled action list): execute_actions (core.py:103-119) is sequential
+//     by definition, but its dependencies are few and can be decided up front:
+//       - a move succeeds iff its destination holds no thing when it runs.  A destination that is free before the
+//         step goes to the FIRST mover that wants it (match.any on the cell, lowest position wins; the winner can
+//         not leave again); a box/wall never leaves during execute; a mobile thing only leaves through its own
+//         move, so the move fails unless that move comes EARLIER in the list — the one case that needs the
+//         sequential loop (execute_sequential), an agent walking into a cell somebody is just leaving;
+//       - a hit on a mobile target checks the range against the target's position at that time: its destination
+//         if its successful move comes earlier in the list, else its old position;
+//       - the draw index of a hit is the number of in-range hits before it (ballot prefix);
+//       - the hits on one target (match.any on the target) are applied in list order by the first of them.
+#define MVP(i) S.mvq[i]      // position of the slot's successful move in this step's list, RK_NONE if none
+#define MPOS(i) S.dtype[i]   // position of the slot's (valid) move action in the list, RK_NONE if none
+#define AMT(i) S.list[i]     // amount drawn by the hit at a position, bit 15 = heal
+
+// The sequential loop over the shuffled list, for the steps the parallel resolution cannot decide.  Scalars go
+// through SCALW: in [0] k, [1] flags, [2] deaths; out the same plus [3] = bit-mask of the positions whose move succeeded.
+ZS_TPL __device__ __noinline__ void execute_sequential(const ZsParams& p, GrpId id, int L) {
+    Env e = env_of(p, id);
+    ZS_VIEWS;
+    if (e.gl == 0) {
+        int k = SCALW(0), fl = SCALW(1), deaths = SCALW(2), n_touched = 0;
+        unsigned succ = 0;
+#pragma unroll 1
+        for (int i = 0; i < L; ++i) {
+            const unsigned long long pk = ACT(i);
+            const uint32_t lo32 = (uint32_t)pk, hi32 = (uint32_t)(pk >> 32);
+            const int kind = lo32 & 7;
+            if (kind == X_NOP) continue;
+            if (kind == X_MOVE) {  // World.thing_move (core.py:140-166)
+                const int c = lo32 >> 16;
+                if (!g_is_thing(GRID(c))) {
+                    const int actor = (lo32 >> 3) & 0xff;
+                    GRID(hi32 & 0xffffu) = (lo32 & 0x800u) ? G_DEAD : G_EMPTY;
+                    GRID(c) = (uint8_t)(actor + 1);
+                    TXY(actor) = BK(actor);
+                    MVP(actor) = (uint8_t)i;
+                    succ |= 1u << i;
+                }
+                continue;
+            }
+            const int dlo = (lo32 >> 18) & 127, dn = (lo32 >> 25) & 63;
+            if (kind <= X_HEAL_M) {  // mobile target: distance between CURRENT positions (core.py:176,194)
+                const int a = (lo32 >> 3) & 0xff;
+                const uint32_t gxy = TXY(a);
+                if (dist2(xy_x(hi32), xy_y(hi32), xy_x(gxy), xy_y(gxy)) > (int)((lo32 >> 11) & 127)) continue;
+                const int amount = dlo + below(DRAWS(k++), dn);
+                if (kind == X_ATTACK_M) TL(a) = (int16_t)(TL(a) - amount);
+                else { const int nl = TL(a) + amount; TL(a) = (int16_t)(nl < 100 ? nl : 100); }
+            } else {
+                const int a = hi32 & 0xffffu;
+                const int amount = dlo + below(DRAWS(k++), dn);
+                if (kind == X_ATTACK_S) {
+                    SL(a) = (int16_t)(SL(a) - amount);
+                    LIST(n_touched++) = (uint16_t)a;
+                } else {
+                    const int mx = __ldg(p.static_max + a);
+                    const int nl = SL(a) + amount;
+                    SL(a) = (int16_t)(nl < mx ? nl : mx);
+                }
+                const int cell = __ldg(p.static_cell + a);
+                if (GRID(cell) == G_STATIC && !(fl & FL_DMG_OVER)) {  // first time this box/wall differs: remember it
+                    const int n = DMG(0);
+                    if (n < ZS_DMG_CAP) { DMG(1 + n) = (uint16_t)a; DMG(0) = (uint16_t)(n + 1); }
+                    else fl |= FL_DMG_OVER;
+                }
+                GRID(cell) = G_STATIC_DMG;
+                fl |= FL_DMG | FL_SL_DIRTY;
+            }
+        }
+        // clean_dead_things for boxes/walls hit this step (core.py:121-138); on the first step of a world the
+        // scan in the clean phase covers them
+        if (!(fl & FL_FRESH)) {
+#pragma unroll 1
+            for (int i = 0; i < n_touched; ++i) {
+                const int si = LIST(i);
+                const int cell = __ldg(p.static_cell + si);
+                if (SL(si) <= 0 && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
+            }
+        }
+        SCALW(0) = k; SCALW(1) = fl; SCALW(2) = deaths; SCALW(3) = (int)succ;
     }
+    gsync<G, CV>(e);
+}
+
+ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e) {
+    ZS_VIEWS;
+    static_assert(MPC <= G, "one lane per slot");
+    const int s = e.gl;  // slot in slot space, list position in position space
+    const int NP = p.P + p.A;
+    const unsigned below_s = (1u << s) - 1u;
+    e.t += 1;
+    const uint32_t t_word = (uint32_t)(e.t + 1);
+
+    // ================= slot space
+    const bool in_cap = G == MPC || s < MPC;
+    const uint32_t rk = in_cap ? RK(s) : RK_NONE;
+    const bool live = rk != RK_NONE;
+    const uint32_t xy = live ? TXY(s) : 0u;
+    const int x = xy_x(xy), y = xy_y(xy);
+    const bool zombie = s >= NP, agent = !zombie && s >= p.P;
+    const int bkind = s < p.P ? (int)p.bot_kinds[s] : -1;
+    int at = ZS_ACT_NONE, adx = 0, ady = 0;
+    if (live && agent) {
+        at = ACTS(3 * (s - p.P)); adx = ACTS(3 * (s - p.P) + 1); ady = ACTS(3 * (s - p.P) + 2);
+        if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; adx = 0; ady = 0; }  // multiagent_env.py:129-131
+    }
+    const bool has_humans = gany<G, CV>(e, live && !zombie);
+
+    // ---- closest(self, others) (utils.py:23-31) for everybody from ONE pass over the (thing, player) distances:
+    // a zombie (things.py:73-82) or a heal_closest agent (agent.py:79-86) takes the minimum over the players in its
+    // own lane; a player's closest zombie is the minimum of the same distances across the zombie lanes (redux.sync)
+    // and lands in the player's lane.  Key = (d^2 << 8) | dict rank: sorted() is stable, ties go to the earlier thing.
+    const bool wantp = live && (zombie || at == ZS_ACT_HEAL_CLOSEST);
+    const uint32_t zkey = (live && zombie) ? rk : 0xffffffffu;
+    uint32_t bestp = 0xffffffffu, zb = 0xffffffffu;
+#pragma unroll 1
+    for (int q = 0; q < NP; ++q) {
+        const uint32_t rq = RK(q), qxy = TXY(q);
+        const bool hq = rq != RK_NONE;  // player q is in the world
+        const uint32_t d = (uint32_t)dist2(x, y, xy_x(qxy), xy_y(qxy)) << 8;
+        if (hq && wantp && q != s) bestp = min(bestp, d | rq);
+        const uint32_t m = gminu<G, CV>(e, hq ? (d | zkey) : 0xffffffffu);
+        if (q == s) zb = m;
+    }
+
+    // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
+    int type = D_IDLE, a = 0, b = 0;
+    unsigned freemask = 0;
+    if (live) {
+        const uint32_t key = (zombie || at == ZS_ACT_HEAL_CLOSEST) ? bestp : zb;
+        const int tg = key == 0xffffffffu ? -1 : (int)SOR(key & 255u);
+        const int d2 = (int)(key >> 8);
+        const uint32_t gxy = tg >= 0 ? TXY(tg) : 0u;
+        const int gx = xy_x(gxy), gy = xy_y(gxy);
+        if (!agent) {
+            // the four adjacent cells (utils.py:34-44): what is on them and how far they are from the target
+            unsigned gs[4];
+            int dd[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {  // no bounds check: cells outside the map hold nothing (utils.py:47-52)
+                gs[d] = grid_at(p, GRIDP, x + adj_dx(d), y + adj_dy(d));
+                dd[d] = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
+                if (!g_is_thing(gs[d])) freemask |= 1u << d;
+            }
+            if (zombie) {  // Zombie.next_step (things.py:70-105)
+                if (!has_humans) {
+                    if (freemask) type = D_WANDER;
+                } else if (d2 <= 2) { type = D_ATTACK; a = tg; }  // distance < 1.5 (things.py:83)
+                else {
+                    // free cells: closest(target, positions), first minimum in adjacency order; boxed in: the first
+                    // Box/Wall among the adjacent cells stably sorted by distance to the target (things.py:88-99)
+                    int bdir = -1, bdist = 0x7fffffff;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const bool cand = freemask ? ((freemask >> d) & 1u) : g_is_static(gs[d]);
+                        if (cand && dd[d] < bdist) { bdir = d; bdist = dd[d]; }
+                    }
+                    if (bdir >= 0) {
+                        const int cx = x + adj_dx(bdir), cy = y + adj_dy(bdir);
+                        if (freemask) { type = D_MOVE; a = cx; b = cy; }
+                        else { type = D_ATTACK; a = p.M + (int)__ldg(p.cell_static + cy * p.W + cx); }
+                    }
+                }
+            } else if (bkind == ZS_KIND_TERMINATOR) {  // Terminator.next_step (players/terminator.py:9-37)
+                if (tg < 0) { type = D_HEAL; a = s; }
+                else if (d2 > c_range2[TM(s) & 15]) {
+                    int bdir = 0, bdist = 0x7fffffff, g = 0;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)  // closest(target, adjacent_positions(self)): out-of-bounds cells included
+                        if (dd[d] < bdist) { bdir = d; bdist = dd[d]; g = (int)gs[d]; }
+                    const int bx = x + adj_dx(bdir), by = y + adj_dy(bdir);
+                    if (g_is_thing(g)) {
+                        type = (g <= G_MAX_SLOT && (g - 1) < NP) ? D_HEAL : D_ATTACK;
+                        a = target_of_cell(p, g, by * p.W + bx);
+                    } else { type = D_MOVE; a = bx; b = by; }
+                } else { type = D_ATTACK; a = tg; }
+            } else if (bkind == ZS_KIND_SNIPER) {  // Sniper.next_step (players/sniper.py:9-19)
+                if (tg >= 0) { type = D_ATTACK; a = tg; }
+            } else if (bkind == ZS_KIND_TROLL) {   // Troll.next_step (players/troll.py:10-12)
+                type = D_HEAL; a = s;
+            } else {                               // Hamster.next_step (players/hamster.py:10-14)
+                if (freemask) type = D_WANDER;
+            }
+        } else {  // Agent.next_step (players/agent.py:28-96)
+            if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + adx; b = y + ady; }
+            else if (at == ZS_ACT_ATTACK_CLOSEST) { if (tg >= 0) { type = D_ATTACK; a = tg; } }
+            else if (at == ZS_ACT_HEAL_CLOSEST) { type = D_HEAL; a = tg >= 0 ? tg : s; }
+            else if (at == ZS_ACT_ATTACK || at == ZS_ACT_HEAL) {
+                if (at == ZS_ACT_HEAL && adx == 0 && ady == 0) { type = D_HEAL; a = s; }
+                else {
+                    const int g = grid_at(p, GRIDP, x + adx, y + ady);
+                    // attack: any thing; heal: Player / Box / Wall only (agent.py:69-75)
+                    const bool ok = at == ZS_ACT_ATTACK ? g_is_thing(g)
+                                                        : (g_is_static(g) || (g_is_thing(g) && (g - 1) < NP));
+                    if (ok) { type = at == ZS_ACT_ATTACK ? D_ATTACK : D_HEAL; a = target_of_cell(p, g, (y + ady) * p.W + (x + adx)); }
+                }
+            }
+        }
+    }
+    // wandering zombies and hamsters draw random.choice(positions) in dict order (things.py:101-103, hamster.py:12-14)
+    int nd = 0;
+    if (wany<G, CV>(e, type == D_WANDER)) {
+        const unsigned wm = gor_bits<G, CV>(e, type == D_WANDER ? (1u << rk) : 0u);
+        if (type == D_WANDER) {
+            int pick = below(draw_at(p, e, t_word, __popc(wm & ((1u << rk) - 1u))), __popc(freemask));
+            int d = 0;
+            for (int q = 0; q < 4; ++q) if ((freemask >> q) & 1u) { if (pick == 0) { d = q; break; } --pick; }
+            type = D_MOVE; a = x + adj_dx(d); b = y + adj_dy(d);
+        }
+        nd = __popc(wm);
+    }
+    // actions list in actor (dict) order (core.py:83-90): the position of an acting thing is its dict rank minus
+    // the idle things before it.  Everything that cannot change before the actor acts is resolved here.
+    int pos = (int)rk;
+    if (wany<G, CV>(e, live && type == D_IDLE)) {
+        const unsigned im = gor_bits<G, CV>(e, (live && type == D_IDLE) ? (1u << rk) : 0u);
+        pos -= __popc(im & ((1u << (rk & 31u)) - 1u));
+    }
+    unsigned long long my_word = X_NOP;
+    const bool acting = type != D_IDLE;
+    bool is_hit = false;
+    if (acting) {
+        if (type == D_MOVE) {  // in bounds and at most one step (core.py:149-153); occupancy is checked when it runs
+            if ((unsigned)a < (unsigned)p.W && (unsigned)b < (unsigned)p.H && dist2(x, y, a, b) <= 1) {
+                const int old = y * p.W + x;
+                my_word = pack_move(s, (DEADW(old >> 5) >> (old & 31)) & 1u, b * p.W + a, old);
+                BK(s) = xy_pack(a, b);
+            }
+        } else {
+            const bool is_static = a >= p.M;
+            int mx = 100, r2, dlo, dn;
+            if (type == D_ATTACK) { const int w = TM(s) & 15; r2 = c_range2[w]; dlo = c_dmg_lo[w]; dn = c_dmg_n[w]; }
+            else {  // heal: randint(MAX_LIFE // 10, MAX_LIFE // 4) of the target's class, range 3 (core.py:194-198)
+                if (is_static) mx = __ldg(p.static_max + (a - p.M));
+                r2 = 9; dlo = mx / 10; dn = mx / 4 - mx / 10 + 1;
+            }
+            if (is_static) {
+                const int cell = __ldg(p.static_cell + (a - p.M));
+                const int gy = cell / p.W, gx = cell - gy * p.W;
+                if (dist2(x, y, gx, gy) <= r2) { my_word = pack_hit(type == D_ATTACK ? X_ATTACK_S : X_HEAL_S, 0, 0, dlo, dn, (uint32_t)(a - p.M)); is_hit = true; }
+            } else { my_word = pack_hit(type == D_ATTACK ? X_ATTACK_M : X_HEAL_M, a, r2, dlo, dn, xy); is_hit = true; }
+        }
+    }
+    const int L = __popc(gballot<G, CV>(e, acting));
+    const int n_ah = __popc(gballot<G, CV>(e, is_hit));
+    // ---- draws of this step, 4 per lane (counter-based: any k is available directly)
+    const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
+    if (s * 4 < n_need)
+        reinterpret_cast<uint4*>(S.draws)[s] = philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)s, p.key0, p.key1);
+    gsync<G, CV>(e);
+    // ---- random.shuffle (core.py:76): for i = L-1 .. 1: j = randbelow(i + 1); swap.  The swaps are a fixed sequence
+    // once the partners are known: every lane follows its own action through them in registers.
+    int jreg = 0;
+    if (s >= 1 && s < L) jreg = below(DRAWS(nd + (L - 1 - s)), s + 1);
+    int my_pos = acting ? pos : -1;
+#pragma unroll 1
+    for (int i = wmax<G, CV>(e, L) - 1; i >= 1; --i) {  // (the other env of the warp may have the longer list)
+        const int j = gbcast<G, CV>(e, jreg, i);
+        if (i < L) my_pos = my_pos == i ? j : (my_pos == j ? i : my_pos);
+    }
+    if (my_pos >= 0) ACT(my_pos) = my_word;
+    if (in_cap) { MPOS(s) = (uint8_t)(((uint32_t)my_word & 7u) == X_MOVE ? my_pos : RK_NONE); MVP(s) = RK_NONE; }
+    gsync<G, CV>(e);
+
+    // ================= position space: execute_actions (core.py:103-119)
+    int k = nd + (L > 1 ? L - 1 : 0);
+    unsigned succ_m = 0;
+    {
+        const unsigned long long pk = s < L ? ACT(s) : 0ull;
+        const uint32_t lo32 = (uint32_t)pk, hi32 = (uint32_t)(pk >> 32);
+        int kind = lo32 & 7;
+        const int who = (lo32 >> 3) & 0xff;  // the actor of a move, the mobile target of a hit
+        const int c = lo32 >> 16;
+        const int g0 = kind == X_MOVE ? (int)GRID(c) : G_STATIC;
+        bool need_seq = false;
+        if (kind == X_MOVE && g0 >= 1 && g0 <= G_MAX_SLOT) need_seq = MPOS(g0 - 1) < s;
+        // an env that needs the sequential loop sits out the parallel resolution (all its actions read as no-ops)
+        const bool seq = gany<G, CV>(e, need_seq);
+        if (seq) kind = X_NOP;
+        // ---- moves (World.thing_move, core.py:140-166)
+        const bool dest_free = kind == X_MOVE && !g_is_thing(g0);
+        const unsigned want = gmatch<G, CV>(e, dest_free ? (uint32_t)c : 0x10000u + (uint32_t)s);
+        const bool success = dest_free && !(want & below_s);
+        succ_m = gballot<G, CV>(e, success);
+        if (success) {
+            GRID(hi32 & 0xffffu) = (lo32 & 0x800u) ? G_DEAD : G_EMPTY;
+            GRID(c) = (uint8_t)(who + 1);
+            MVP(who) = (uint8_t)s;  // things[dest] = thing; del things[old]: goes last in the dict
+        }
+        gsync<G, CV>(e);
+        // ---- hits (World.thing_attack / thing_heal, core.py:168-208)
+        const bool on_static = kind >= X_ATTACK_S;
+        bool inrange = on_static;  // boxes/walls do not move: their range was checked when the word was built
+        if (kind == X_ATTACK_M || kind == X_HEAL_M) {  // distance between CURRENT positions (core.py:176,194)
+            uint32_t txy = TXY(who);
+            if (MVP(who) < s) txy = BK(who);
+            inrange = dist2(xy_x(hi32), xy_y(hi32), xy_x(txy), xy_y(txy)) <= (int)((lo32 >> 11) & 127);
+        }
+        if (wany<G, CV>(e, inrange)) {
+            const unsigned hit_m = gballot<G, CV>(e, inrange);
+            const int si = hi32 & 0xffffu;
+            const bool heal = kind == X_HEAL_M || kind == X_HEAL_S;
+            if (inrange) {
+                const int amount = (int)((lo32 >> 18) & 127) + below(DRAWS(k + __popc(hit_m & below_s)), (int)((lo32 >> 25) & 63));
+                AMT(s) = (uint16_t)(amount | (heal ? 0x8000 : 0));
+            }
+            k += __popc(hit_m);
+            const uint32_t tid = on_static ? 0x100u + (uint32_t)si : (uint32_t)who;
+            const unsigned grp = gmatch<G, CV>(e, inrange ? tid : 0x20000u + (uint32_t)s);
+            const bool lead = inrange && !(grp & below_s);  // the first hit on a target applies all of them, in order
+            gsync<G, CV>(e);
+            int life = 0;
+            if (lead) {
+                life = on_static ? (int)SL(si) : (int)TL(who);
+                const int mx = on_static ? (int)__ldg(p.static_max + si) : 100;
+                unsigned bits = grp;
+                while (bits) {
+                    const int v = AMT(__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    if (v & 0x8000) { life += v & 0x7fff; life = life < mx ? life : mx; }
+                    else life -= v;
+                }
+                if (on_static) SL(si) = (int16_t)life; else TL(who) = (int16_t)life;
+            }
+            const bool slead = lead && on_static;
+            if (wany<G, CV>(e, slead)) {
+                // a box/wall changed: occupancy code, damaged list, and clean_dead_things (core.py:121-138) for the
+                // ones destroyed now (on the first step of a world the scan in the clean phase covers them)
+                bool pristine = false, gone = false;
+                if (slead) {
+                    const int cell = __ldg(p.static_cell + si);
+                    const int gc = GRID(cell);
+                    pristine = gc == G_STATIC;
+                    gone = life <= 0 && !(e.flags & FL_FRESH) && g_is_static(gc);
+                    GRID(cell) = gone ? G_EMPTY : G_STATIC_DMG;
+                }
+                e.deaths += __popc(gballot<G, CV>(e, gone));
+                if (gany<G, CV>(e, slead)) e.flags |= FL_DMG | FL_SL_DIRTY;
+                unsigned new_m = gballot<G, CV>(e, pristine);
+                if (e.flags & FL_DMG_OVER) new_m = 0u;
+                if (wany<G, CV>(e, new_m != 0u)) {
+                    const int n0 = DMG(0);
+                    const int idx = n0 + __popc(new_m & below_s), tot = n0 + __popc(new_m);
+                    gsync<G, CV>(e);
+                    if (new_m) {
+                        if (pristine && idx < ZS_DMG_CAP) DMG(1 + idx) = (uint16_t)si;
+                        if (s == 0) DMG(0) = (uint16_t)(tot < ZS_DMG_CAP ? tot : ZS_DMG_CAP);
+                        if (tot > ZS_DMG_CAP) e.flags |= FL_DMG_OVER;
+                    }
+                }
+            }
+        }
+        gsync<G, CV>(e);
+        if (seq) {  // rare, and possibly only one env of the warp: the divergent flavour from here
+            if (s == 0) { SCALW(0) = k; SCALW(1) = e.flags; SCALW(2) = e.deaths; }
+            gsync<G, false>(e);
+            execute_sequential<MPC, G, false>(p, id_of(e), L);
+            k = SCALW(0); e.flags = SCALW(1); e.deaths = SCALW(2); succ_m = (unsigned)SCALW(3);
+        }
+    }
+
+    // ================= slot space: clean_dead_things (core.py:121-138)
+    int nd_all = 0;
+    const bool fresh_scan = (e.flags & FL_FRESH) && (e.flags & FL_DMG);
+    if (e.flags & FL_FRESH) {  // first step of this world: every box/wall with life <= 0 leaves now
+        if (e.flags & FL_DMG) {
+            const bool over = e.flags & FL_DMG_OVER;
+            const int n_list = over ? p.S : (int)DMG(0);
+#pragma unroll 1
+            for (int i = e.gl; i < n_list; i += G) {
+                const int si = over ? i : (int)DMG(1 + i);
+                if (SL(si) <= 0) {
+                    const int cell = __ldg(p.static_cell + si);
+                    if (g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; ++nd_all; }
+                }
+            }
+        }
+        e.flags &= ~FL_FRESH;
+    }
+    // deaths, dead bodies and the new dict order in one pass.  Survivors that did not move keep their relative
+    // order, the movers follow in move order (re-inserted at the end, core.py:158-159).
+    const int mvp = in_cap ? (int)MVP(s) : RK_NONE;
+    const bool moved = mvp != RK_NONE;
+    uint32_t nxy = xy;
+    if (moved) { nxy = BK(s); TXY(s) = nxy; }
+    const bool dead = live && TL(s) <= 0;
+    if (dead) {
+        const int c = xy_y(nxy) * p.W + xy_x(nxy);
+        GRID(c) = G_DEAD;                         // DeadBody overwrites any decoration (core.py:30-31,126-128)
+        atomicOr(&DEADW(c >> 5), 1u << (c & 31));
+        TM(s) &= 0x7f;
+    }
+    const unsigned dead_m = gballot<G, CV>(e, dead);
+    e.deaths += __popc(dead_m);
+    if (wany<G, CV>(e, fresh_scan)) e.deaths += gadd<G, CV>(e, nd_all);  // (nd_all is 0 for an env that did not scan)
+    e.zd += __popc(dead_m >> NP);
+    if (wany<G, CV>(e, succ_m || dead_m)) {  // (an env without changes gets its old ranks back)
+        const bool alive = live && !dead;
+        const unsigned stay_m = gor_bits<G, CV>(e, (alive && !moved) ? (1u << rk) : 0u);
+        const unsigned move_m = gor_bits<G, CV>(e, (alive && moved) ? (1u << mvp) : 0u);
+        if (live) {
+            int nr = RK_NONE;
+            if (alive) {
+                nr = !moved ? __popc(stay_m & ((1u << rk) - 1u)) : __popc(stay_m) + __popc(move_m & ((1u << mvp) - 1u));
+                SOR(nr) = (uint8_t)s;
+            }
+            RK(s) = (uint8_t)nr;
+        }
+        e.nlive = __popc(stay_m) + __popc(move_m);
+    }
+    gsync<G, CV>(e);
+    return k;
 }
 
 // ---------------------------------------------------------------- World.spawn_in_random (core.py:40-66)
@@ -669,18 +1036,18 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
             else { const int x = i / p.H; const int y = i - x * p.H; c = y * p.W + x; }
             ok = !g_is_thing(GRID(c));
         }
-        const unsigned m = gballot<G>(e, ok);
+        const unsigned m = gballot<G, CV>(e, ok);
         if (ok) CAND(n + __popc(m & ((1u << e.gl) - 1u))) = (uint16_t)c;
         n += __popc(m);
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
     const int placed = count < n ? count : n;
 #pragma unroll 1
     for (int it = e.gl; it < placed; it += G) {
         const int i = n - 1 - it;
         DRAWS(it) = i >= 1 ? (uint32_t)below(draw_at(p, e, t_word, k + it), i + 1) : 0u;
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
     if (lane == 0) {
 #pragma unroll 1
         for (int it = 0; it < placed; ++it) {
@@ -698,7 +1065,7 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
         }
         SCALW(ZS_S_STAMP_COUNTER) = rank0 + placed;
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
     return k + (n > 1 ? n - 1 : 0);
 }
 
@@ -717,21 +1084,21 @@ ZS_TPL __device__ __noinline__ int spawn_zombies(const ZsParams& p, GrpId id, in
     for (int b0 = NP; b0 < p.M; b0 += G) {
         const int s = b0 + lane;
         const bool free_slot = s < p.M && !(TM(s) & 0x80);
-        const unsigned m = gballot<G>(e, free_slot);
+        const unsigned m = gballot<G, CV>(e, free_slot);
         const int pos = n + __popc(m & ((1u << e.gl) - 1u));
         if (free_slot && pos < count) LIST(pos) = (uint16_t)s;
         n += __popc(m);
     }
     const int made = count < n ? count : n;
-    gsync<G>(e);
+    gsync<G, CV>(e);
 #pragma unroll 1
     for (int i = e.gl; i < made; i += G) {
         const int s = LIST(i);
         TL(s) = (int16_t)(50 + below(draw_at(p, e, t_word, k + i), 51));
         TM(s) = ZS_WEAPON_CLAWS;
     }
-    gsync<G>(e);
-    return spawn_in_random<MPC, G>(p, id, episode, t_word, k + count, made, 1, rank0);
+    gsync<G, CV>(e);
+    return spawn_in_random<MPC, G, false>(p, id, episode, t_word, k + count, made, 1, rank0);
 }
 
 // Game.__initialize_world__ (game.py:151-169) + reward_tracker.reset (reward.py:26-28).  Out of line and
@@ -759,7 +1126,7 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
         RK(s) = RK_NONE; MVQ(s) = RK_NONE;
         if (s < NP) TL(s) = 100;
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
     // trolls and hamsters are created without a weapon: Player.__init__ draws random.choice([Gun, Shotgun, Rifle,
     // Knife, Axe]) (things.py:115-116), in player_names order, before the agents are created (game.py:157-165)
 #pragma unroll 1
@@ -781,25 +1148,25 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
                                                    : pick == 2 ? ZS_WEAPON_GUN : pick == 3 ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN);
         }
     }
-    gsync<G>(e);
-    build_grid<MPC, G>(p, id, flags);  // every slot is out of the world here: statics (all present) only
+    gsync<G, CV>(e);
+    build_grid<MPC, G, false>(p, id, flags);  // every slot is out of the world here: statics (all present) only
 #pragma unroll 1
     for (int s = e.gl; s < p.P; s += G) LIST(s) = (uint16_t)s;
     if (lane == 0) SCALW(ZS_S_STAMP_COUNTER) = 0;
-    gsync<G>(e);
-    k = spawn_in_random<MPC, G>(p, id, episode, 0u, k, p.P, 0, 0);
+    gsync<G, CV>(e);
+    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.P, 0, 0);
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) LIST(a) = (uint16_t)(p.P + a);
-    gsync<G>(e);
-    k = spawn_in_random<MPC, G>(p, id, episode, 0u, k, p.A, 0, SCALW(ZS_S_STAMP_COUNTER));
-    k = spawn_zombies<MPC, G>(p, id, episode, 0u, k, p.initial_zombies, SCALW(ZS_S_STAMP_COUNTER));
+    gsync<G, CV>(e);
+    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.A, 0, SCALW(ZS_S_STAMP_COUNTER));
+    k = spawn_zombies<MPC, G, false>(p, id, episode, 0u, k, p.initial_zombies, SCALW(ZS_S_STAMP_COUNTER));
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) PREVL(a) = TL(p.P + a);
     if (lane == 0) {
         SCALW(ZS_S_T) = -1; SCALW(ZS_S_EPISODE) = episode; SCALW(ZS_S_DEATHS) = 0; SCALW(ZS_S_ZOMBIE_DEATHS) = 0;
         SCALW(ZS_S_FLAGS) = flags; SCALW(ZS_S_PREV_ZOMBIE_DEATHS) = 0; SCALW(ZS_S_EPISODE_STEPS) = 0;
     }
-    gsync<G>(e);
+    gsync<G, CV>(e);
     return k;
 }
 
@@ -813,8 +1180,8 @@ ZS_TPL __device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, boo
     for (int s0 = 0; s0 < (ONE ? 1 : (NP)); s0 += G) {
         const int s = s0 + lane;
         const bool al = s < NP && TL(s) > 0;
-        alive += __popc(gballot<G>(e, al));
-        ag += __popc(gballot<G>(e, al && s >= p.P));
+        alive += __popc(gballot<G, CV>(e, al));
+        ag += __popc(gballot<G, CV>(e, al && s >= p.P));
     }
     agents_alive = ag > 0;                    // rules/rules.py:13-18
     const bool players_alive = alive > 0;     // rules/rules.py:6-11
@@ -823,7 +1190,8 @@ ZS_TPL __device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, boo
         bool z = false;
 #pragma unroll 1
         for (int s = NP + e.gl; s < p.M; s += G) z |= (TM(s) & 0x80) && TL(s) > 0;
-        ended = !players_alive || !gany<G>(e, z);
+        const bool any_z = gany<G, CV>(e, z);  // (every lane of the warp votes: no short-circuit around a primitive)
+        ended = !players_alive || !any_z;
     } else if (p.rules == ZS_RULES_SURVIVAL) {  // survival.py:5-7
         ended = !players_alive;
     } else if (p.rules == ZS_RULES_SAFEHOUSE) {  // safehouse.py:10-32
@@ -833,14 +1201,15 @@ ZS_TPL __device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, boo
             const uint32_t xy = TXY(s);
             out |= TL(s) > 0 && !objective_bit(p, xy_y(xy) * p.W + xy_x(xy));
         }
-        ended = players_alive ? !gany<G>(e, out) : true;
+        const bool any_out = gany<G, CV>(e, out);
+        ended = players_alive ? !any_out : true;
     } else {  // evacuation.py:13-57: at least half the team alive and the living form one 4-connected cluster
         const bool half = 2 * alive >= NP;  // len(alive) >= len(all) / 2.0
         won = half;
         ended = true;
-        if (half) {
+        {
             int together = 0;
-            if (lane == 0) {
+            if (half && lane == 0) {
                 unsigned long long seen = 0, pending = 0;
                 int first = 0;
                 while (TL(first) <= 0) ++first;
@@ -858,8 +1227,8 @@ ZS_TPL __device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, boo
                     }
                 }
             }
-            together = gbcast<G>(e, together, 0);
-            ended = together == alive;
+            together = gbcast<G, CV>(e, together, 0);
+            if (half) ended = together == alive;
         }
     }
 }

@@ -125,3 +125,6 @@ class ZsEngine(object):
 
     def launch_count(self):
         return int(self.L.zs_launch_count(self.h))
+
+    def lanes_per_env(self):
+        return int(self.L.zs_lanes_per_env(self.h))
