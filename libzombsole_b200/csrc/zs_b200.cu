@@ -30,52 +30,10 @@ __device__ __forceinline__ void discrete_to_action(const ZsParams& p, int id, in
     else type = id == 4 ? ZS_ACT_ATTACK_CLOSEST : id == 5 ? ZS_ACT_HEAL : ZS_ACT_HEAL_CLOSEST;
 }
 
-template <int MODE, int MPC, int G>
-__global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
-    ZS_CONSTS;
-    // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
-    constexpr bool CV = MODE == MODE_STEP;
-    constexpr int EPW = 32 / G;  // envs per warp
-    const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    Env e;
-    e.gl = wlane & (G - 1);
-    e.gshift = wlane & ~(G - 1);
-    e.gm = G == 32 ? 0xffffffffu : (0xffffu << e.gshift);
-    const int slot = wid * EPW + (wlane / G);
-    const int env = blockIdx.x * (ZS_WPC * EPW) + slot;
-    if (p.tmpl_smem_off >= 0) {
-        // stage the pristine observation planes once per CTA: the source of the per-step TMA bulk copies
-        uint4* dst = reinterpret_cast<uint4*>(zs_smem + p.tmpl_smem_off);
-        const uint4* src = reinterpret_cast<const uint4*>(p.tmpl_obs);
-        const int n4 = p.cells >> 2, nsrc = (p.tmpl_planes > 1 ? 2 : 1) * n4;
-        for (int i = threadIdx.x; i < p.tmpl_planes * n4; i += blockDim.x) dst[i] = i < nsrc ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
-        fence_proxy_async_smem();
-        __syncthreads();
-    }
-    if (env >= p.N) return;
-    e.b = (uint32_t)slot * (uint32_t)p.smem_per_env;
-    e.env = env; e.env_global = p.env_base + (uint32_t)env;
-    const int lane = e.gl;
-    ZS_VIEWS;
-
-    if (MODE == MODE_RESET) {
-        if (io.env_mask && !io.env_mask[env]) return;
-        // slots keep their last position/life until re-placed; bring them in so the store is complete
-        load_state<MPC, G, CV>(p, e);
-        const int k = initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
-        scalars_from_smem<MPC, G, CV>(p, e);
-        if (io.draws && lane == 0) io.draws[env] = k;
-        if (io.obs) encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
-        store_state<MPC, G, CV>(p, e);
-        return;
-    }
-    load_state<MPC, G, CV>(p, e);
-    build_grid<MPC, G, false>(p, id_of(e), e.flags);
-    if (MODE == MODE_ENCODE) {
-        encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
-        return;
-    }
-
+// ---------------------------------------------------------------- the K-step loop, more slots than lanes
+ZS_TPL __device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO& io, Env& e) {
+    ZS_CONSTS; ZS_VIEWS;
+    const int lane = e.gl, env = e.env;
     const int A = p.A, NP = p.P + p.A;
     const int R = p.obs_per_agent ? A : 1;
     const bool world_obs = p.obs_scope == ZS_OBS_WORLD;
@@ -122,9 +80,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
         gsync<G, CV>(e);
         if (step + 1 < io.n_steps) fetch_action(step + 1);
 
-        int k;
-        if constexpr (ONE) k = world_step_one<MPC, G, CV>(p, e);
-        else k = world_step<MPC, G, CV>(p, e);
+        int k = world_step<MPC, G, CV>(p, e);
         e.ep_steps += 1;
 
         // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order.
@@ -210,6 +166,170 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
         }
         gsync<G, CV>(e);
     }
+}
+
+// ---------------------------------------------------------------- the K-step loop, one lane per slot
+// Agent a is handled by the lane of its slot (P + a): its action, its tracker life and its reward never leave
+// that lane's registers.  Output cursors advance by one step's stride instead of being recomputed.
+ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io, Env& e) {
+    ZS_CONSTS; ZS_VIEWS;
+    const int lane = e.gl, env = e.env;
+    const int A = p.A, P = p.P, NP = p.P + p.A;
+    const int aidx = lane - P;
+    const bool is_agent = aidx >= 0 && aidx < A;
+    const bool per_agent = p.obs_per_agent != 0;
+    const bool lane_sum = !per_agent && A > 1;  // one reward from the sum of several agents' lives (reward.py:37-41)
+    const bool want_mask = per_agent || io.agent_mask != nullptr;
+    const bool world_obs = p.obs_scope == ZS_OBS_WORLD;
+    const bool auto_reset = p.auto_reset || io.force_auto_reset;
+    // agent actions for the coming step, fetched one step ahead (Agent.set_action, agent.py:22-25)
+    int at = ZS_ACT_NONE, adx = 0, ady = 0;
+    auto fetch_action = [&](int step) {
+        at = ZS_ACT_NONE; adx = 0; ady = 0;
+        if (!is_agent) return;
+        const size_t ia = ((size_t)step * p.N + env) * A + aidx;
+        if (io.actions == nullptr) discrete_to_action(p, synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), aidx), at, adx, ady);
+        else if (io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, io.actions[ia], at, adx, ady);
+        else { const int32_t* q = io.actions + ia * 3; at = q[0]; adx = q[1]; ady = q[2]; }
+    };
+    fetch_action(0);
+    const size_t obs_stride = (size_t)p.N * p.obs_elems;
+    int32_t* const obs_first = io.obs ? io.obs + (size_t)env * p.obs_elems : nullptr;
+    int32_t* obs_cur = obs_first;
+    int oslot = 0;
+    size_t sn = env;  // step * N + env
+#pragma unroll 1
+    for (int step = 0; step < io.n_steps; ++step, sn += p.N) {
+        int32_t* const obs_out = obs_cur;
+        if (obs_out) {
+            if (++oslot >= io.obs_slots) { oslot = 0; obs_cur = obs_first; } else obs_cur += obs_stride;
+            // pass 1 of the world observation does not depend on the transition: issue its stores now
+            if (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
+        }
+        // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
+        unsigned alive_before = 0;
+        if (want_mask) alive_before = gballot<G, CV>(e, is_agent && TL(is_agent ? lane : 0) > 0) >> P;
+        const int life_before = is_agent ? (int)PREVL(aidx) : 0;
+        const int zd_before = e.prev_zd;
+        const int my_at = at, my_dx = adx, my_dy = ady;
+        if (step + 1 < io.n_steps) fetch_action(step + 1);
+
+        int k = world_step_one<MPC, G, CV>(p, e, my_at, my_dx, my_dy);
+        e.ep_steps += 1;
+
+        // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order.
+        // A tracker whose inputs did not change yields exactly +0.0.
+        const int life_now = is_agent ? (int)TL(lane) : 0;
+        double rew = 0.0;
+        if (lane_sum) {
+            const int sum_prev = gadd<G, CV>(e, life_before), sum_new = gadd<G, CV>(e, life_now);
+            if (sum_prev != sum_new || zd_before != e.zd) rew = __dsub_rn(total_reward(e.zd, sum_new), total_reward(zd_before, sum_prev));
+        } else if (is_agent && (life_before != life_now || zd_before != e.zd)) {
+            rew = __dsub_rn(total_reward(e.zd, life_now), total_reward(zd_before, life_before));
+        }
+        if (is_agent) PREVL(aidx) = (int16_t)life_now;
+        e.prev_zd = e.zd;
+
+        // ---- Game.spawn_zombies_to_maintain_minimum (game.py:196-201)
+        if (p.minimum_zombies > 0) {
+            const int zc = __popc(gballot<G, CV>(e, lane >= NP && lane < p.M && (TM(lane < p.M ? lane : 0) & 0x80)));
+            if (zc < p.minimum_zombies) {  // rare, and possibly only one env of the warp: the divergent flavour
+                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive);
+                e.nlive = SCALW(ZS_S_STAMP_COUNTER);
+            }
+        }
+
+        // ---- rules and end reward (gym_env.py:130-141, multiagent_env.py:143-162)
+        bool ended, won, agents_alive;
+        rules_eval<MPC, G, CV>(p, e, ended, won, agents_alive);
+        bool done = false, trunc = false;
+        double end_reward = 0.0;
+        if (ended) { done = true; end_reward = won ? 10.0 : -10.0; }
+        else if (!agents_alive) { trunc = true; end_reward = -10.0; }
+        if (!per_agent) {
+            if (done || trunc) rew = __dadd_rn(rew, end_reward);
+            if (io.reward && (lane_sum ? lane == 0 : aidx == 0)) io.reward[sn] = rew;
+            if (io.agent_mask && is_agent) io.agent_mask[sn * A + aidx] = (alive_before >> aidx) & 1u;
+        } else if (is_agent) {
+            if (!((alive_before >> aidx) & 1u)) rew = 0.0;
+            else if (life_now > 0) rew = __dadd_rn(rew, end_reward);
+            if (io.reward) io.reward[sn * A + aidx] = rew;
+            if (io.agent_mask) io.agent_mask[sn * A + aidx] = (alive_before >> aidx) & 1u;
+        }
+        if (p.max_steps > 0 && e.ep_steps >= p.max_steps) trunc = true;  // gymnasium TimeLimit
+        if (lane == 0) {
+            if (io.terminated) io.terminated[sn] = done;
+            if (io.truncated) io.truncated[sn] = trunc;
+            if (io.draws) io.draws[sn] = k;
+        }
+
+        // ---- same-step auto-reset (rare, and possibly only one env of the warp: the divergent flavour)
+        if ((done || trunc) && auto_reset) {
+            if (lane == 0) {
+                atomicAdd(p.stats + 0, 1ull);
+                if (done && won) atomicAdd(p.stats + 1, 1ull);
+                atomicAdd(p.stats + 2, (unsigned long long)e.ep_steps);
+                atomicAdd(p.stats + 3, (unsigned long long)e.zd);
+            }
+            initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
+            scalars_from_smem<MPC, G, false>(p, e);
+        }
+        if (obs_out) {
+            if (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
+            else encode_surroundings<MPC, G, CV>(p, e, obs_out);
+        }
+        gsync<G, CV>(e);
+    }
+}
+
+template <int MODE, int MPC, int G>
+__global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
+    ZS_CONSTS;
+    // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
+    constexpr bool CV = MODE == MODE_STEP;
+    constexpr int EPW = 32 / G;  // envs per warp
+    const int wlane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    Env e;
+    e.gl = wlane & (G - 1);
+    e.gshift = wlane & ~(G - 1);
+    e.gm = G == 32 ? 0xffffffffu : (0xffffu << e.gshift);
+    const int slot = wid * EPW + (wlane / G);
+    const int env = blockIdx.x * (ZS_WPC * EPW) + slot;
+    if (p.tmpl_smem_off >= 0) {
+        // stage the pristine observation planes once per CTA: the source of the per-step TMA bulk copies
+        uint4* dst = reinterpret_cast<uint4*>(zs_smem + p.tmpl_smem_off);
+        const uint4* src = reinterpret_cast<const uint4*>(p.tmpl_obs);
+        const int n4 = p.cells >> 2, nsrc = (p.tmpl_planes > 1 ? 2 : 1) * n4;
+        for (int i = threadIdx.x; i < p.tmpl_planes * n4; i += blockDim.x) dst[i] = i < nsrc ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+        fence_proxy_async_smem();
+        __syncthreads();
+    }
+    if (env >= p.N) return;
+    e.b = (uint32_t)slot * (uint32_t)p.smem_per_env;
+    e.env = env; e.env_global = p.env_base + (uint32_t)env;
+    const int lane = e.gl;
+    ZS_VIEWS;
+
+    if (MODE == MODE_RESET) {
+        if (io.env_mask && !io.env_mask[env]) return;
+        // slots keep their last position/life until re-placed; bring them in so the store is complete
+        load_state<MPC, G, CV>(p, e);
+        const int k = initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
+        scalars_from_smem<MPC, G, CV>(p, e);
+        if (io.draws && lane == 0) io.draws[env] = k;
+        if (io.obs) encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
+        store_state<MPC, G, CV>(p, e);
+        return;
+    }
+    load_state<MPC, G, CV>(p, e);
+    build_grid<MPC, G, false>(p, id_of(e), e.flags);
+    if (MODE == MODE_ENCODE) {
+        encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
+        return;
+    }
+
+    if constexpr (ONE) step_loop_one<MPC, G, CV>(p, io, e);
+    else step_loop_general<MPC, G, CV>(p, io, e);
     store_state<MPC, G, CV>(p, e);
 }
 

@@ -39,6 +39,7 @@
 
 #define RK_NONE 255           // rank of a slot that is not in the world
 #define ZS_DMG_CAP 24         // damaged boxes/walls tracked individually; more than that -> full scan
+#define ZS_DEAD_CAP 38        // dead-body cells tracked individually (one-lane-per-slot kernels); more -> bitmap scan
 #define ZS_NP_MAX (ZS_MAX_BOTS + ZS_MAX_AGENTS)
 
 struct ZsParams {
@@ -132,6 +133,7 @@ struct alignas(16) EnvS {
     uint16_t list[MPC];
     int16_t prev[MPC < ZS_MAX_AGENTS ? MPC : ZS_MAX_AGENTS];  // reward tracker's agents_life
     uint16_t dmg[ZS_DMG_CAP + 8];           // dmg[0] = count, dmg[1..] = damaged static indices
+    uint16_t dbl[ZS_DEAD_CAP + 2];          // dbl[0] = count, dbl[1..] = cells that got a dead body in this world (repeats allowed)
     uint8_t tm[MPC];                        // bit7 in world, bits0-3 weapon code
     uint8_t rk[MPC];                        // dict-order rank among the things in the world (RK_NONE if absent)
     uint8_t sor[MPC];                       // slot of a rank
@@ -153,6 +155,7 @@ struct Env {
 #define FL_DMG 2         // some box/wall has life != MAX_LIFE (else the observation needs no static patches)
 #define FL_SL_DIRTY 4    // static lives changed during this launch: write them back
 #define FL_DMG_OVER 8    // more than ZS_DMG_CAP damaged boxes/walls: scan instead of using the list
+#define FL_DEAD_OVER 16  // the dead-body list is not complete (overflow, or a kernel that does not keep it): scan the bitmap
 
 // Bind the shared-memory views of `e` in the current scope (S: the struct; GRIDP/DEADP/SLP/CANDP: the tail).
 #define ZS_VIEWS                                                                                   \
@@ -185,6 +188,7 @@ struct Env {
 #define SCALW(i) S.scal[i]
 #define MASKW(i) S.masks[i]
 #define DMG(i) S.dmg[i]
+#define DBL(i) S.dbl[i]
 
 // ---------------------------------------------------------------- TMA bulk copies (shared -> global)
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {

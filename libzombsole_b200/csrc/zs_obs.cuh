@@ -87,10 +87,10 @@ __device__ __forceinline__ void obs_store_cell(const ZsParams& p, int32_t* obs, 
     else { obs[c] = channel_label(p, ci); obs[p.cells + c] = ci.life; obs[2 * p.cells + c] = ci.weapon; }
 }
 
-// World scope, pass 2: the cells that differ from the pristine layer are patched with scalar stores, in the
-// layering order of the reference (decorations under things, observation.py:41-42): damaged or destroyed
-// boxes/walls, then dead bodies, then the mobile things.  Each layer is separated by __syncwarp(), which
-// orders the stores of different lanes to the same address (and all of them after pass 1).
+// World scope, pass 2: the cells that differ from the pristine layer are patched with scalar stores.  The
+// reference shows the thing on a cell, else its decoration (observation.py:41-42); the occupancy grid says which
+// one that is, so every patched cell is written by exactly one lane and the three kinds of patches (damaged or
+// destroyed boxes/walls, dead bodies, mobile things) need no ordering among themselves — only after pass 1.
 ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e, int32_t* obs) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl;
@@ -105,26 +105,37 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const 
             const int si = over ? i : (int)DMG(1 + i);
             const int life = SL(si);
             if (over && life == __ldg(p.static_max + si)) continue;
+            const int cell = __ldg(p.static_cell + si);
             CellInfo ci;
             ci.life = life; ci.weapon = 0; ci.agent = -1;
             ci.label = __ldg(p.static_label + si);
-            if (life <= 0 && !fresh) { ci.label = 0; ci.life = 0; }  // destroyed: gone from World.things
-            obs_store_cell(p, obs, __ldg(p.static_cell + si), ci);
+            if (life <= 0 && !fresh) {  // destroyed: gone from World.things; whatever took the cell patches it itself
+                if (GRID(cell) != G_EMPTY) continue;
+                ci.label = 0; ci.life = 0;
+            }
+            obs_store_cell(p, obs, cell, ci);
         }
     }
-    gsync<G, CV>(e);
+    CellInfo body;
+    body.label = ZS_LABEL_DEAD_BODY; body.life = 0; body.weapon = 0; body.agent = -1;
+    if (!(e.flags & FL_DEAD_OVER)) {  // dead bodies of this world, from the list (a thing standing on one hides it)
+        const int n_list = DBL(0);
 #pragma unroll 1
-    for (int w = lane; w < p.dead_words; w += G) {
-        uint32_t bits = DEADW(w);
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            CellInfo ci;
-            ci.label = ZS_LABEL_DEAD_BODY; ci.life = 0; ci.weapon = 0; ci.agent = -1;
-            obs_store_cell(p, obs, w * 32 + b, ci);
+        for (int i = lane; i < n_list; i += G) {
+            const int c = DBL(1 + i);
+            if (GRID(c) == G_DEAD) obs_store_cell(p, obs, c, body);
+        }
+    } else {
+#pragma unroll 1
+        for (int w = lane; w < p.dead_words; w += G) {
+            uint32_t bits = DEADW(w);
+            while (bits) {
+                const int c = w * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (GRID(c) == G_DEAD) obs_store_cell(p, obs, c, body);
+            }
         }
     }
-    gsync<G, CV>(e);
 #pragma unroll 1
     for (int s = lane; s < p.M; s += G) {
         const int m = TM(s);

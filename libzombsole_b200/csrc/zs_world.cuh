@@ -88,6 +88,37 @@ ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId
     return n == 0 ? 0 : (n <= ZS_DMG_CAP ? FL_DMG : (FL_DMG | FL_DMG_OVER));
 }
 
+// The cells that carry a dead body, as a short list (or, past ZS_DEAD_CAP, a flag for bitmap scans).
+ZS_TPL __device__ __noinline__ int scan_dead_bodies(const ZsParams& p, GrpId id) {
+    ZS_CONSTS;
+    Env e = env_of(p, id);
+    ZS_VIEWS;
+    int n = 0;
+#pragma unroll 1
+    for (int w0 = 0; w0 < p.dead_words; w0 += G) {
+        const int w = w0 + e.gl;
+        uint32_t bits = w < p.dead_words ? DEADW(w) : 0u;
+        // lanes take turns appending their word's cells (rare: once per launch)
+#pragma unroll 1
+        for (int l = 0; l < G; ++l) {
+            const int cnt = gbcast<G, CV>(e, __popc(bits), l);
+            if (e.gl == l) {
+                int m = n;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (m < ZS_DEAD_CAP) DBL(1 + m) = (uint16_t)(w * 32 + b);
+                    ++m;
+                }
+            }
+            n += cnt;
+        }
+    }
+    if (e.gl == 0) DBL(0) = (uint16_t)(n < ZS_DEAD_CAP ? n : ZS_DEAD_CAP);
+    gsync<G, CV>(e);
+    return n <= ZS_DEAD_CAP ? 0 : FL_DEAD_OVER;
+}
+
 ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
     const size_t row = (size_t)e.env * p.Mp;
@@ -107,6 +138,8 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
     gsync<G, CV>(e);
     e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e));
     e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e));
+    if (ONE) e.flags |= scan_dead_bodies<MPC, G, false>(p, id_of(e));
+    else e.flags |= FL_DEAD_OVER;
 }
 
 ZS_TPL __device__ __forceinline__ void store_state(const ZsParams& p, Env& e) {
@@ -679,7 +712,8 @@ ZS_TPL __device__ __noinline__ void execute_sequential(const ZsParams& p, GrpId 
     gsync<G, CV>(e);
 }
 
-ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e) {
+// (at, adx, ady): the action of the agent whose slot this lane is (Agent.set_action, agent.py:22-25).
+ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, int at, int adx, int ady) {
     ZS_VIEWS;
     static_assert(MPC <= G, "one lane per slot");
     const int s = e.gl;  // slot in slot space, list position in position space
@@ -696,11 +730,8 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e) 
     const int x = xy_x(xy), y = xy_y(xy);
     const bool zombie = s >= NP, agent = !zombie && s >= p.P;
     const int bkind = s < p.P ? (int)p.bot_kinds[s] : -1;
-    int at = ZS_ACT_NONE, adx = 0, ady = 0;
-    if (live && agent) {
-        at = ACTS(3 * (s - p.P)); adx = ACTS(3 * (s - p.P) + 1); ady = ACTS(3 * (s - p.P) + 2);
-        if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; adx = 0; ady = 0; }  // multiagent_env.py:129-131
-    }
+    if (!(live && agent)) at = ZS_ACT_NONE;
+    else if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; adx = 0; ady = 0; }  // multiagent_env.py:129-131
     const bool has_humans = gany<G, CV>(e, live && !zombie);
 
     // ---- closest(self, others) (utils.py:23-31) for everybody from ONE pass over the (thing, player) distances:
@@ -988,6 +1019,15 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e) 
         TM(s) &= 0x7f;
     }
     const unsigned dead_m = gballot<G, CV>(e, dead);
+    if (wany<G, CV>(e, dead)) {  // remember the cells for the observation patches (the bitmap stays the state)
+        const int n0 = DBL(0), idx = n0 + __popc(dead_m & below_s), tot = n0 + __popc(dead_m);
+        gsync<G, CV>(e);  // (everybody has read the count before lane 0 rewrites it)
+        if (dead && idx < ZS_DEAD_CAP) DBL(1 + idx) = (uint16_t)(xy_y(nxy) * p.W + xy_x(nxy));
+        if (dead_m) {
+            if (tot > ZS_DEAD_CAP) e.flags |= FL_DEAD_OVER;
+            if (s == 0) DBL(0) = (uint16_t)(tot < ZS_DEAD_CAP ? tot : ZS_DEAD_CAP);
+        }
+    }
     e.deaths += __popc(dead_m);
     if (wany<G, CV>(e, fresh_scan)) e.deaths += gadd<G, CV>(e, nd_all);  // (nd_all is 0 for an env that did not scan)
     e.zd += __popc(dead_m >> NP);
@@ -1111,10 +1151,11 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
     ZS_VIEWS;
     const int lane = e.gl;
     const int NP = p.P + p.A;
-    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY | FL_DMG_OVER)) | FL_FRESH;
+    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY | FL_DMG_OVER)) | FL_FRESH | (ONE ? 0 : FL_DEAD_OVER);
     e.episode = episode;
 #pragma unroll 1
     for (int w = e.gl; w < p.dead_words; w += G) DEADW(w) = 0;
+    if (lane == 0) DBL(0) = 0;  // a new world has no dead bodies
     int k = 0;
 #pragma unroll 1
     for (int s = e.gl; s < p.Mp; s += G) {
