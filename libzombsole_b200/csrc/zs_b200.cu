@@ -213,6 +213,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
         const int zd_before = e.prev_zd;
         const int my_at = at, my_dx = adx, my_dy = ady;
         if (step + 1 < io.n_steps) fetch_action(step + 1);
+        PH(0);
 
         int k = world_step_one<MPC, G, CV>(p, e, my_at, my_dx, my_dy);
         e.ep_steps += 1;
@@ -263,6 +264,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
             if (io.draws) io.draws[sn] = k;
         }
 
+        PH(9);
         // ---- same-step auto-reset (rare, and possibly only one env of the warp: the divergent flavour)
         if ((done || trunc) && auto_reset) {
             if (lane == 0) {
@@ -274,12 +276,23 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
             initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
             scalars_from_smem<MPC, G, false>(p, e);
         }
+        PH(10);
         if (obs_out) {
             if (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
             else encode_surroundings<MPC, G, CV>(p, e, obs_out);
         }
         gsync<G, CV>(e);
+        PH(11);
     }
+#ifdef ZS_PHASE_CLOCKS
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long tot = 0;
+        for (int i = 0; i < 13; ++i) tot += zs_ph[i];
+        printf("phase cycles/step over %d steps (total %.0f):", io.n_steps, (double)tot / io.n_steps);
+        for (int i = 0; i < 13; ++i) { printf(" [%d] %.0f", i, (double)zs_ph[i] / io.n_steps); zs_ph[i] = 0; }
+        printf("\n");
+    }
+#endif
 }
 
 template <int MODE, int MPC, int G>
@@ -328,6 +341,9 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
         return;
     }
 
+#ifdef ZS_PHASE_CLOCKS
+    e.ph_last = clock64();
+#endif
     if constexpr (ONE) step_loop_one<MPC, G, CV>(p, io, e);
     else step_loop_general<MPC, G, CV>(p, io, e);
     store_state<MPC, G, CV>(p, e);
@@ -587,11 +603,13 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     if (p.Z > 0) { int zc = p.n_zs > 0 ? p.n_zs : cells; if (zc > cand) cand = zc; }
     p.cand_cap = cand;
     p.off_cand = take(cand * 2);
+    p.off_spl = take(p.Sp * 4);
+    p.off_sidx = take(p.Sp);
     p.smem_per_env = round_up(struct_bytes + off, 16);
-    // lanes per env: a half warp when an env has at most 16 slots AND the batch does not fit the chip as
-    // one full-warp wave (148 SMs x 28 resident warps); small batches are latency-bound and want the lanes
-    // (two envs per warp run in lock-step: an odd env count would leave half a warp without an env)
-    h->lanes_per_env = (p.mpc == 16 && p.N % 2 == 0 && p.N > prop.multiProcessorCount * ZS_MIN_CTAS * ZS_WPC) ? 16 : 32;
+    // lanes per env: a half warp (two envs per warp, in lock-step) when an env has at most 16 slots, the env count is
+    // even and the batch is large enough that the halved instruction count matters more than the few extra cycles a
+    // two-env warp needs per step (measured cross-over: about 16 envs per SM)
+    h->lanes_per_env = (p.mpc == 16 && p.N % 2 == 0 && p.N > prop.multiProcessorCount * 16) ? 16 : 32;
     if (const char* force = getenv("ZS_LANES_PER_ENV")) {
         const int v = atoi(force);
         if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) h->lanes_per_env = v;

@@ -8,7 +8,7 @@
 //     and the per-step scratch, in a struct templated on the slot capacity MPC so that every field has
 //     a COMPILE-TIME offset (LDS [base + imm]);
 //   * after it, at run-time offsets: the occupancy grid, one byte per map cell (0 empty, 1..250 mobile
-//     slot+1, 253/255 box or wall, 254 dead-body decoration) — the shared-memory-staged stand-in for
+//     slot+1, 255 box or wall, 254 dead-body decoration) — the shared-memory-staged stand-in for
 //     the reference's position-keyed dicts World.things / World.decoration (zombsole/core.py:15-16) —
 //     the dead-body bitmap, the static lives and the spawn candidate list.
 // Phases that are parallel in the reference's semantics (every actor decides against the pre-step
@@ -23,10 +23,9 @@
 #define ZS_WPC 4              // warps per CTA
 #define ZS_MIN_CTAS 7         // 7 CTAs x 4 warps resident per SM: 4,096 full-warp envs fit the 148 SMs in one wave
 
-// occupancy-grid byte codes
+// occupancy-grid byte codes (a box/wall is on the grid while it is in World.things, whatever its life)
 #define G_EMPTY 0
 #define G_MAX_SLOT 250        // 1..250: mobile slot + 1
-#define G_STATIC_DMG 253      // box/wall present, life != MAX_LIFE
 #define G_DEAD 254            // DeadBody decoration and no thing
 #define G_STATIC 255          // pristine box/wall present
 
@@ -38,7 +37,6 @@
 #define D_WANDER 4            // zombie with no humans: destination drawn in dict order (things.py:101-103)
 
 #define RK_NONE 255           // rank of a slot that is not in the world
-#define ZS_DMG_CAP 24         // damaged boxes/walls tracked individually; more than that -> full scan
 #define ZS_DEAD_CAP 38        // dead-body cells tracked individually (one-lane-per-slot kernels); more -> bitmap scan
 #define ZS_NP_MAX (ZS_MAX_BOTS + ZS_MAX_AGENTS)
 
@@ -71,7 +69,7 @@ struct ZsParams {
     int16_t* PREV; int16_t* SLIFE; uint32_t* DEAD; int32_t* SCAL;
     unsigned long long* stats;     // [4]
     // ---- shared memory: run-time sized tail behind EnvS<MPC> (byte offsets from the end of the struct)
-    int32_t off_dead, off_sl, off_cand;
+    int32_t off_dead, off_sl, off_cand, off_spl, off_sidx;
     int32_t cand_cap;
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
     int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
@@ -119,20 +117,21 @@ extern __shared__ __align__(16) unsigned char zs_smem[];
 
 template <int MPC>
 struct alignas(16) EnvS {
+    static constexpr int GEN = MPC > 32 ? MPC : 1;  // arrays only the general (more slots than lanes) kernels use
     unsigned long long act[MPC];            // the step's action list (packed, see pack_action)
     uint32_t txy[MPC];                      // x | y << 16 (int16 each)
     uint32_t bk[MPC];                       // per step: closest-player key of a zombie / heal_closest agent
-    uint32_t draws[3 * MPC + 16];           // per step: the draws, 4 per Philox block
-    uint32_t zb[MPC < ZS_NP_MAX ? MPC : ZS_NP_MAX];  // per step: closest-zombie key of a player slot
+    uint32_t draws[3 * MPC + 4];            // per step: the draws, 4 per Philox block
+    uint32_t zb[GEN < ZS_NP_MAX ? GEN : ZS_NP_MAX];  // per step: closest-zombie key of a player slot
     int32_t scal[8];                        // scalar hand-off around out-of-line functions
-    int32_t acts[3 * (MPC < ZS_MAX_AGENTS ? MPC : ZS_MAX_AGENTS) + 1];  // agent actions of the step (type, dx, dy)
+    int32_t acts[3 * (GEN < ZS_MAX_AGENTS ? GEN : ZS_MAX_AGENTS) + 1];  // agent actions of the step (type, dx, dy)
     uint32_t masks[2 * ((MPC + 31) / 32) + 2];  // rank bit-masks: stayers, then movers
     int16_t tl[MPC];                        // life
-    int16_t da[MPC];
-    int16_t db[MPC];
+    int16_t da[GEN];
+    int16_t db[GEN];
     uint16_t list[MPC];
     int16_t prev[MPC < ZS_MAX_AGENTS ? MPC : ZS_MAX_AGENTS];  // reward tracker's agents_life
-    uint16_t dmg[ZS_DMG_CAP + 8];           // dmg[0] = count, dmg[1..] = damaged static indices
+    uint16_t spn[8];                        // spn[0] = entries of the static patch list (SPL, in the run-time tail)
     uint16_t dbl[ZS_DEAD_CAP + 2];          // dbl[0] = count, dbl[1..] = cells that got a dead body in this world (repeats allowed)
     uint8_t tm[MPC];                        // bit7 in world, bits0-3 weapon code
     uint8_t rk[MPC];                        // dict-order rank among the things in the world (RK_NONE if absent)
@@ -149,12 +148,14 @@ struct Env {
     int32_t gl;       // lane within the group
     uint32_t gm;      // member mask of the group
     int32_t gshift;   // first lane of the group within the warp
+#ifdef ZS_PHASE_CLOCKS
+    long long ph_last;
+#endif
 };
 // Env::flags: bit0 is state (ZS_S_FLAGS); the others live for one launch only
 #define FL_FRESH 1       // first step of a world: boxes/walls with life <= 0 are still present
-#define FL_DMG 2         // some box/wall has life != MAX_LIFE (else the observation needs no static patches)
+#define FL_DMG 2         // the static patch list is not empty
 #define FL_SL_DIRTY 4    // static lives changed during this launch: write them back
-#define FL_DMG_OVER 8    // more than ZS_DMG_CAP damaged boxes/walls: scan instead of using the list
 #define FL_DEAD_OVER 16  // the dead-body list is not complete (overflow, or a kernel that does not keep it): scan the bitmap
 
 // Bind the shared-memory views of `e` in the current scope (S: the struct; GRIDP/DEADP/SLP/CANDP: the tail).
@@ -164,7 +165,9 @@ struct Env {
     uint32_t* const DEADP = reinterpret_cast<uint32_t*>(GRIDP + p.off_dead);                         \
     int16_t* const SLP = reinterpret_cast<int16_t*>(GRIDP + p.off_sl);                               \
     uint16_t* const CANDP = reinterpret_cast<uint16_t*>(GRIDP + p.off_cand);                         \
-    (void)S; (void)GRIDP; (void)DEADP; (void)SLP; (void)CANDP
+    uint32_t* const SPLP = reinterpret_cast<uint32_t*>(GRIDP + p.off_spl);                           \
+    uint8_t* const SIDXP = GRIDP + p.off_sidx;                         \
+    (void)S; (void)GRIDP; (void)DEADP; (void)SLP; (void)CANDP; (void)SPLP; (void)SIDXP
 #define GRID(i) GRIDP[i]
 #define DEADW(i) DEADP[i]
 #define SL(i) SLP[i]
@@ -187,7 +190,9 @@ struct Env {
 #define ZB(i) S.zb[i]
 #define SCALW(i) S.scal[i]
 #define MASKW(i) S.masks[i]
-#define DMG(i) S.dmg[i]
+#define SPN S.spn[0]
+#define SPL(i) SPLP[i]
+#define SIDX(i) SIDXP[i]
 #define DBL(i) S.dbl[i]
 
 // ---------------------------------------------------------------- TMA bulk copies (shared -> global)
@@ -198,6 +203,24 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---------------------------------------------------------------- phase clocks (development builds only)
+// -DZS_PHASE_CLOCKS: thread 0 of CTA 0 accumulates the cycles it spends in each phase of the step loop and prints
+// them at the end of the launch (tools/phase_clocks.sh) — the latency chain of one warp, which is what bounds
+// small batches.
+#ifdef ZS_PHASE_CLOCKS
+__device__ unsigned long long zs_ph[20];
+#define PH(i)                                                                         \
+    do {                                                                              \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                                    \
+            const long long _c = clock64();                                           \
+            atomicAdd(&zs_ph[i], (unsigned long long)(_c - e.ph_last));               \
+            e.ph_last = clock64();                                                    \
+        }                                                                             \
+    } while (0)
+#else
+#define PH(i) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------- lane-group primitives
 // G = lanes per env.  With G == 16 a *.sync primitive on the half warp's own member mask costs a convergence
@@ -260,7 +283,7 @@ __device__ __forceinline__ uint32_t draw_at(const ZsParams& p, const Env& e, uin
 __device__ __forceinline__ int below(uint32_t u, int n) { return (int)__umulhi(u, (uint32_t)n); }
 
 __device__ __forceinline__ bool g_is_thing(int g) { return g != G_EMPTY && g != G_DEAD; }
-__device__ __forceinline__ bool g_is_static(int g) { return g == G_STATIC || g == G_STATIC_DMG; }
+__device__ __forceinline__ bool g_is_static(int g) { return g == G_STATIC; }
 
 // World.things.get((x, y)) as a grid byte; positions outside the map hold nothing
 __device__ __forceinline__ int grid_at(const ZsParams& p, const uint8_t* GRIDP, int x, int y) {
@@ -280,3 +303,19 @@ __device__ __forceinline__ int adj_dy(int a) { return a == 0 ? 1 : a == 1 ? -1 :
 
 __device__ __forceinline__ int floordiv100(int a) { return a >= 0 ? a / 100 : -((-a + 99) / 100); }
 __device__ __forceinline__ int max_life_of_label(int label) { return label == ZS_LABEL_BOX ? 10 : 200; }
+
+// ---------------------------------------------------------------- the static patch list (SPL)
+// Boxes and walls keep their damage across episodes (game.py:154-155), so over a long run more and more cells
+// differ from the pristine observation template.  SPL holds one 32-bit entry per box/wall whose OBSERVATION differs
+// (cell | payload << 16): the world-scope observation patches them every step straight from the list, the first
+// clean_dead_things of a world and the grid rebuild walk it instead of all the statics, and SIDX (one byte per static:
+// 0 not listed, entry + 1, or 255 = listed further back, found by searching for the cell) finds the entry when the
+// box/wall is hit again.  Payload: simple encoding — the cell value itself; channels —
+// label << 12 | (life & 0xfff); 0 — the box/wall is gone from World.things.  Entries are never removed.
+__device__ __forceinline__ int static_payload(const ZsParams& p, int max_life, int life, bool present) {
+    if (!present) return 0;
+    const int label = max_life == 10 ? ZS_LABEL_BOX : ZS_LABEL_WALL;
+    if (p.obs_enc == ZS_OBS_SIMPLE) { const int adj = life < 100 ? life : 100; return 256 * label + floordiv100(15 * adj); }
+    return (label << 12) | (life & 0xfff);
+}
+#define SIDX_FAR 255

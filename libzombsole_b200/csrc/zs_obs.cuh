@@ -91,29 +91,23 @@ __device__ __forceinline__ void obs_store_cell(const ZsParams& p, int32_t* obs, 
 // reference shows the thing on a cell, else its decoration (observation.py:41-42); the occupancy grid says which
 // one that is, so every patched cell is written by exactly one lane and the three kinds of patches (damaged or
 // destroyed boxes/walls, dead bodies, mobile things) need no ordering among themselves — only after pass 1.
-ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, const Env& e, int32_t* obs) {
+ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e, int32_t* obs) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl;
-    const bool fresh = e.flags & FL_FRESH;
     if (p.tmpl_smem_off >= 0 && lane == 0) bulk_wait_all();  // pass 1 (TMA) has landed before any cell is patched
     gsync<G, CV>(e);
-    if (e.flags & FL_DMG) {  // launch-lifetime: the boxes/walls whose life differs from MAX_LIFE (a short list)
-        const bool over = e.flags & FL_DMG_OVER;
-        const int n_list = over ? p.S : (int)DMG(0);
+    PH(12);
+    if (e.flags & FL_DMG) {  // boxes/walls whose observation differs from the template: the static patch list
+        const int n_list = SPN;
+        const bool simple = p.obs_enc == ZS_OBS_SIMPLE;
 #pragma unroll 1
         for (int i = lane; i < n_list; i += G) {
-            const int si = over ? i : (int)DMG(1 + i);
-            const int life = SL(si);
-            if (over && life == __ldg(p.static_max + si)) continue;
-            const int cell = __ldg(p.static_cell + si);
-            CellInfo ci;
-            ci.life = life; ci.weapon = 0; ci.agent = -1;
-            ci.label = __ldg(p.static_label + si);
-            if (life <= 0 && !fresh) {  // destroyed: gone from World.things; whatever took the cell patches it itself
-                if (GRID(cell) != G_EMPTY) continue;
-                ci.label = 0; ci.life = 0;
-            }
-            obs_store_cell(p, obs, cell, ci);
+            const uint32_t w = SPL(i);
+            const int cell = w & 0xffffu, pay = w >> 16;
+            // gone from World.things: whatever took the cell patches it itself
+            if (pay == 0 && GRID(cell) != G_EMPTY) continue;
+            if (simple) obs[cell] = pay;
+            else { obs[cell] = pay >> 12; obs[p.cells + cell] = (int)((uint32_t)pay << 20) >> 20; obs[2 * p.cells + cell] = 0; }
         }
     }
     CellInfo body;
@@ -180,7 +174,7 @@ ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, co
     }
 }
 
-ZS_TPL __device__ __forceinline__ void encode_obs(const ZsParams& p, const Env& e, int32_t* obs) {
+ZS_TPL __device__ __forceinline__ void encode_obs(const ZsParams& p, Env& e, int32_t* obs) {
     if (p.obs_scope == ZS_OBS_WORLD) { obs_world_template<MPC, G, CV>(p, e, obs); obs_world_patch<MPC, G, CV>(p, e, obs); }
     else encode_surroundings<MPC, G, CV>(p, e, obs);
 }

@@ -67,25 +67,81 @@ ZS_TPL __device__ __noinline__ int ranks_from_stamps(const ZsParams& p, GrpId id
     return n;
 }
 
-// Which boxes/walls differ from their MAX_LIFE: a short list (DMG) or, past ZS_DMG_CAP, a flag for full scans.
-ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId id) {
+// Build the static patch list (zs_device.cuh) from the static lives: state import / start of a launch.
+ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId id, int fresh) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
-    const int lane = e.gl;
     int n = 0;
 #pragma unroll 1
     for (int i0 = 0; i0 < p.Sp; i0 += G) {
-        const int i = i0 + lane;
-        const bool dmg = i < p.Sp && SL(i) != __ldg(p.static_max + i);
-        const unsigned m = gballot<G, CV>(e, dmg);
+        const int i = i0 + e.gl;
+        bool listed = false;
+        int pay = 0;
+        if (i < p.S) {
+            const int life = SL(i), mx = __ldg(p.static_max + i);
+            pay = static_payload(p, mx, life, life > 0 || fresh);
+            listed = pay != static_payload(p, mx, mx, true);
+        }
+        const unsigned m = gballot<G, CV>(e, listed);
         const int pos = n + __popc(m & ((1u << e.gl) - 1u));
-        if (dmg && pos < ZS_DMG_CAP) DMG(1 + pos) = (uint16_t)i;
+        if (listed) SPL(pos) = (uint32_t)__ldg(p.static_cell + i) | ((uint32_t)pay << 16);
+        if (i < p.Sp) SIDX(i) = listed ? (uint8_t)(pos + 1 < SIDX_FAR ? pos + 1 : SIDX_FAR) : (uint8_t)0;
         n += __popc(m);
     }
-    if (lane == 0) DMG(0) = (uint16_t)(n < ZS_DMG_CAP ? n : ZS_DMG_CAP);
+    if (e.gl == 0) SPN = (uint16_t)n;
     gsync<G, CV>(e);
-    return n == 0 ? 0 : (n <= ZS_DMG_CAP ? FL_DMG : (FL_DMG | FL_DMG_OVER));
+    return n == 0 ? 0 : FL_DMG;
+}
+
+// entry + 1 of a cell listed at or beyond entry SIDX_FAR - 1
+ZS_TPL __device__ __forceinline__ int spl_find_far(const ZsParams& p, const Env& e, int cell) {
+    ZS_VIEWS;
+    int i = SIDX_FAR - 1;
+    while ((int)(SPL(i) & 0xffffu) != cell) ++i;
+    return i + 1;
+}
+
+// One box/wall changed (single-lane contexts): refresh or create its entry.
+ZS_TPL __device__ __forceinline__ void spl_update_one(const ZsParams& p, const Env& e, int si, int cell, int life, bool present) {
+    ZS_VIEWS;
+    const int mx = __ldg(p.static_max + si);
+    const int pay = static_payload(p, mx, life, present);
+    int idx = SIDX(si);
+    if (idx == 0) {
+        if (pay == static_payload(p, mx, mx, true)) return;
+        idx = (int)SPN + 1;
+        SPN = (uint16_t)idx;
+        SIDX(si) = (uint8_t)(idx < SIDX_FAR ? idx : SIDX_FAR);
+    } else if (idx == SIDX_FAR) idx = spl_find_far<MPC, G, CV>(p, e, cell);
+    SPL(idx - 1) = (uint32_t)cell | ((uint32_t)pay << 16);
+}
+
+// A new world: every box/wall is back in World.things, also the ones with life <= 0 (game.py:154-155).
+ZS_TPL __device__ __forceinline__ void spl_refresh_present(const ZsParams& p, const Env& e) {
+    ZS_VIEWS;
+    const int n = SPN;
+#pragma unroll 1
+    for (int i = e.gl; i < n; i += G) {
+        const int cell = SPL(i) & 0xffffu;
+        const int si = __ldg(p.cell_static + cell);
+        SPL(i) = (uint32_t)cell | ((uint32_t)static_payload(p, __ldg(p.static_max + si), SL(si), true) << 16);
+    }
+}
+
+// First clean_dead_things of a world (core.py:121-138): every box/wall with life <= 0 leaves now.  Returns this
+// lane's count.
+ZS_TPL __device__ __forceinline__ int spl_clean_fresh(const ZsParams& p, const Env& e) {
+    ZS_VIEWS;
+    const int n = SPN;
+    int gone = 0;
+#pragma unroll 1
+    for (int i = e.gl; i < n; i += G) {
+        const int cell = SPL(i) & 0xffffu;
+        if (!g_is_static(GRID(cell))) continue;
+        if (SL(__ldg(p.cell_static + cell)) <= 0) { GRID(cell) = G_EMPTY; SPL(i) = (uint32_t)cell; ++gone; }
+    }
+    return gone;
 }
 
 // The cells that carry a dead body, as a short list (or, past ZS_DEAD_CAP, a flag for bitmap scans).
@@ -137,7 +193,7 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
     scalars_from_lane<G, CV>(e, e.gl < 8 ? p.SCAL[(size_t)e.env * 8 + e.gl] : 0);
     gsync<G, CV>(e);
     e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e));
-    e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e));
+    e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e), e.flags & FL_FRESH);
     if (ONE) e.flags |= scan_dead_bodies<MPC, G, false>(p, id_of(e));
     else e.flags |= FL_DEAD_OVER;
 }
@@ -174,17 +230,14 @@ ZS_TPL __device__ __noinline__ void build_grid(const ZsParams& p, GrpId id, int 
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
-    const bool fresh = flags & FL_FRESH;
     const uint4* tg = (const uint4*)p.tmpl_grid;
 #pragma unroll 1
     for (int i = e.gl; i < (p.cells_pad >> 4); i += G) reinterpret_cast<uint4*>(GRIDP)[i] = __ldg(tg + i);
     gsync<G, CV>(e);
-    if (flags & FL_DMG) {
+    if (flags & FL_DMG) {  // boxes/walls that are gone from World.things (payload 0 in the static patch list)
+        const int n = SPN;
 #pragma unroll 1
-        for (int i = e.gl; i < p.S; i += G) {
-            const int life = SL(i);
-            if (life != __ldg(p.static_max + i)) GRID(__ldg(p.static_cell + i)) = (life <= 0 && !fresh) ? G_EMPTY : G_STATIC_DMG;
-        }
+        for (int i = e.gl; i < n; i += G) { const uint32_t w = SPL(i); if ((w >> 16) == 0u) GRID(w & 0xffffu) = G_EMPTY; }
         gsync<G, CV>(e);
     }
 #pragma unroll 1
@@ -515,34 +568,28 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
             } else {
                 const int a = hi32 & 0xffffu;
                 const int amount = dlo + below(DRAWS(k++), dn);
-                if (kind == X_ATTACK_S) {
-                    SL(a) = (int16_t)(SL(a) - amount);
-                    LIST(n_touched++) = (uint16_t)a;
-                } else {
+                if (kind == X_ATTACK_S) SL(a) = (int16_t)(SL(a) - amount);
+                else {
                     const int mx = dlo == 1 ? 10 : 200;  // MAX_LIFE // 10 is 1 for a Box, 20 for a Wall
                     const int nl = SL(a) + amount;
                     SL(a) = (int16_t)(nl < mx ? nl : mx);
                 }
-                const int cell = __ldg(p.static_cell + a);
-                if (GRID(cell) == G_STATIC && !(fl & FL_DMG_OVER)) {  // first time this box/wall differs: remember it
-                    const int n = DMG(0);
-                    if (n < ZS_DMG_CAP) { DMG(1 + n) = (uint16_t)a; DMG(0) = (uint16_t)(n + 1); }
-                    else fl |= FL_DMG_OVER;
-                }
-                GRID(cell) = G_STATIC_DMG;
-                fl |= FL_DMG | FL_SL_DIRTY;
+                LIST(n_touched++) = (uint16_t)a;
+                fl |= FL_SL_DIRTY;
             }
         }
-        // clean_dead_things for boxes/walls hit this step (core.py:121-138); the scan below covers them on the
-        // first step of a world
-        if (!(fl & FL_FRESH)) {
+        // the boxes/walls hit this step: their patch-list entries, and clean_dead_things (core.py:121-138) for the
+        // ones destroyed now (on the first step of a world the clean phase below covers them)
 #pragma unroll 1
-            for (int i = 0; i < n_touched; ++i) {
-                const int si = LIST(i);
-                const int cell = __ldg(p.static_cell + si);
-                if (SL(si) <= 0 && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
-            }
+        for (int i = 0; i < n_touched; ++i) {
+            const int si = LIST(i);
+            const int cell = __ldg(p.static_cell + si);
+            const int life = SL(si);
+            const bool fresh = fl & FL_FRESH;
+            if (life <= 0 && !fresh && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
+            spl_update_one<MPC, G, CV>(p, e, si, cell, life, life > 0 || fresh);
         }
+        if (SPN) fl |= FL_DMG;
         e.flags = fl; e.deaths = deaths;
     }
     k = gbcast<G, CV>(e, k, 0);
@@ -553,20 +600,8 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
 
     // ---- clean_dead_things (core.py:121-138)
     int nd_all = 0, nd_z = 0;
-    const bool fresh_scan = (e.flags & FL_FRESH) && (e.flags & FL_DMG);
     if (e.flags & FL_FRESH) {  // first step of this world: every box/wall with life <= 0 leaves now
-        if (e.flags & FL_DMG) {
-            const bool over = e.flags & FL_DMG_OVER;
-            const int n_list = over ? p.S : (int)DMG(0);
-#pragma unroll 1
-            for (int i = e.gl; i < n_list; i += G) {
-                const int si = over ? i : (int)DMG(1 + i);
-                if (SL(si) <= 0) {
-                    const int cell = __ldg(p.static_cell + si);
-                    if (g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; ++nd_all; }
-                }
-            }
-        }
+        if (e.flags & FL_DMG) nd_all = spl_clean_fresh<MPC, G, CV>(p, e);
         e.flags &= ~FL_FRESH;
     }
     for (int w = e.gl; w < 2 * rw; w += G) MASKW(w) = 0u;
@@ -679,34 +714,28 @@ ZS_TPL __device__ __noinline__ void execute_sequential(const ZsParams& p, GrpId 
             } else {
                 const int a = hi32 & 0xffffu;
                 const int amount = dlo + below(DRAWS(k++), dn);
-                if (kind == X_ATTACK_S) {
-                    SL(a) = (int16_t)(SL(a) - amount);
-                    LIST(n_touched++) = (uint16_t)a;
-                } else {
+                if (kind == X_ATTACK_S) SL(a) = (int16_t)(SL(a) - amount);
+                else {
                     const int mx = __ldg(p.static_max + a);
                     const int nl = SL(a) + amount;
                     SL(a) = (int16_t)(nl < mx ? nl : mx);
                 }
-                const int cell = __ldg(p.static_cell + a);
-                if (GRID(cell) == G_STATIC && !(fl & FL_DMG_OVER)) {  // first time this box/wall differs: remember it
-                    const int n = DMG(0);
-                    if (n < ZS_DMG_CAP) { DMG(1 + n) = (uint16_t)a; DMG(0) = (uint16_t)(n + 1); }
-                    else fl |= FL_DMG_OVER;
-                }
-                GRID(cell) = G_STATIC_DMG;
-                fl |= FL_DMG | FL_SL_DIRTY;
+                LIST(n_touched++) = (uint16_t)a;
+                fl |= FL_SL_DIRTY;
             }
         }
-        // clean_dead_things for boxes/walls hit this step (core.py:121-138); on the first step of a world the
-        // scan in the clean phase covers them
-        if (!(fl & FL_FRESH)) {
+        // the boxes/walls hit this step: their patch-list entries, and clean_dead_things (core.py:121-138) for the
+        // ones destroyed now (on the first step of a world the clean phase below covers them)
 #pragma unroll 1
-            for (int i = 0; i < n_touched; ++i) {
-                const int si = LIST(i);
-                const int cell = __ldg(p.static_cell + si);
-                if (SL(si) <= 0 && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
-            }
+        for (int i = 0; i < n_touched; ++i) {
+            const int si = LIST(i);
+            const int cell = __ldg(p.static_cell + si);
+            const int life = SL(si);
+            const bool fresh = fl & FL_FRESH;
+            if (life <= 0 && !fresh && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
+            spl_update_one<MPC, G, CV>(p, e, si, cell, life, life > 0 || fresh);
         }
+        if (SPN) fl |= FL_DMG;
         SCALW(0) = k; SCALW(1) = fl; SCALW(2) = deaths; SCALW(3) = (int)succ;
     }
     gsync<G, CV>(e);
@@ -751,6 +780,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
         if (q == s) zb = m;
     }
 
+    PH(1);
     // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
     int type = D_IDLE, a = 0, b = 0;
     unsigned freemask = 0;
@@ -825,6 +855,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             }
         }
     }
+    PH(2);
     // wandering zombies and hamsters draw random.choice(positions) in dict order (things.py:101-103, hamster.py:12-14)
     int nd = 0;
     if (wany<G, CV>(e, type == D_WANDER)) {
@@ -871,6 +902,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     }
     const int L = __popc(gballot<G, CV>(e, acting));
     const int n_ah = __popc(gballot<G, CV>(e, is_hit));
+    PH(3);
     // ---- draws of this step, 4 per lane (counter-based: any k is available directly)
     const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
     if (s * 4 < n_need)
@@ -878,6 +910,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     gsync<G, CV>(e);
     // ---- random.shuffle (core.py:76): for i = L-1 .. 1: j = randbelow(i + 1); swap.  The swaps are a fixed sequence
     // once the partners are known: every lane follows its own action through them in registers.
+    PH(4);
     int jreg = 0;
     if (s >= 1 && s < L) jreg = below(DRAWS(nd + (L - 1 - s)), s + 1);
     int my_pos = acting ? pos : -1;
@@ -890,6 +923,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     if (in_cap) { MPOS(s) = (uint8_t)(((uint32_t)my_word & 7u) == X_MOVE ? my_pos : RK_NONE); MVP(s) = RK_NONE; }
     gsync<G, CV>(e);
 
+    PH(5);
     // ================= position space: execute_actions (core.py:103-119)
     int k = nd + (L > 1 ? L - 1 : 0);
     unsigned succ_m = 0;
@@ -916,6 +950,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             MVP(who) = (uint8_t)s;  // things[dest] = thing; del things[old]: goes last in the dict
         }
         gsync<G, CV>(e);
+        PH(6);
         // ---- hits (World.thing_attack / thing_heal, core.py:168-208)
         const bool on_static = kind >= X_ATTACK_S;
         bool inrange = on_static;  // boxes/walls do not move: their range was checked when the word was built
@@ -952,29 +987,31 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             }
             const bool slead = lead && on_static;
             if (wany<G, CV>(e, slead)) {
-                // a box/wall changed: occupancy code, damaged list, and clean_dead_things (core.py:121-138) for the
-                // ones destroyed now (on the first step of a world the scan in the clean phase covers them)
-                bool pristine = false, gone = false;
+                // a box/wall changed: clean_dead_things (core.py:121-138) for the ones destroyed now (on the first step of
+                // a world the clean phase covers them), and their entries in the static patch list
+                bool is_new = false, gone = false;
+                int cell = 0, pay = 0, idx = 0;
                 if (slead) {
-                    const int cell = __ldg(p.static_cell + si);
-                    const int gc = GRID(cell);
-                    pristine = gc == G_STATIC;
-                    gone = life <= 0 && !(e.flags & FL_FRESH) && g_is_static(gc);
-                    GRID(cell) = gone ? G_EMPTY : G_STATIC_DMG;
+                    const int mx = __ldg(p.static_max + si);
+                    const bool fresh = e.flags & FL_FRESH;
+                    cell = __ldg(p.static_cell + si);
+                    gone = life <= 0 && !fresh && g_is_static(GRID(cell));
+                    if (gone) GRID(cell) = G_EMPTY;
+                    pay = static_payload(p, mx, life, life > 0 || fresh);
+                    idx = SIDX(si);
+                    is_new = idx == 0 && pay != static_payload(p, mx, mx, true);
                 }
                 e.deaths += __popc(gballot<G, CV>(e, gone));
-                if (gany<G, CV>(e, slead)) e.flags |= FL_DMG | FL_SL_DIRTY;
-                unsigned new_m = gballot<G, CV>(e, pristine);
-                if (e.flags & FL_DMG_OVER) new_m = 0u;
-                if (wany<G, CV>(e, new_m != 0u)) {
-                    const int n0 = DMG(0);
-                    const int idx = n0 + __popc(new_m & below_s), tot = n0 + __popc(new_m);
-                    gsync<G, CV>(e);
-                    if (new_m) {
-                        if (pristine && idx < ZS_DMG_CAP) DMG(1 + idx) = (uint16_t)si;
-                        if (s == 0) DMG(0) = (uint16_t)(tot < ZS_DMG_CAP ? tot : ZS_DMG_CAP);
-                        if (tot > ZS_DMG_CAP) e.flags |= FL_DMG_OVER;
-                    }
+                if (gany<G, CV>(e, slead)) e.flags |= FL_SL_DIRTY;
+                const unsigned new_m = gballot<G, CV>(e, is_new);
+                const int n0 = SPN;
+                gsync<G, CV>(e);  // (everybody has read the count before lane 0 rewrites it)
+                if (is_new) { idx = n0 + __popc(new_m & below_s) + 1; SIDX(si) = (uint8_t)(idx < SIDX_FAR ? idx : SIDX_FAR); }
+                else if (idx == SIDX_FAR) idx = spl_find_far<MPC, G, CV>(p, e, cell);
+                if (slead && idx) SPL(idx - 1) = (uint32_t)cell | ((uint32_t)pay << 16);
+                if (new_m) {
+                    if (s == 0) SPN = (uint16_t)(n0 + __popc(new_m));
+                    e.flags |= FL_DMG;
                 }
             }
         }
@@ -987,22 +1024,12 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
         }
     }
 
+    PH(7);
     // ================= slot space: clean_dead_things (core.py:121-138)
     int nd_all = 0;
     const bool fresh_scan = (e.flags & FL_FRESH) && (e.flags & FL_DMG);
     if (e.flags & FL_FRESH) {  // first step of this world: every box/wall with life <= 0 leaves now
-        if (e.flags & FL_DMG) {
-            const bool over = e.flags & FL_DMG_OVER;
-            const int n_list = over ? p.S : (int)DMG(0);
-#pragma unroll 1
-            for (int i = e.gl; i < n_list; i += G) {
-                const int si = over ? i : (int)DMG(1 + i);
-                if (SL(si) <= 0) {
-                    const int cell = __ldg(p.static_cell + si);
-                    if (g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; ++nd_all; }
-                }
-            }
-        }
+        if (e.flags & FL_DMG) nd_all = spl_clean_fresh<MPC, G, CV>(p, e);
         e.flags &= ~FL_FRESH;
     }
     // deaths, dead bodies and the new dict order in one pass.  Survivors that did not move keep their relative
@@ -1046,6 +1073,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
         e.nlive = __popc(stay_m) + __popc(move_m);
     }
     gsync<G, CV>(e);
+    PH(8);
     return k;
 }
 
@@ -1151,7 +1179,7 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
     ZS_VIEWS;
     const int lane = e.gl;
     const int NP = p.P + p.A;
-    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY | FL_DMG_OVER)) | FL_FRESH | (ONE ? 0 : FL_DEAD_OVER);
+    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH | (ONE ? 0 : FL_DEAD_OVER);
     e.episode = episode;
 #pragma unroll 1
     for (int w = e.gl; w < p.dead_words; w += G) DEADW(w) = 0;
@@ -1189,6 +1217,7 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
                                                    : pick == 2 ? ZS_WEAPON_GUN : pick == 3 ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN);
         }
     }
+    if (flags & FL_DMG) spl_refresh_present<MPC, G, CV>(p, e);
     gsync<G, CV>(e);
     build_grid<MPC, G, false>(p, id, flags);  // every slot is out of the world here: statics (all present) only
 #pragma unroll 1
