@@ -171,37 +171,42 @@ ZS_TPL __device__ __forceinline__ void step_loop_general(const ZsParams& p, cons
 // ---------------------------------------------------------------- the K-step loop, one lane per slot
 // Agent a is handled by the lane of its slot (P + a): its action, its tracker life and its reward never leave
 // that lane's registers.  Output cursors advance by one step's stride instead of being recomputed.
-ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io, Env& e) {
+// FAST = the standard rollout shape, fixed at compile time: one agent, one reward per env, world-scope observation,
+// no minimum-zombie respawn, a discrete action tape in, observation / reward / terminated / truncated out and no
+// diagnostics outputs (zs_launch picks it when a launch has that shape).
+template <int MPC, int G, bool CV, bool FAST>
+__device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl, env = e.env;
-    const int A = p.A, P = p.P, NP = p.P + p.A;
+    const int A = FAST ? 1 : p.A, P = p.P, NP = P + A;
     const int aidx = lane - P;
     const bool is_agent = aidx >= 0 && aidx < A;
-    const bool per_agent = p.obs_per_agent != 0;
-    const bool lane_sum = !per_agent && A > 1;  // one reward from the sum of several agents' lives (reward.py:37-41)
-    const bool want_mask = per_agent || io.agent_mask != nullptr;
-    const bool world_obs = p.obs_scope == ZS_OBS_WORLD;
+    const bool per_agent = FAST ? false : p.obs_per_agent != 0;
+    const bool lane_sum = FAST ? false : (!per_agent && A > 1);  // one reward from the sum of several agents' lives (reward.py:37-41)
+    const bool want_mask = FAST ? false : (per_agent || io.agent_mask != nullptr);
+    const bool world_obs = FAST ? true : p.obs_scope == ZS_OBS_WORLD;
     const bool auto_reset = p.auto_reset || io.force_auto_reset;
-    // agent actions for the coming step, fetched one step ahead (Agent.set_action, agent.py:22-25)
-    int at = ZS_ACT_NONE, adx = 0, ady = 0;
-    auto fetch_action = [&](int step) {
-        at = ZS_ACT_NONE; adx = 0; ady = 0;
+    // The agent's action for the coming step is LOADED one step ahead and decoded when its step starts, so the load's
+    // latency hides under the previous transition (Agent.set_action, agent.py:22-25).
+    int raw0 = -1, raw1 = 0, raw2 = 0;
+    auto load_action = [&](int step) {
         if (!is_agent) return;
         const size_t ia = ((size_t)step * p.N + env) * A + aidx;
-        if (io.actions == nullptr) discrete_to_action(p, synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), aidx), at, adx, ady);
-        else if (io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, io.actions[ia], at, adx, ady);
-        else { const int32_t* q = io.actions + ia * 3; at = q[0]; adx = q[1]; ady = q[2]; }
+        if (FAST) { raw0 = io.actions[ia]; return; }
+        if (io.actions == nullptr) raw0 = synthetic_action(p, e.env_global, (uint32_t)(io.first_step + step), aidx);
+        else if (io.fmt == ZS_ACTIONS_DISCRETE) raw0 = io.actions[ia];
+        else { const int32_t* q = io.actions + ia * 3; raw0 = q[0]; raw1 = q[1]; raw2 = q[2]; }
     };
-    fetch_action(0);
+    load_action(0);
     const size_t obs_stride = (size_t)p.N * p.obs_elems;
-    int32_t* const obs_first = io.obs ? io.obs + (size_t)env * p.obs_elems : nullptr;
+    int32_t* const obs_first = (FAST || io.obs) ? io.obs + (size_t)env * p.obs_elems : nullptr;
     int32_t* obs_cur = obs_first;
     int oslot = 0;
     size_t sn = env;  // step * N + env
 #pragma unroll 1
     for (int step = 0; step < io.n_steps; ++step, sn += p.N) {
         int32_t* const obs_out = obs_cur;
-        if (obs_out) {
+        if (FAST || obs_out) {
             if (++oslot >= io.obs_slots) { oslot = 0; obs_cur = obs_first; } else obs_cur += obs_stride;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
             if (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
@@ -211,8 +216,12 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
         if (want_mask) alive_before = gballot<G, CV>(e, is_agent && TL(is_agent ? lane : 0) > 0) >> P;
         const int life_before = is_agent ? (int)PREVL(aidx) : 0;
         const int zd_before = e.prev_zd;
-        const int my_at = at, my_dx = adx, my_dy = ady;
-        if (step + 1 < io.n_steps) fetch_action(step + 1);
+        int my_at = ZS_ACT_NONE, my_dx = 0, my_dy = 0;
+        if (is_agent) {
+            if (FAST || io.actions == nullptr || io.fmt == ZS_ACTIONS_DISCRETE) discrete_to_action(p, raw0, my_at, my_dx, my_dy);
+            else { my_at = raw0; my_dx = raw1; my_dy = raw2; }
+        }
+        if (step + 1 < io.n_steps) load_action(step + 1);
         PH(0);
 
         int k = world_step_one<MPC, G, CV>(p, e, my_at, my_dx, my_dy);
@@ -232,7 +241,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
         e.prev_zd = e.zd;
 
         // ---- Game.spawn_zombies_to_maintain_minimum (game.py:196-201)
-        if (p.minimum_zombies > 0) {
+        if (!FAST && p.minimum_zombies > 0) {
             const int zc = __popc(gballot<G, CV>(e, lane >= NP && lane < p.M && (TM(lane < p.M ? lane : 0) & 0x80)));
             if (zc < p.minimum_zombies) {  // rare, and possibly only one env of the warp: the divergent flavour
                 k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive);
@@ -249,8 +258,8 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
         else if (!agents_alive) { trunc = true; end_reward = -10.0; }
         if (!per_agent) {
             if (done || trunc) rew = __dadd_rn(rew, end_reward);
-            if (io.reward && (lane_sum ? lane == 0 : aidx == 0)) io.reward[sn] = rew;
-            if (io.agent_mask && is_agent) io.agent_mask[sn * A + aidx] = (alive_before >> aidx) & 1u;
+            if ((FAST || io.reward) && (lane_sum ? lane == 0 : aidx == 0)) io.reward[sn] = rew;
+            if (!FAST && io.agent_mask && is_agent) io.agent_mask[sn * A + aidx] = (alive_before >> aidx) & 1u;
         } else if (is_agent) {
             if (!((alive_before >> aidx) & 1u)) rew = 0.0;
             else if (life_now > 0) rew = __dadd_rn(rew, end_reward);
@@ -259,9 +268,9 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
         }
         if (p.max_steps > 0 && e.ep_steps >= p.max_steps) trunc = true;  // gymnasium TimeLimit
         if (lane == 0) {
-            if (io.terminated) io.terminated[sn] = done;
-            if (io.truncated) io.truncated[sn] = trunc;
-            if (io.draws) io.draws[sn] = k;
+            if (FAST || io.terminated) io.terminated[sn] = done;
+            if (FAST || io.truncated) io.truncated[sn] = trunc;
+            if (!FAST && io.draws) io.draws[sn] = k;
         }
 
         PH(9);
@@ -277,7 +286,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
             scalars_from_smem<MPC, G, false>(p, e);
         }
         PH(10);
-        if (obs_out) {
+        if (FAST || obs_out) {
             if (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
             else encode_surroundings<MPC, G, CV>(p, e, obs_out);
         }
@@ -295,7 +304,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_one(const ZsParams& p, const Zs
 #endif
 }
 
-template <int MODE, int MPC, int G>
+template <int MODE, int MPC, int G, bool FAST>
 __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     ZS_CONSTS;
     // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const 
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
 #endif
-    if constexpr (ONE) step_loop_one<MPC, G, CV>(p, io, e);
+    if constexpr (ONE) step_loop_one<MPC, G, CV, FAST>(p, io, e);
     else step_loop_general<MPC, G, CV>(p, io, e);
     store_state<MPC, G, CV>(p, e);
 }
@@ -478,21 +487,34 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     ZsParams pp = h->p;
     if (MODE != MODE_STEP || io.n_steps < 4) pp.tmpl_smem_off = -1;
     const dim3 grid((pp.N + h->envs_per_cta - 1) / h->envs_per_cta), block(ZS_WPC * 32);
+    // the standard rollout shape gets the kernel with that shape compiled in (step_loop_one)
+    const bool fast = MODE == MODE_STEP && pp.mpc <= 32 && pp.A == 1 && !pp.obs_per_agent && pp.minimum_zombies == 0 &&
+                      pp.obs_scope == ZS_OBS_WORLD && io.actions && io.fmt == ZS_ACTIONS_DISCRETE && io.obs && io.reward &&
+                      io.terminated && io.truncated && !io.draws && !io.agent_mask;
     switch (pp.mpc) {
         case 16:
-            if (h->lanes_per_env == 16) zs_sim_kernel<MODE, 16, 16><<<grid, block, h->smem_bytes, st>>>(pp, io);
-            else zs_sim_kernel<MODE, 16, 32><<<grid, block, h->smem_bytes, st>>>(pp, io);
+            if (h->lanes_per_env == 16) {
+                if (fast) zs_sim_kernel<MODE, 16, 16, MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io);
+                else zs_sim_kernel<MODE, 16, 16, false><<<grid, block, h->smem_bytes, st>>>(pp, io);
+            } else {
+                if (fast) zs_sim_kernel<MODE, 16, 32, MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io);
+                else zs_sim_kernel<MODE, 16, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io);
+            }
             break;
-        case 32: zs_sim_kernel<MODE, 32, 32><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
-        case 128: zs_sim_kernel<MODE, 128, 32><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
-        default: zs_sim_kernel<MODE, 256, 32><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
+        case 32:
+            if (fast) zs_sim_kernel<MODE, 32, 32, MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io);
+            else zs_sim_kernel<MODE, 32, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io);
+            break;
+        case 128: zs_sim_kernel<MODE, 128, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
+        default: zs_sim_kernel<MODE, 256, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
     }
 }
 template <int MPC, int G>
 static cudaError_t set_smem_attr_for(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && MPC <= 32) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     return e;
 }
 static int set_smem_attr(int mpc, int lanes, int bytes) {
@@ -534,6 +556,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     memset(&p, 0, sizeof(p));
     p.N = cfg->num_envs; p.env_base = (uint32_t)cfg->env_index_base;
     p.key0 = (uint32_t)cfg->seed; p.key1 = (uint32_t)(cfg->seed >> 32);
+    for (int r = 0; r < 10; ++r) { p.rkey0[r] = p.key0 + (uint32_t)r * 0x9E3779B9u; p.rkey1[r] = p.key1 + (uint32_t)r * 0xBB67AE85u; }
     p.rules = cfg->rules; p.P = cfg->n_bots; p.A = cfg->n_agents;
     p.Z = cfg->initial_zombies > cfg->minimum_zombies ? cfg->initial_zombies : cfg->minimum_zombies;
     p.M = lay.n_slots; p.Mp = lay.slot_pitch; p.Ap = lay.agent_pitch; p.S = map->n_statics; p.Sp = lay.static_pitch;

@@ -45,6 +45,7 @@ struct ZsParams {
     int32_t N;
     uint32_t env_base;        // low 32 bits of the global index of env 0
     uint32_t key0, key1;      // Philox key = seed
+    uint32_t rkey0[10], rkey1[10];  // its round keys (key + r * Weyl constants), so the key schedule costs no instructions
     int32_t rules, P, A, Z, M, Mp, Ap, S, Sp, W, H, cells, cells_pad, dead_words;
     int32_t initial_zombies, minimum_zombies;
     int32_t obs_scope, obs_enc, sw, obs_count, obs_C;
@@ -107,6 +108,17 @@ __device__ __noinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c
         c0 = hi1 ^ c1 ^ k0; c1 = lo1;
         c2 = hi0 ^ c3 ^ k1; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// the env draw stream: key = seed, round keys straight from the kernel parameters
+__device__ __noinline__ uint4 philox_draws(const ZsParams& p, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ p.rkey0[r]; c1 = lo1;
+        c2 = hi0 ^ c3 ^ p.rkey1[r]; c3 = lo0;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -278,7 +290,7 @@ __device__ __forceinline__ int xy_y(uint32_t xy) { return (int)xy >> 16; }
 __device__ __forceinline__ uint32_t xy_pack(int x, int y) { return (uint32_t)(uint16_t)x | ((uint32_t)y << 16); }
 
 __device__ __forceinline__ uint32_t draw_at(const ZsParams& p, const Env& e, uint32_t t_word, int k) {
-    return word_of(philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)(k >> 2), p.key0, p.key1), k & 3);
+    return word_of(philox_draws(p, e.env_global, (uint32_t)e.episode, t_word, (uint32_t)(k >> 2)), k & 3);
 }
 __device__ __forceinline__ int below(uint32_t u, int n) { return (int)__umulhi(u, (uint32_t)n); }
 

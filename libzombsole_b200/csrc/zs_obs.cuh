@@ -91,35 +91,65 @@ __device__ __forceinline__ void obs_store_cell(const ZsParams& p, int32_t* obs, 
 // reference shows the thing on a cell, else its decoration (observation.py:41-42); the occupancy grid says which
 // one that is, so every patched cell is written by exactly one lane and the three kinds of patches (damaged or
 // destroyed boxes/walls, dead bodies, mobile things) need no ordering among themselves — only after pass 1.
+__device__ __forceinline__ void obs_store_static(const ZsParams& p, int32_t* obs, int cell, int pay) {
+    if (p.obs_enc == ZS_OBS_SIMPLE) obs[cell] = pay;
+    else { obs[cell] = pay >> 12; obs[p.cells + cell] = (int)((uint32_t)pay << 20) >> 20; obs[2 * p.cells + cell] = 0; }
+}
+__device__ __forceinline__ CellInfo thing_info(const ZsParams& p, int s, int life, int meta) {
+    CellInfo ci;
+    ci.life = life; ci.weapon = meta & 15; ci.agent = s - p.P;
+    ci.label = s < p.P ? ZS_LABEL_PLAYER : s < p.P + p.A ? ZS_LABEL_AGENT : ZS_LABEL_ZOMBIE;
+    return ci;
+}
+
 ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e, int32_t* obs) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl;
+    CellInfo body;
+    body.label = ZS_LABEL_DEAD_BODY; body.life = 0; body.weapon = 0; body.agent = -1;
+    // The first round of every kind of patch is read from shared memory BEFORE waiting for pass 1: the reads do
+    // not depend on it, and issued together their latencies overlap.
+    const int n_spl = (e.flags & FL_DMG) ? (int)SPN : 0;                 // boxes/walls whose observation differs
+    const int n_dead = (e.flags & FL_DEAD_OVER) ? 0 : (int)DBL(0);        // dead bodies of this world, from the list
+    const uint32_t w0 = lane < n_spl ? SPL(lane) : 0xffff0000u;
+    const int cell0 = w0 & 0xffffu, pay0 = w0 >> 16;
+    const int dc0 = lane < n_dead ? (int)DBL(1 + lane) : 0;
+    // gone from World.things (payload 0): whatever took the cell patches it itself; a thing on a dead body hides it
+    const bool do_static0 = lane < n_spl && (pay0 != 0 || GRID(cell0) == G_EMPTY);
+    const bool do_dead0 = lane < n_dead && GRID(dc0) == G_DEAD;
+    int tm0 = 0, tl0 = 0;
+    uint32_t txy0 = 0;
+    if (ONE && (G == MPC || lane < MPC)) { tm0 = TM(lane); tl0 = TL(lane); txy0 = TXY(lane); }
     if (p.tmpl_smem_off >= 0 && lane == 0) bulk_wait_all();  // pass 1 (TMA) has landed before any cell is patched
     gsync<G, CV>(e);
     PH(12);
-    if (e.flags & FL_DMG) {  // boxes/walls whose observation differs from the template: the static patch list
-        const int n_list = SPN;
-        const bool simple = p.obs_enc == ZS_OBS_SIMPLE;
+    if (do_static0) obs_store_static(p, obs, cell0, pay0);
+    if (do_dead0) obs_store_cell(p, obs, dc0, body);
+    if (ONE) {
+        if (tm0 & 0x80) obs_store_cell(p, obs, xy_y(txy0) * p.W + xy_x(txy0), thing_info(p, lane, tl0, tm0));
+    } else {
 #pragma unroll 1
-        for (int i = lane; i < n_list; i += G) {
-            const uint32_t w = SPL(i);
-            const int cell = w & 0xffffu, pay = w >> 16;
-            // gone from World.things: whatever took the cell patches it itself
-            if (pay == 0 && GRID(cell) != G_EMPTY) continue;
-            if (simple) obs[cell] = pay;
-            else { obs[cell] = pay >> 12; obs[p.cells + cell] = (int)((uint32_t)pay << 20) >> 20; obs[2 * p.cells + cell] = 0; }
+        for (int s = lane; s < p.M; s += G) {
+            const int m = TM(s);
+            if (!(m & 0x80)) continue;
+            const uint32_t xy = TXY(s);
+            obs_store_cell(p, obs, xy_y(xy) * p.W + xy_x(xy), thing_info(p, s, TL(s), m));
         }
     }
-    CellInfo body;
-    body.label = ZS_LABEL_DEAD_BODY; body.life = 0; body.weapon = 0; body.agent = -1;
-    if (!(e.flags & FL_DEAD_OVER)) {  // dead bodies of this world, from the list (a thing standing on one hides it)
-        const int n_list = DBL(0);
+    // further rounds (long lists are rare)
 #pragma unroll 1
-        for (int i = lane; i < n_list; i += G) {
-            const int c = DBL(1 + i);
-            if (GRID(c) == G_DEAD) obs_store_cell(p, obs, c, body);
-        }
-    } else {
+    for (int i = lane + G; i < n_spl; i += G) {
+        const uint32_t w = SPL(i);
+        const int cell = w & 0xffffu, pay = w >> 16;
+        if (pay == 0 && GRID(cell) != G_EMPTY) continue;
+        obs_store_static(p, obs, cell, pay);
+    }
+#pragma unroll 1
+    for (int i = lane + G; i < n_dead; i += G) {
+        const int c = DBL(1 + i);
+        if (GRID(c) == G_DEAD) obs_store_cell(p, obs, c, body);
+    }
+    if (e.flags & FL_DEAD_OVER) {  // the list is not complete: walk the dead-body bitmap
 #pragma unroll 1
         for (int w = lane; w < p.dead_words; w += G) {
             uint32_t bits = DEADW(w);
@@ -129,16 +159,6 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e
                 if (GRID(c) == G_DEAD) obs_store_cell(p, obs, c, body);
             }
         }
-    }
-#pragma unroll 1
-    for (int s = lane; s < p.M; s += G) {
-        const int m = TM(s);
-        if (!(m & 0x80)) continue;
-        CellInfo ci;
-        ci.life = TL(s); ci.weapon = m & 15; ci.agent = s - p.P;
-        ci.label = s < p.P ? ZS_LABEL_PLAYER : s < p.P + p.A ? ZS_LABEL_AGENT : ZS_LABEL_ZOMBIE;
-        const uint32_t xy = TXY(s);
-        obs_store_cell(p, obs, xy_y(xy) * p.W + xy_x(xy), ci);
     }
 }
 

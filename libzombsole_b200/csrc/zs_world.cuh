@@ -522,7 +522,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
 #pragma unroll 1
     for (int blk = lane; blk * 4 < n_need; blk += G)
-        reinterpret_cast<uint4*>(S.draws)[blk] = philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)blk, p.key0, p.key1);
+        reinterpret_cast<uint4*>(S.draws)[blk] = philox_draws(p, e.env_global, (uint32_t)e.episode, t_word, (uint32_t)blk);
     gsync<G, CV>(e);
     // Fisher-Yates partner of every iteration (random.shuffle: for i = L-1 .. 1: j = randbelow(i + 1))
 #pragma unroll 1
@@ -906,7 +906,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     // ---- draws of this step, 4 per lane (counter-based: any k is available directly)
     const int n_need = nd + (L > 1 ? L - 1 : 0) + n_ah;
     if (s * 4 < n_need)
-        reinterpret_cast<uint4*>(S.draws)[s] = philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)s, p.key0, p.key1);
+        reinterpret_cast<uint4*>(S.draws)[s] = philox_draws(p, e.env_global, (uint32_t)e.episode, t_word, (uint32_t)s);
     gsync<G, CV>(e);
     // ---- random.shuffle (core.py:76): for i = L-1 .. 1: j = randbelow(i + 1); swap.  The swaps are a fixed sequence
     // once the partners are known: every lane follows its own action through them in registers.
@@ -1303,7 +1303,17 @@ ZS_TPL __device__ __forceinline__ void rules_eval(const ZsParams& p, Env& e, boo
     }
 }
 
+// life / 100.0, correctly rounded like the reference's float division.  For the integers that occur (|life sum| is
+// a few thousand at most) one Newton correction of the product with RN(1/100) is exact — checked exhaustively for
+// |a| <= 200,000 against exact rational arithmetic (tests/test_reward_division.py); anything larger takes the division.
+__device__ __forceinline__ double div100(int a) {
+    const double x = __int2double_rn(a);
+    if (a > 200000 || a < -200000) return __ddiv_rn(x, 100.0);
+    const double r = 0.01;  // RN(1/100)
+    const double q0 = __dmul_rn(x, r);
+    return __fma_rn(__fma_rn(-100.0, q0, x), r, q0);
+}
 __device__ __forceinline__ double total_reward(int zombie_deaths, int life_sum) {
     // reward.py:37-41 / 90-92: int + float, the division first
-    return __dadd_rn(__int2double_rn(zombie_deaths), __ddiv_rn(__int2double_rn(life_sum), 100.0));
+    return __dadd_rn(__int2double_rn(zombie_deaths), div100(life_sum));
 }

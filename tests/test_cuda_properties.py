@@ -207,3 +207,27 @@ def test_vector_env_public_api():
     obs, reward, term, trunc, info = menv.step(torch.randint(-1, 7, (64, 4), device=menv.device))
     assert obs.shape == (64, 4, 3, 21, 21) and reward.shape == (64, 4) and info["agent_mask"].shape == (64, 4)
     menv.close()
+
+
+@pytest.mark.parametrize("name,N,K,lanes", [("c1_bridge_ext", 4096, 64, "16"), ("c1_bridge_ext", 4096, 64, "32"),
+                                            ("gym_v0_alone", 1024, 80, "16"), ("safehouse_small", 1000, 64, "32")])
+def test_standard_rollout_shape_matches_oracle(name, N, K, lanes, monkeypatch):
+    """The rollout shape with its own compiled-in kernel (one agent, world observation, discrete action tape in,
+    observation / reward / flags out, nothing else): every reward bit, flag and the final observation vs the oracle."""
+    from oracle import oracle as orc
+    monkeypatch.setenv("ZS_LANES_PER_ENV", lanes)
+    eng, cfg, m = engine(name, N, seed=21)
+    assert eng.lanes_per_env() == int(lanes)
+    obs = eng.new_obs(3)
+    rew, term, trunc = eng.new_outputs(K)
+    acts = torch.zeros((K, N, eng.A), dtype=torch.int32, device=eng.device)
+    for s in range(K):
+        eng.fill_synthetic_actions(s, acts[s])
+    eng.rollout(K, 0, acts, abi.ACTIONS_DISCRETE, obs, rew, term, trunc)
+    ref = orc.OracleEnv(cfg, m)
+    o, r, te, tr = ref.rollout_synthetic(K, 0)
+    assert np.array_equal(obs[(K - 1) % 3].cpu().numpy().reshape(N, -1), o)
+    assert np.array_equal(rew.cpu().numpy().view(np.uint64).reshape(K, N, 1), r.view(np.uint64))
+    assert np.array_equal(term.cpu().numpy(), te) and np.array_equal(trunc.cpu().numpy(), tr)
+    assert np.array_equal(eng.episode_stats().cpu().numpy(), ref.stats())
+    eng.close()
