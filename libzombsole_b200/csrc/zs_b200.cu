@@ -296,9 +296,9 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
 #ifdef ZS_PHASE_CLOCKS
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long tot = 0;
-        for (int i = 0; i < 13; ++i) tot += zs_ph[i];
+        for (int i = 0; i < 13; ++i) tot += zs_ph[i];  // (13.. are inside [10])
         printf("phase cycles/step over %d steps (total %.0f):", io.n_steps, (double)tot / io.n_steps);
-        for (int i = 0; i < 13; ++i) { printf(" [%d] %.0f", i, (double)zs_ph[i] / io.n_steps); zs_ph[i] = 0; }
+        for (int i = 0; i < 18; ++i) { printf(" [%d] %.0f", i, (double)zs_ph[i] / io.n_steps); zs_ph[i] = 0; }
         printf("\n");
     }
 #endif

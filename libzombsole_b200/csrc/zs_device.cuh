@@ -111,8 +111,9 @@ __device__ __noinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c
     }
     return make_uint4(c0, c1, c2, c3);
 }
-// the env draw stream: key = seed, round keys straight from the kernel parameters
-__device__ __noinline__ uint4 philox_draws(const ZsParams& p, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+// the env draw stream: key = seed, round keys straight from the kernel parameters (constant-bank operands: inline only —
+// behind a call the parameter struct is reached through a generic pointer and every key becomes a load)
+__device__ __forceinline__ uint4 philox_draws(const ZsParams& p, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -150,6 +151,7 @@ struct alignas(16) EnvS {
     uint8_t sor[MPC];                       // slot of a rank
     uint8_t mvq[MPC];                       // order of this step's successful moves, RK_NONE if none
     uint8_t dtype[MPC];
+    alignas(16) uint8_t fyj[MPC];           // per step: Fisher-Yates partner of every list position (one-lane-per-slot kernels)
 };
 
 // The env a lane group is working on (warp-uniform within the group).
@@ -290,7 +292,7 @@ __device__ __forceinline__ int xy_y(uint32_t xy) { return (int)xy >> 16; }
 __device__ __forceinline__ uint32_t xy_pack(int x, int y) { return (uint32_t)(uint16_t)x | ((uint32_t)y << 16); }
 
 __device__ __forceinline__ uint32_t draw_at(const ZsParams& p, const Env& e, uint32_t t_word, int k) {
-    return word_of(philox_draws(p, e.env_global, (uint32_t)e.episode, t_word, (uint32_t)(k >> 2)), k & 3);
+    return word_of(philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)(k >> 2), p.key0, p.key1), k & 3);
 }
 __device__ __forceinline__ int below(uint32_t u, int n) { return (int)__umulhi(u, (uint32_t)n); }
 

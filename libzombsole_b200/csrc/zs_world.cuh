@@ -36,7 +36,9 @@ __device__ __forceinline__ int scalar_of_lane(const Env& e) {
 ZS_TPL __device__ __forceinline__ void scalars_from_smem(const ZsParams& p, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
     gsync<G, CV>(e);
-    scalars_from_lane<G, CV>(e, e.gl < 8 ? SCALW(e.gl) : 0);
+    e.t = SCALW(ZS_S_T); e.episode = SCALW(ZS_S_EPISODE); e.deaths = SCALW(ZS_S_DEATHS); e.zd = SCALW(ZS_S_ZOMBIE_DEATHS);
+    e.nlive = SCALW(ZS_S_STAMP_COUNTER); e.flags = SCALW(ZS_S_FLAGS); e.prev_zd = SCALW(ZS_S_PREV_ZOMBIE_DEATHS);
+    e.ep_steps = SCALW(ZS_S_EPISODE_STEPS);
 }
 
 // Dict-order ranks from arbitrary order-preserving stamps (state import / start of a launch): the rank of
@@ -911,13 +913,23 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     // ---- random.shuffle (core.py:76): for i = L-1 .. 1: j = randbelow(i + 1); swap.  The swaps are a fixed sequence
     // once the partners are known: every lane follows its own action through them in registers.
     PH(4);
-    int jreg = 0;
-    if (s >= 1 && s < L) jreg = below(DRAWS(nd + (L - 1 - s)), s + 1);
+    // The partners go through shared memory as bytes and come back as broadcast 128-bit loads, so the swap loop is
+    // pure register arithmetic with compile-time indices (iterations at or beyond L change nothing).
+    if (in_cap) S.fyj[s] = (uint8_t)((s >= 1 && s < L) ? below(DRAWS(nd + (L - 1 - s)), s + 1) : s);
+    gsync<G, CV>(e);
     int my_pos = acting ? pos : -1;
-#pragma unroll 1
-    for (int i = wmax<G, CV>(e, L) - 1; i >= 1; --i) {  // (the other env of the warp may have the longer list)
-        const int j = gbcast<G, CV>(e, jreg, i);
-        if (i < L) my_pos = my_pos == i ? j : (my_pos == j ? i : my_pos);
+    {
+        uint32_t jw[MPC / 4];
+#pragma unroll
+        for (int q = 0; q < MPC / 16; ++q) {
+            const uint4 v = reinterpret_cast<const uint4*>(S.fyj)[q];
+            jw[4 * q] = v.x; jw[4 * q + 1] = v.y; jw[4 * q + 2] = v.z; jw[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = MPC - 1; i >= 1; --i) {
+            const int j = (int)((jw[i >> 2] >> (8 * (i & 3))) & 0xffu);  // j == i beyond the list: both branches keep my_pos
+            my_pos = my_pos == i ? j : (my_pos == j ? i : my_pos);
+        }
     }
     if (my_pos >= 0) ACT(my_pos) = my_word;
     if (in_cap) { MPOS(s) = (uint8_t)(((uint32_t)my_word & 7u) == X_MOVE ? my_pos : RK_NONE); MVP(s) = RK_NONE; }
@@ -941,7 +953,8 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
         if (seq) kind = X_NOP;
         // ---- moves (World.thing_move, core.py:140-166)
         const bool dest_free = kind == X_MOVE && !g_is_thing(g0);
-        const unsigned want = gmatch<G, CV>(e, dest_free ? (uint32_t)c : 0x10000u + (uint32_t)s);
+        // (match.any takes time per DISTINCT value: everybody who does not take part shares one dummy)
+        const unsigned want = gmatch<G, CV>(e, dest_free ? (uint32_t)c : 0x10000u);
         const bool success = dest_free && !(want & below_s);
         succ_m = gballot<G, CV>(e, success);
         if (success) {
@@ -969,7 +982,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             }
             k += __popc(hit_m);
             const uint32_t tid = on_static ? 0x100u + (uint32_t)si : (uint32_t)who;
-            const unsigned grp = gmatch<G, CV>(e, inrange ? tid : 0x20000u + (uint32_t)s);
+            const unsigned grp = gmatch<G, CV>(e, inrange ? tid : 0x20000u);
             const bool lead = inrange && !(grp & below_s);  // the first hit on a target applies all of them, in order
             gsync<G, CV>(e);
             int life = 0;
@@ -1117,21 +1130,29 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
     }
     gsync<G, CV>(e);
     if (lane == 0) {
+        // the swaps are the only sequential part: iteration `it` takes the candidate at its partner's position and
+        // leaves its own there (positions >= i are never read again); the chosen cell replaces the draw
 #pragma unroll 1
         for (int it = 0; it < placed; ++it) {
             const int i = n - 1 - it;
-            if (i >= 1) { const int j = (int)DRAWS(it); const uint16_t tmp = CAND(i); CAND(i) = CAND(j); CAND(j) = tmp; }
-            const int c = CAND(i);
-            const int s = LIST(it);
-            const int y = c / p.W;
-            TXY(s) = xy_pack(c - y * p.W, y);
-            TM(s) |= 0x80;
-            RK(s) = (uint8_t)(rank0 + it);
-            SOR(rank0 + it) = (uint8_t)s;
-            MVQ(s) = RK_NONE;
-            GRID(c) = (uint8_t)(s + 1);
+            int c = CAND(i);
+            if (i >= 1) { const int j = (int)DRAWS(it); const int cj = CAND(j); CAND(j) = (uint16_t)c; c = cj; }
+            DRAWS(it) = (uint32_t)c;
         }
         SCALW(ZS_S_STAMP_COUNTER) = rank0 + placed;
+    }
+    gsync<G, CV>(e);
+#pragma unroll 1
+    for (int it = e.gl; it < placed; it += G) {  // spawns.pop() for the it-th thing: place it, append it to the dict order
+        const int c = (int)DRAWS(it);
+        const int s = LIST(it);
+        const int y = c / p.W;
+        TXY(s) = xy_pack(c - y * p.W, y);
+        TM(s) |= 0x80;
+        RK(s) = (uint8_t)(rank0 + it);
+        SOR(rank0 + it) = (uint8_t)s;
+        MVQ(s) = RK_NONE;
+        GRID(c) = (uint8_t)(s + 1);
     }
     gsync<G, CV>(e);
     return k + (n > 1 ? n - 1 : 0);
@@ -1181,6 +1202,9 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
     const int NP = p.P + p.A;
     const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH | (ONE ? 0 : FL_DEAD_OVER);
     e.episode = episode;
+#ifdef ZS_PHASE_CLOCKS
+    e.ph_last = clock64();
+#endif
 #pragma unroll 1
     for (int w = e.gl; w < p.dead_words; w += G) DEADW(w) = 0;
     if (lane == 0) DBL(0) = 0;  // a new world has no dead bodies
@@ -1217,19 +1241,24 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
                                                    : pick == 2 ? ZS_WEAPON_GUN : pick == 3 ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN);
         }
     }
+    PH(13);
     if (flags & FL_DMG) spl_refresh_present<MPC, G, CV>(p, e);
     gsync<G, CV>(e);
     build_grid<MPC, G, false>(p, id, flags);  // every slot is out of the world here: statics (all present) only
+    PH(14);
 #pragma unroll 1
     for (int s = e.gl; s < p.P; s += G) LIST(s) = (uint16_t)s;
     if (lane == 0) SCALW(ZS_S_STAMP_COUNTER) = 0;
     gsync<G, CV>(e);
     k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.P, 0, 0);
+    PH(15);
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) LIST(a) = (uint16_t)(p.P + a);
     gsync<G, CV>(e);
     k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.A, 0, SCALW(ZS_S_STAMP_COUNTER));
+    PH(16);
     k = spawn_zombies<MPC, G, false>(p, id, episode, 0u, k, p.initial_zombies, SCALW(ZS_S_STAMP_COUNTER));
+    PH(17);
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) PREVL(a) = TL(p.P + a);
     if (lane == 0) {
