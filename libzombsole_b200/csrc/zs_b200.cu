@@ -305,7 +305,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
 }
 
 template <int MODE, int MPC, int G, bool FAST>
-__global__ void __launch_bounds__(ZS_WPC * 32, ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
+__global__ void __launch_bounds__(ZS_WPC * 32, G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     ZS_CONSTS;
     // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
     constexpr bool CV = MODE == MODE_STEP;

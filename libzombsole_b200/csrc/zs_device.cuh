@@ -22,6 +22,9 @@
 
 #define ZS_WPC 4              // warps per CTA
 #define ZS_MIN_CTAS 7         // 7 CTAs x 4 warps resident per SM: 4,096 full-warp envs fit the 148 SMs in one wave
+#ifndef ZS_MIN_CTAS_G16
+#define ZS_MIN_CTAS_G16 6     // two envs per warp: 6 CTAs (80 registers) measured slightly ahead of 7 (72) and of 5 (96)
+#endif
 
 // occupancy-grid byte codes (a box/wall is on the grid while it is in World.things, whatever its life)
 #define G_EMPTY 0

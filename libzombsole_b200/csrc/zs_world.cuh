@@ -763,6 +763,14 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     const int bkind = s < p.P ? (int)p.bot_kinds[s] : -1;
     if (!(live && agent)) at = ZS_ACT_NONE;
     else if (at == ZS_ACT_ABSENT) { at = ZS_ACT_HEAL; adx = 0; ady = 0; }  // multiagent_env.py:129-131
+    // what is on the four adjacent cells (utils.py:34-44) does not depend on the target: read it now, so the loads
+    // are back by the time the closest things are known.  No bounds check: cells outside the map hold nothing
+    // (utils.py:47-52)
+    unsigned gs[4];
+    unsigned freemask = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) gs[d] = (live && !agent) ? (unsigned)grid_at(p, GRIDP, x + adj_dx(d), y + adj_dy(d)) : (unsigned)G_STATIC;
+    const int my_tm = in_cap ? (int)TM(s) : 0;
     const bool has_humans = gany<G, CV>(e, live && !zombie);
 
     // ---- closest(self, others) (utils.py:23-31) for everybody from ONE pass over the (thing, player) distances:
@@ -785,7 +793,6 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     PH(1);
     // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
     int type = D_IDLE, a = 0, b = 0;
-    unsigned freemask = 0;
     if (live) {
         const uint32_t key = (zombie || at == ZS_ACT_HEAL_CLOSEST) ? bestp : zb;
         const int tg = key == 0xffffffffu ? -1 : (int)SOR(key & 255u);
@@ -793,12 +800,10 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
         const uint32_t gxy = tg >= 0 ? TXY(tg) : 0u;
         const int gx = xy_x(gxy), gy = xy_y(gxy);
         if (!agent) {
-            // the four adjacent cells (utils.py:34-44): what is on them and how far they are from the target
-            unsigned gs[4];
+            // the four adjacent cells: how far they are from the target
             int dd[4];
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {  // no bounds check: cells outside the map hold nothing (utils.py:47-52)
-                gs[d] = grid_at(p, GRIDP, x + adj_dx(d), y + adj_dy(d));
+            for (int d = 0; d < 4; ++d) {
                 dd[d] = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
                 if (!g_is_thing(gs[d])) freemask |= 1u << d;
             }
@@ -823,7 +828,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
                 }
             } else if (bkind == ZS_KIND_TERMINATOR) {  // Terminator.next_step (players/terminator.py:9-37)
                 if (tg < 0) { type = D_HEAL; a = s; }
-                else if (d2 > c_range2[TM(s) & 15]) {
+                else if (d2 > c_range2[my_tm & 15]) {
                     int bdir = 0, bdist = 0x7fffffff, g = 0;
 #pragma unroll
                     for (int d = 0; d < 4; ++d)  // closest(target, adjacent_positions(self)): out-of-bounds cells included
@@ -890,7 +895,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
         } else {
             const bool is_static = a >= p.M;
             int mx = 100, r2, dlo, dn;
-            if (type == D_ATTACK) { const int w = TM(s) & 15; r2 = c_range2[w]; dlo = c_dmg_lo[w]; dn = c_dmg_n[w]; }
+            if (type == D_ATTACK) { const int w = my_tm & 15; r2 = c_range2[w]; dlo = c_dmg_lo[w]; dn = c_dmg_n[w]; }
             else {  // heal: randint(MAX_LIFE // 10, MAX_LIFE // 4) of the target's class, range 3 (core.py:194-198)
                 if (is_static) mx = __ldg(p.static_max + (a - p.M));
                 r2 = 9; dlo = mx / 10; dn = mx / 4 - mx / 10 + 1;
