@@ -114,7 +114,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_general(const ZsParams& p, cons
 #pragma unroll 1
             for (int s0 = NP; s0 < p.M; s0 += G) zc += __popc(gballot<G, CV>(e, s0 + lane < p.M && (TM(s0 + lane) & 0x80)));
             if (zc < p.minimum_zombies) {
-                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive);
+                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive, false);
                 e.nlive = SCALW(ZS_S_STAMP_COUNTER);
             }
         }
@@ -211,6 +211,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
             // pass 1 of the world observation does not depend on the transition: issue its stores now
             if (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
         }
+        PH(18);
         // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
         unsigned alive_before = 0;
         if (want_mask) alive_before = gballot<G, CV>(e, is_agent && TL(is_agent ? lane : 0) > 0) >> P;
@@ -222,6 +223,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
             else { my_at = raw0; my_dx = raw1; my_dy = raw2; }
         }
         if (step + 1 < io.n_steps) load_action(step + 1);
+        PH(19);
         PH(0);
 
         int k = world_step_one<MPC, G, CV>(p, e, my_at, my_dx, my_dy);
@@ -244,7 +246,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         if (!FAST && p.minimum_zombies > 0) {
             const int zc = __popc(gballot<G, CV>(e, lane >= NP && lane < p.M && (TM(lane < p.M ? lane : 0) & 0x80)));
             if (zc < p.minimum_zombies) {  // rare, and possibly only one env of the warp: the divergent flavour
-                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive);
+                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive, false);
                 e.nlive = SCALW(ZS_S_STAMP_COUNTER);
             }
         }
@@ -298,7 +300,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         unsigned long long tot = 0;
         for (int i = 0; i < 13; ++i) tot += zs_ph[i];  // (13.. are inside [10])
         printf("phase cycles/step over %d steps (total %.0f):", io.n_steps, (double)tot / io.n_steps);
-        for (int i = 0; i < 18; ++i) { printf(" [%d] %.0f", i, (double)zs_ph[i] / io.n_steps); zs_ph[i] = 0; }
+        for (int i = 0; i < 20; ++i) { printf(" [%d] %.0f", i, (double)zs_ph[i] / io.n_steps); zs_ph[i] = 0; }
         printf("\n");
     }
 #endif
@@ -327,6 +329,11 @@ __global__ void __launch_bounds__(ZS_WPC * 32, G == 16 ? ZS_MIN_CTAS_G16 : ZS_MI
         __syncthreads();
     }
     if (env >= p.N) return;
+    e.tmpl_saddr = 0;
+    if (p.tmpl_smem_off >= 0) {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(zs_smem + p.tmpl_smem_off);
+        asm volatile("mov.u32 %0, %1;" : "=r"(e.tmpl_saddr) : "r"(a));
+    }
     e.b = (uint32_t)slot * (uint32_t)p.smem_per_env;
     e.env = env; e.env_global = p.env_base + (uint32_t)env;
     const int lane = e.gl;

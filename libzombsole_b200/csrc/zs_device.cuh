@@ -165,6 +165,7 @@ struct Env {
     int32_t gl;       // lane within the group
     uint32_t gm;      // member mask of the group
     int32_t gshift;   // first lane of the group within the warp
+    uint32_t tmpl_saddr;  // shared-space address of the CTA's observation template (TMA source), computed once per launch
 #ifdef ZS_PHASE_CLOCKS
     long long ph_last;
 #endif
@@ -216,6 +217,10 @@ struct Env {
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+// the same with the shared-space address already at hand (kept opaque so it is not recomputed at every use)
+__device__ __forceinline__ void bulk_store_s(void* gdst, uint32_t saddr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

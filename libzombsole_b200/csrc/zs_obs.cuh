@@ -43,7 +43,7 @@ __device__ __forceinline__ int channel_label(const ZsParams& p, const CellInfo& 
 // row is not 16-byte aligned (cell count not a multiple of 4) or the template does not fit, it is streamed
 // from the L1-resident template with 128-bit loads/stores instead.  Either way it is issued BEFORE the
 // world transition and drains underneath the latency-bound game logic.
-ZS_TPL __device__ __forceinline__ void obs_world_template(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
+ZS_TPL __device__ __forceinline__ void obs_world_template(const ZsParams& p, Env& e, int32_t* __restrict__ obs) {
     ZS_CONSTS;
     const int lane = e.gl;
     const int cells = p.cells;
@@ -52,9 +52,9 @@ ZS_TPL __device__ __forceinline__ void obs_world_template(const ZsParams& p, con
         // TMA: the group's lane 0 issues one bulk copy per plane from the CTA-shared template to the env's row —
         // no per-lane loads/stores at all.  obs_world_patch waits for the group before it patches cells.
         if (lane == 0) {
-            const unsigned char* t = zs_smem + p.tmpl_smem_off;
             const uint32_t plane = (uint32_t)cells * 4u;
-            for (int c = 0; c < p.tmpl_planes; ++c) bulk_store(obs + (size_t)c * cells, t + (size_t)c * plane, plane);
+            bulk_store_s(obs, e.tmpl_saddr, plane);
+            for (int c = 1; c < p.tmpl_planes; ++c) bulk_store_s(obs + (size_t)c * cells, e.tmpl_saddr + (uint32_t)c * plane, plane);
             bulk_commit();
         }
         return;

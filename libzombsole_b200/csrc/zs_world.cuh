@@ -16,6 +16,7 @@ __device__ __forceinline__ Env env_of(const ZsParams& p, const GrpId& id) {
     Env e;
     e.b = id.b; e.env = id.env; e.env_global = p.env_base + (uint32_t)id.env; e.gl = id.gl; e.gm = id.gm; e.gshift = id.gshift;
     e.t = e.episode = e.deaths = e.zd = e.nlive = e.flags = e.prev_zd = e.ep_steps = 0;
+    e.tmpl_saddr = 0;
     return e;
 }
 __device__ __forceinline__ GrpId id_of(const Env& e) { GrpId id; id.b = e.b; id.env = e.env; id.gl = e.gl; id.gm = e.gm; id.gshift = e.gshift; return id; }
@@ -233,7 +234,7 @@ ZS_TPL __device__ __noinline__ void build_grid(const ZsParams& p, GrpId id, int 
     Env e = env_of(p, id);
     ZS_VIEWS;
     const uint4* tg = (const uint4*)p.tmpl_grid;
-#pragma unroll 1
+#pragma unroll 4
     for (int i = e.gl; i < (p.cells_pad >> 4); i += G) reinterpret_cast<uint4*>(GRIDP)[i] = __ldg(tg + i);
     gsync<G, CV>(e);
     if (flags & FL_DMG) {  // boxes/walls that are gone from World.things (payload 0 in the static patch list)
@@ -780,15 +781,19 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     const bool wantp = live && (zombie || at == ZS_ACT_HEAL_CLOSEST);
     const uint32_t zkey = (live && zombie) ? rk : 0xffffffffu;
     uint32_t bestp = 0xffffffffu, zb = 0xffffffffu;
-#pragma unroll 1
-    for (int q = 0; q < NP; ++q) {
+    auto one_player = [&](int q) {
         const uint32_t rq = RK(q), qxy = TXY(q);
         const bool hq = rq != RK_NONE;  // player q is in the world
         const uint32_t d = (uint32_t)dist2(x, y, xy_x(qxy), xy_y(qxy)) << 8;
         if (hq && wantp && q != s) bestp = min(bestp, d | rq);
         const uint32_t m = gminu<G, CV>(e, hq ? (d | zkey) : 0xffffffffu);
         if (q == s) zb = m;
-    }
+    };
+    // (the first four players unrolled: their loads and reductions are independent and overlap)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (q < NP) one_player(q);
+#pragma unroll 1
+    for (int q = 4; q < NP; ++q) one_player(q);
 
     PH(1);
     // ---- get_actions (core.py:80-101): every actor decides against the pre-step world
@@ -1100,9 +1105,11 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
 // zombie (which = 1) spawn cells, or of the whole map, x-major, when the map has no such spawn cells.  Only
 // the first `count` Fisher-Yates iterations decide placements (spawns.pop() takes from the end); the rest of
 // the shuffle only advances the draw counter.  New things are appended to the dict order (rank0 + i).
+// all_free: the caller knows that nothing stands on any cell of the spawn list (a new world: spawn cells never
+// carry boxes/walls, and player and zombie spawn cells are different cells), so the list is taken as it is.
 // Returns the new draw index; the new number of things in the world is left in SCALW(ZS_S_STAMP_COUNTER).
 ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, int episode,
-                                                   uint32_t t_word, int k, int count, int which, int rank0) {
+                                                   uint32_t t_word, int k, int count, int which, int rank0, bool all_free) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
@@ -1112,19 +1119,25 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
     const int n_spawn = which ? p.n_zs : p.n_ps;
     const int n_src = n_spawn > 0 ? n_spawn : p.cells;
     int n = 0;
+    if (all_free && n_spawn > 0) {
+#pragma unroll 4
+        for (int i = lane; i < n_spawn; i += G) CAND(i) = __ldg(spawn + i);
+        n = n_spawn;
+    } else {
 #pragma unroll 1
-    for (int b0 = 0; b0 < n_src; b0 += G) {
-        const int i = b0 + lane;
-        bool ok = false;
-        int c = 0;
-        if (i < n_src) {
-            if (n_spawn > 0) c = __ldg(spawn + i);
-            else { const int x = i / p.H; const int y = i - x * p.H; c = y * p.W + x; }
-            ok = !g_is_thing(GRID(c));
+        for (int b0 = 0; b0 < n_src; b0 += G) {
+            const int i = b0 + lane;
+            bool ok = false;
+            int c = 0;
+            if (i < n_src) {
+                if (n_spawn > 0) c = __ldg(spawn + i);
+                else { const int x = i / p.H; const int y = i - x * p.H; c = y * p.W + x; }
+                ok = !g_is_thing(GRID(c));
+            }
+            const unsigned m = gballot<G, CV>(e, ok);
+            if (ok) CAND(n + __popc(m & ((1u << e.gl) - 1u))) = (uint16_t)c;
+            n += __popc(m);
         }
-        const unsigned m = gballot<G, CV>(e, ok);
-        if (ok) CAND(n + __popc(m & ((1u << e.gl) - 1u))) = (uint16_t)c;
-        n += __popc(m);
     }
     gsync<G, CV>(e);
     const int placed = count < n ? count : n;
@@ -1166,7 +1179,7 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
 // Game.spawn_zombies (game.py:189-194): `count` Zombie() constructions (life draws, things.py:62)
 // followed by spawn_in_random on the zombie spawn cells; free zombie slots are taken in ascending order.
 ZS_TPL __device__ __noinline__ int spawn_zombies(const ZsParams& p, GrpId id, int episode,
-                                                 uint32_t t_word, int k, int count, int rank0) {
+                                                 uint32_t t_word, int k, int count, int rank0, bool all_free) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
@@ -1192,7 +1205,7 @@ ZS_TPL __device__ __noinline__ int spawn_zombies(const ZsParams& p, GrpId id, in
         TM(s) = ZS_WEAPON_CLAWS;
     }
     gsync<G, CV>(e);
-    return spawn_in_random<MPC, G, false>(p, id, episode, t_word, k + count, made, 1, rank0);
+    return spawn_in_random<MPC, G, false>(p, id, episode, t_word, k + count, made, 1, rank0, all_free);
 }
 
 // Game.__initialize_world__ (game.py:151-169) + reward_tracker.reset (reward.py:26-28).  Out of line and
@@ -1255,14 +1268,14 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
     for (int s = e.gl; s < p.P; s += G) LIST(s) = (uint16_t)s;
     if (lane == 0) SCALW(ZS_S_STAMP_COUNTER) = 0;
     gsync<G, CV>(e);
-    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.P, 0, 0);
+    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.P, 0, 0, true);
     PH(15);
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) LIST(a) = (uint16_t)(p.P + a);
     gsync<G, CV>(e);
-    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.A, 0, SCALW(ZS_S_STAMP_COUNTER));
+    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.A, 0, SCALW(ZS_S_STAMP_COUNTER), p.P == 0);
     PH(16);
-    k = spawn_zombies<MPC, G, false>(p, id, episode, 0u, k, p.initial_zombies, SCALW(ZS_S_STAMP_COUNTER));
+    k = spawn_zombies<MPC, G, false>(p, id, episode, 0u, k, p.initial_zombies, SCALW(ZS_S_STAMP_COUNTER), true);
     PH(17);
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) PREVL(a) = TL(p.P + a);

@@ -10,11 +10,15 @@ name, N, K = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 cfg, m = pu.build(pu.CONFIGS[name], N, 0, auto_reset=True, max_episode_steps=1000)
 eng = ZsEngine(cfg, m)
 obs = eng.new_obs(4)
-eng.rollout(K, 0, None, abi.ACTIONS_DISCRETE, obs, None, None, None)   # warm-up launch
+rew, term, trunc = eng.new_outputs(K)
+acts = torch.zeros((2 * K, N, eng.A), dtype=torch.int32, device=eng.device)
+for s in range(2 * K):
+    eng.fill_synthetic_actions(s, acts[s])
+eng.rollout(K, 0, acts[:K], abi.ACTIONS_DISCRETE, obs, rew, term, trunc)   # warm-up launch
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 torch.cuda.synchronize()
 ev[0].record()
-eng.rollout(K, K, None, abi.ACTIONS_DISCRETE, obs, None, None, None)   # the profiled launch
+eng.rollout(K, K, acts[K:], abi.ACTIONS_DISCRETE, obs, rew, term, trunc)   # the profiled launch
 ev[1].record()
 torch.cuda.synchronize()
 print("%s N=%d K=%d: %.3e env-steps/s" % (name, N, K, N * K / ev[0].elapsed_time(ev[1]) * 1e3))
