@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(ZS_WPC * 32, G == 16 ? ZS_MIN_CTAS_G16 : ZS_MI
     if (MODE == MODE_RESET) {
         if (io.env_mask && !io.env_mask[env]) return;
         // slots keep their last position/life until re-placed; bring them in so the store is complete
-        load_state<MPC, G, CV>(p, e);
+        load_state<MPC, G, CV>(p, e, false);
+        e.flags |= FL_DEAD_LAUNCH;
         const int k = initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
         scalars_from_smem<MPC, G, CV>(p, e);
         if (io.draws && lane == 0) io.draws[env] = k;
@@ -350,7 +351,8 @@ __global__ void __launch_bounds__(ZS_WPC * 32, G == 16 ? ZS_MIN_CTAS_G16 : ZS_MI
         store_state<MPC, G, CV>(p, e);
         return;
     }
-    load_state<MPC, G, CV>(p, e);
+    load_state<MPC, G, CV>(p, e, MODE == MODE_STEP && io.n_steps >= 4);
+    if (!(MODE == MODE_STEP && io.n_steps >= 4)) e.flags |= FL_DEAD_LAUNCH;
     build_grid<MPC, G, false>(p, id_of(e), e.flags);
     if (MODE == MODE_ENCODE) {
         encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);

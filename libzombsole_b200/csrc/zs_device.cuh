@@ -175,6 +175,7 @@ struct Env {
 #define FL_DMG 2         // the static patch list is not empty
 #define FL_SL_DIRTY 4    // static lives changed during this launch: write them back
 #define FL_DEAD_OVER 16  // the dead-body list is not complete (overflow, or a kernel that does not keep it): scan the bitmap
+#define FL_DEAD_LAUNCH 32  // ... for the whole launch (single-step launches do not build the list), also across world inits
 
 // Bind the shared-memory views of `e` in the current scope (S: the struct; GRIDP/DEADP/SLP/CANDP: the tail).
 #define ZS_VIEWS                                                                                   \

@@ -83,8 +83,10 @@ ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId
         int pay = 0;
         if (i < p.S) {
             const int life = SL(i), mx = __ldg(p.static_max + i);
-            pay = static_payload(p, mx, life, life > 0 || fresh);
-            listed = pay != static_payload(p, mx, mx, true);
+            if (life != mx) {  // (most boxes/walls are pristine)
+                pay = static_payload(p, mx, life, life > 0 || fresh);
+                listed = pay != static_payload(p, mx, mx, true);
+            }
         }
         const unsigned m = gballot<G, CV>(e, listed);
         const int pos = n + __popc(m & ((1u << e.gl) - 1u));
@@ -178,7 +180,8 @@ ZS_TPL __device__ __noinline__ int scan_dead_bodies(const ZsParams& p, GrpId id)
     return n <= ZS_DEAD_CAP ? 0 : FL_DEAD_OVER;
 }
 
-ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
+// with_lists: also build the dead-body list (worth it when the launch runs several steps; a single step walks the bitmap)
+ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, bool with_lists) {
     ZS_CONSTS; ZS_VIEWS;
     const size_t row = (size_t)e.env * p.Mp;
 #pragma unroll 1
@@ -197,7 +200,7 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e) {
     gsync<G, CV>(e);
     e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e));
     e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e), e.flags & FL_FRESH);
-    if (ONE) e.flags |= scan_dead_bodies<MPC, G, false>(p, id_of(e));
+    if (ONE && with_lists) e.flags |= scan_dead_bodies<MPC, G, false>(p, id_of(e));
     else e.flags |= FL_DEAD_OVER;
 }
 
@@ -1218,7 +1221,7 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
     ZS_VIEWS;
     const int lane = e.gl;
     const int NP = p.P + p.A;
-    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH | (ONE ? 0 : FL_DEAD_OVER);
+    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH | ((ONE && !(flags_in & FL_DEAD_LAUNCH)) ? 0 : (FL_DEAD_OVER | (flags_in & FL_DEAD_LAUNCH)));
     e.episode = episode;
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
