@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, G == 16 ? ZS_MIN_CTAS_G16 : ZS_MI
     e.gshift = wlane & ~(G - 1);
     e.gm = G == 32 ? 0xffffffffu : (0xffffu << e.gshift);
     const int slot = wid * EPW + (wlane / G);
-    const int env = blockIdx.x * (ZS_WPC * EPW) + slot;
+    const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;  // (a CTA has ZS_WPC warps, or fewer for small batches)
     if (p.tmpl_smem_off >= 0) {
         // stage the pristine observation planes once per CTA: the source of the per-step TMA bulk copies
         uint4* dst = reinterpret_cast<uint4*>(zs_smem + p.tmpl_smem_off);
@@ -417,6 +417,7 @@ struct ZsHandle {
     int sm_count;
     int envs_per_cta;
     int lanes_per_env;
+    int warps_per_cta;
     int smem_bytes;
 };
 
@@ -495,7 +496,7 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     // staging the observation template for the TMA pays off when a launch runs several steps
     ZsParams pp = h->p;
     if (MODE != MODE_STEP || io.n_steps < 4) pp.tmpl_smem_off = -1;
-    const dim3 grid((pp.N + h->envs_per_cta - 1) / h->envs_per_cta), block(ZS_WPC * 32);
+    const dim3 grid((pp.N + h->envs_per_cta - 1) / h->envs_per_cta), block(h->warps_per_cta * 32);
     // the standard rollout shape gets the kernel with that shape compiled in (step_loop_one)
     const bool fast = MODE == MODE_STEP && pp.mpc <= 32 && pp.A == 1 && !pp.obs_per_agent && pp.minimum_zombies == 0 &&
                       pp.obs_scope == ZS_OBS_WORLD && io.actions && io.fmt == ZS_ACTIONS_DISCRETE && io.obs && io.reward &&
@@ -646,7 +647,12 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         const int v = atoi(force);
         if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) h->lanes_per_env = v;
     }
-    h->envs_per_cta = ZS_WPC * (32 / h->lanes_per_env);
+    // warps per CTA: ZS_WPC, or 2 when the batch is small enough that 4-warp CTAs would spread unevenly over the SMs
+    // (a small batch is latency-bound: the most loaded SM sets the pace)
+    h->warps_per_cta = ZS_WPC;
+    if ((p.N + ZS_WPC * (32 / h->lanes_per_env) - 1) / (ZS_WPC * (32 / h->lanes_per_env)) < prop.multiProcessorCount * 5) h->warps_per_cta = 2;
+    if (const char* force = getenv("ZS_WARPS_PER_CTA")) { const int v = atoi(force); if (v == 1 || v == 2 || v == 4) h->warps_per_cta = v; }
+    h->envs_per_cta = h->warps_per_cta * (32 / h->lanes_per_env);
     h->smem_bytes = p.smem_per_env * h->envs_per_cta;
     p.tmpl_smem_off = -1; p.tmpl_planes = 0;
     if (p.obs_scope == ZS_OBS_WORLD && (p.cells & 3) == 0) {
