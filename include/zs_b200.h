@@ -48,9 +48,9 @@ extern "C" {
 
 /* rules (zombsole/rules/factory.py:7-19) */
 enum { ZS_RULES_EXTERMINATION = 0, ZS_RULES_SURVIVAL = 1, ZS_RULES_EVACUATION = 2, ZS_RULES_SAFEHOUSE = 3 };
-/* mobile thing kinds; the bots mirror zombsole/players/{terminator,sniper,troll,hamster}.py */
+/* mobile thing kinds; the bots mirror zombsole/players/{terminator,sniper,troll,hamster,randoman}.py */
 enum { ZS_KIND_ZOMBIE = 0, ZS_KIND_TERMINATOR = 1, ZS_KIND_AGENT = 2, ZS_KIND_SNIPER = 3, ZS_KIND_TROLL = 4,
-       ZS_KIND_HAMSTER = 5 };
+       ZS_KIND_HAMSTER = 5, ZS_KIND_RANDOMAN = 6 };
 /* observation thing labels (zombsole/gym/observation.py:18-26) */
 enum { ZS_LABEL_BOX = 1, ZS_LABEL_DEAD_BODY = 2, ZS_LABEL_OBJECTIVE = 3, ZS_LABEL_WALL = 4,
        ZS_LABEL_ZOMBIE = 5, ZS_LABEL_PLAYER = 6, ZS_LABEL_AGENT = 7 };

@@ -12,8 +12,9 @@ ZS_MAX_AGENTS = 32
 ZS_MAX_SLOTS = 250
 
 RULES = {"extermination": 0, "survival": 1, "evacuation": 2, "safehouse": 3}
-KIND_ZOMBIE, KIND_TERMINATOR, KIND_AGENT, KIND_SNIPER, KIND_TROLL, KIND_HAMSTER = 0, 1, 2, 3, 4, 5
-BOT_KINDS = {"terminator": KIND_TERMINATOR, "sniper": KIND_SNIPER, "troll": KIND_TROLL, "hamster": KIND_HAMSTER}
+KIND_ZOMBIE, KIND_TERMINATOR, KIND_AGENT, KIND_SNIPER, KIND_TROLL, KIND_HAMSTER, KIND_RANDOMAN = 0, 1, 2, 3, 4, 5, 6
+BOT_KINDS = {"terminator": KIND_TERMINATOR, "sniper": KIND_SNIPER, "troll": KIND_TROLL, "hamster": KIND_HAMSTER,
+             "randoman": KIND_RANDOMAN}
 WEAPONS = {"knife": 10, "axe": 11, "gun": 12, "rifle": 13, "shotgun": 14, "random": 255}
 WEAPON_CLAWS = 1
 ACT_NONE, ACT_MOVE, ACT_ATTACK_CLOSEST, ACT_ATTACK, ACT_HEAL, ACT_HEAL_CLOSEST, ACT_ABSENT = range(7)

@@ -438,7 +438,8 @@ static int validate(const ZsConfig* cfg, const ZsMap* map) {
     if (cfg->n_bots < 0 || cfg->n_bots > ZS_MAX_BOTS) return fail("n_bots out of range");
     for (int i = 0; i < cfg->n_bots; ++i)
         if (cfg->bot_kinds[i] != ZS_KIND_TERMINATOR && cfg->bot_kinds[i] != ZS_KIND_SNIPER &&
-            cfg->bot_kinds[i] != ZS_KIND_TROLL && cfg->bot_kinds[i] != ZS_KIND_HAMSTER) return fail("unsupported bot kind");
+            cfg->bot_kinds[i] != ZS_KIND_TROLL && cfg->bot_kinds[i] != ZS_KIND_HAMSTER &&
+            cfg->bot_kinds[i] != ZS_KIND_RANDOMAN) return fail("unsupported bot kind");
     if (cfg->n_agents < 1 || cfg->n_agents > ZS_MAX_AGENTS) return fail("n_agents out of range");
     for (int i = 0; i < cfg->n_agents; ++i) {
         int w = cfg->agent_weapons[i];
@@ -578,6 +579,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     p.n_ps = map->n_player_spawns; p.n_zs = map->n_zombie_spawns; p.obs_elems = lay.obs_elems_per_env;
     memcpy(p.agent_weapons, cfg->agent_weapons, sizeof(p.agent_weapons));
     memcpy(p.bot_kinds, cfg->bot_kinds, sizeof(p.bot_kinds));
+    for (int i = 0; i < cfg->n_bots; ++i) if (cfg->bot_kinds[i] == ZS_KIND_RANDOMAN) p.has_randoman = 1;
     memcpy(p.agent_obs_ids, cfg->agent_obs_ids, sizeof(p.agent_obs_ids));
 
     // ---- map tables

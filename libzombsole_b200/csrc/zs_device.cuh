@@ -38,6 +38,7 @@
 #define D_ATTACK 2
 #define D_HEAL 3
 #define D_WANDER 4            // zombie with no humans: destination drawn in dict order (things.py:101-103)
+#define D_RANDOM 5            // randoman: action, target / direction drawn in dict order (players/randoman.py:9-21)
 
 #define RK_NONE 255           // rank of a slot that is not in the world
 #define ZS_DEAD_CAP 38        // dead-body cells tracked individually (one-lane-per-slot kernels); more -> bitmap scan
@@ -54,6 +55,7 @@ struct ZsParams {
     int32_t obs_scope, obs_enc, sw, obs_count, obs_C;
     int32_t obs_per_agent, max_steps, auto_reset, n_discrete;
     int32_t n_ps, n_zs;
+    int32_t has_randoman;     // some bot is a randoman: decide-phase draws are resolved sequentially in dict order
     int64_t obs_elems;
     uint8_t agent_weapons[ZS_MAX_AGENTS];
     uint8_t bot_kinds[ZS_MAX_BOTS];

@@ -301,6 +301,85 @@ ZS_TPL __device__ __forceinline__ int prefix_popc(const ZsParams& p, const Env& 
     return n + __popc(MASKW(word0 + (bit >> 5)) & ((1u << (bit & 31)) - 1u));
 }
 
+// ---------------------------------------------------------------- decide-phase draws with a randoman around
+// A decision that draws is handed over as DTYPE(s) = D_WANDER (free adjacent cells as a bit-mask in BK(s)) or D_RANDOM
+// and comes back packed in BK(s): type << 29 | (b + 1) << 15 | (a + 1) for a move to (a, b), type << 29 | target for a hit.
+__device__ __forceinline__ uint32_t pack_decision(int type, int a, int b) {
+    return ((uint32_t)type << 29) | ((uint32_t)(b + 1) << 15) | (uint32_t)(a + (type == D_MOVE ? 1 : 0));
+}
+__device__ __forceinline__ void unpack_decision(uint32_t w, int& type, int& a, int& b) {
+    type = (int)(w >> 29);
+    a = (int)(w & 0x7fffu) - (type == D_MOVE ? 1 : 0);
+    b = (int)((w >> 15) & 0x3fffu) - 1;
+}
+// The draws of wandering zombies / hamsters (one each) and randomans (two or three each: what the second one means and
+// whether there is a third depends on the first) are consumed in actor (dict) order, so with a randoman in the game the
+// drawing actors are walked one after the other.  RandoMan.next_step (players/randoman.py:9-21): random.choice(('move',
+// 'attack', 'heal')); attack / heal: random.choice(list(things.values())) — any thing of World.things by dict index:
+// the boxes/walls still in the world in file order, then the mobile things in dict order; move: coordinate
+// random.choice((0, 1)) changes by random.choice((-1, 1)), drawn in that order.  Returns the draws consumed.
+ZS_TPL __device__ __noinline__ int decide_draws_seq(const ZsParams& p, GrpId id, int episode, uint32_t t_word, int nlive, int flags) {
+    ZS_CONSTS;
+    Env e = env_of(p, id);
+    ZS_VIEWS;
+    e.episode = episode;
+    const int lane = e.gl;
+    const bool fresh = flags & FL_FRESH;
+    int n_sp = 0;  // boxes/walls in World.things
+#pragma unroll 1
+    for (int i0 = 0; i0 < p.S; i0 += G) n_sp += __popc(gballot<G, CV>(e, i0 + lane < p.S && (SL(i0 + lane) > 0 || fresh)));
+    int k = 0;
+#pragma unroll 1
+    for (int r = 0; r < nlive; ++r) {
+        const int s = SOR(r);
+        const int ty = DTYPE(s);
+        if (ty != D_WANDER && ty != D_RANDOM) continue;
+        const uint32_t xy = TXY(s);
+        const int x = xy_x(xy), y = xy_y(xy);
+        uint32_t out;
+        if (ty == D_WANDER) {
+            const unsigned fm = BK(s);
+            int pick = below(draw_at(p, e, t_word, k), __popc(fm));
+            k += 1;
+            int d = 0;
+            for (int q = 0; q < 4; ++q) if ((fm >> q) & 1u) { if (pick == 0) { d = q; break; } --pick; }
+            out = pack_decision(D_MOVE, x + adj_dx(d), y + adj_dy(d));
+        } else {
+            const int action = below(draw_at(p, e, t_word, k), 3);
+            if (action == 0) {
+                const int axis = below(draw_at(p, e, t_word, k + 1), 2);
+                const int sign = below(draw_at(p, e, t_word, k + 2), 2) ? 1 : -1;
+                k += 3;
+                out = pack_decision(D_MOVE, x + (axis == 0 ? sign : 0), y + (axis == 1 ? sign : 0));
+            } else {
+                const int idx = below(draw_at(p, e, t_word, k + 1), n_sp + nlive);
+                k += 2;
+                int target;
+                if (idx >= n_sp) target = SOR(idx - n_sp);
+                else {  // the idx-th box/wall that is still in the world, in file order
+                    int base = 0, found = -1;
+#pragma unroll 1
+                    for (int i0 = 0; i0 < p.S && found < 0; i0 += G) {
+                        unsigned m = gballot<G, CV>(e, i0 + lane < p.S && (SL(i0 + lane) > 0 || fresh));
+                        const int c = __popc(m);
+                        if (idx < base + c) {
+                            for (int q = idx - base; q > 0; --q) m &= m - 1;
+                            found = i0 + __ffs(m) - 1;
+                        }
+                        base += c;
+                    }
+                    target = p.M + found;
+                }
+                out = pack_decision(action == 1 ? D_ATTACK : D_HEAL, target, 0);
+            }
+        }
+        gsync<G, CV>(e);  // (everybody has read BK(s))
+        if (lane == 0) BK(s) = out;
+    }
+    gsync<G, CV>(e);
+    return k;
+}
+
 // ---------------------------------------------------------------- World.step (core.py:72-78)
 // General version: more slots than lanes (round loops over the slots).  Returns the draws consumed so far in this step.
 ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
@@ -419,6 +498,8 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                     type = D_HEAL; a = s;
                 } else if (p.bot_kinds[s] == ZS_KIND_HAMSTER) { // Hamster.next_step (players/hamster.py:10-14)
                     if (freemask) { type = D_WANDER; a = (int)freemask; any_wander = true; }
+                } else if (p.bot_kinds[s] == ZS_KIND_RANDOMAN) { // RandoMan.next_step: resolved in decide_draws_seq
+                    type = D_RANDOM; any_wander = true;
                 } else {  // Terminator.next_step (players/terminator.py:9-37)
                     if (tg < 0) { type = D_HEAL; a = s; }
                     else if (d2 > c_range2[TM(s) & 15]) {
@@ -455,7 +536,22 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     n_idle = gadd<G, CV>(e, n_idle);
     gsync<G, CV>(e);
     int nd = 0;
-    if (gany<G, CV>(e, any_wander)) {
+    if (p.has_randoman) {
+        if (gany<G, CV>(e, any_wander)) {
+#pragma unroll 1
+            for (int s = e.gl; s < p.M; s += G) if (DTYPE(s) == D_WANDER) BK(s) = (uint32_t)DA(s);
+            gsync<G, CV>(e);
+            nd = decide_draws_seq<MPC, G, false>(p, id_of(e), e.episode, t_word, e.nlive, e.flags);
+#pragma unroll 1
+            for (int s = e.gl; s < p.M; s += G) {
+                if (DTYPE(s) != D_WANDER && DTYPE(s) != D_RANDOM) continue;
+                int ty, a, b;
+                unpack_decision(BK(s), ty, a, b);
+                DTYPE(s) = (uint8_t)ty; DA(s) = (int16_t)a; DB(s) = (int16_t)b;
+            }
+            gsync<G, CV>(e);
+        }
+    } else if (gany<G, CV>(e, any_wander)) {
         // wandering zombies and hamsters draw random.choice(positions) in dict order (things.py:101-103, hamster.py:12-14)
         int mine = 0;
 #pragma unroll 1
@@ -851,8 +947,10 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
                 if (tg >= 0) { type = D_ATTACK; a = tg; }
             } else if (bkind == ZS_KIND_TROLL) {   // Troll.next_step (players/troll.py:10-12)
                 type = D_HEAL; a = s;
-            } else {                               // Hamster.next_step (players/hamster.py:10-14)
+            } else if (bkind == ZS_KIND_HAMSTER) { // Hamster.next_step (players/hamster.py:10-14)
                 if (freemask) type = D_WANDER;
+            } else {                               // RandoMan.next_step: resolved in decide_draws_seq
+                type = D_RANDOM;
             }
         } else {  // Agent.next_step (players/agent.py:28-96)
             if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + adx; b = y + ady; }
@@ -873,7 +971,14 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     PH(2);
     // wandering zombies and hamsters draw random.choice(positions) in dict order (things.py:101-103, hamster.py:12-14)
     int nd = 0;
-    if (wany<G, CV>(e, type == D_WANDER)) {
+    if (p.has_randoman) {
+        if (wany<G, CV>(e, type == D_WANDER || type == D_RANDOM)) {
+            if (in_cap) { MPOS(s) = (uint8_t)type; BK(s) = freemask; }  // (MPOS = DTYPE, free until the list is built)
+            gsync<G, CV>(e);
+            nd = decide_draws_seq<MPC, G, false>(p, id_of(e), e.episode, t_word, e.nlive, e.flags);
+            if (type == D_WANDER || type == D_RANDOM) unpack_decision(BK(s), type, a, b);
+        }
+    } else if (wany<G, CV>(e, type == D_WANDER)) {
         const unsigned wm = gor_bits<G, CV>(e, type == D_WANDER ? (1u << rk) : 0u);
         if (type == D_WANDER) {
             int pick = below(draw_at(p, e, t_word, __popc(wm & ((1u << rk) - 1u))), __popc(freemask));
@@ -1241,11 +1346,11 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
         if (s < NP) TL(s) = 100;
     }
     gsync<G, CV>(e);
-    // trolls and hamsters are created without a weapon: Player.__init__ draws random.choice([Gun, Shotgun, Rifle,
+    // trolls, hamsters and randomans are created without a weapon: Player.__init__ draws random.choice([Gun, Shotgun, Rifle,
     // Knife, Axe]) (things.py:115-116), in player_names order, before the agents are created (game.py:157-165)
 #pragma unroll 1
     for (int b = 0; b < p.P; ++b) {
-        if (p.bot_kinds[b] == ZS_KIND_TROLL || p.bot_kinds[b] == ZS_KIND_HAMSTER) {
+        if (p.bot_kinds[b] == ZS_KIND_TROLL || p.bot_kinds[b] == ZS_KIND_HAMSTER || p.bot_kinds[b] == ZS_KIND_RANDOMAN) {
             const int pick = below(draw_at(p, e, 0u, k), 5);
             ++k;
             if (lane == 0) TM(b) = (uint8_t)(pick == 0 ? ZS_WEAPON_GUN : pick == 1 ? ZS_WEAPON_SHOTGUN

@@ -57,7 +57,7 @@ ZSO_EXPORT void zso_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint
 }
 
 /* ------------------------------------------------------------------ types */
-enum { T_BOX = 0, T_WALL, T_ZOMBIE, T_TERMINATOR, T_AGENT, T_SNIPER, T_TROLL, T_HAMSTER };
+enum { T_BOX = 0, T_WALL, T_ZOMBIE, T_TERMINATOR, T_AGENT, T_SNIPER, T_TROLL, T_HAMSTER, T_RANDOMAN };
 enum { A_MOVE = 1, A_ATTACK = 2, A_HEAL = 3 };
 
 typedef struct Thing {
@@ -436,16 +436,16 @@ static void initialize_world(const ZsoHandle* h, Env* e, int env_local, int epis
     for (int i = 0; i < h->S; ++i) world_insert(h, e, i); /* same objects: life persists (game.py:154-155) */
     int32_t ids[ZS_MAX_SLOTS];
     /* bots (create_player, game.py:157-159): terminator carries a Shotgun (terminator.py:41-42), sniper a Rifle
-       (sniper.py:23-24); troll and hamster are created without a weapon and Player.__init__ draws
+       (sniper.py:23-24); troll, hamster and randoman are created without a weapon and Player.__init__ draws
        random.choice([Gun, Shotgun, Rifle, Knife, Axe]) (things.py:115-116) */
     for (int b = 0; b < h->P; ++b) {
         Thing* t = &e->things[h->S + b];
         t->life = 100; t->in_world = 0;
         switch (h->cfg.bot_kinds[b]) {
             case ZS_KIND_SNIPER: t->type = T_SNIPER; t->weapon = ZS_WEAPON_RIFLE; break;
-            case ZS_KIND_TROLL: case ZS_KIND_HAMSTER: {
+            case ZS_KIND_TROLL: case ZS_KIND_HAMSTER: case ZS_KIND_RANDOMAN: {
                 static const uint8_t choices[5] = { ZS_WEAPON_GUN, ZS_WEAPON_SHOTGUN, ZS_WEAPON_RIFLE, ZS_WEAPON_KNIFE, ZS_WEAPON_AXE };
-                t->type = h->cfg.bot_kinds[b] == ZS_KIND_TROLL ? T_TROLL : T_HAMSTER;
+                t->type = h->cfg.bot_kinds[b] == ZS_KIND_TROLL ? T_TROLL : h->cfg.bot_kinds[b] == ZS_KIND_HAMSTER ? T_HAMSTER : T_RANDOMAN;
                 t->weapon = choices[randbelow(h, e, 5)];
                 break;
             }
@@ -598,6 +598,26 @@ static const int32_t DISCRETE_ACTIONS[7][3] = {
     { ZS_ACT_ATTACK_CLOSEST, 0, 0 }, { ZS_ACT_HEAL, 0, 0 }, { ZS_ACT_HEAL_CLOSEST, 0, 0 },
 };
 
+/* RandoMan.next_step (players/randoman.py:9-21): random.choice(('move', 'attack', 'heal')); attack / heal take
+   random.choice(list(things.values())) — ANY thing in World.things, boxes and walls included, in dict order; move
+   changes one coordinate (random.choice((0, 1))) by random.choice((-1, 1)), drawn in that order */
+static int randoman_next_step(const ZsoHandle* h, Env* e, int self, Action* out) {
+    const Thing* me = &e->things[self];
+    out->actor = self;
+    int action = (int)randbelow(h, e, 3);
+    if (action != 0) {
+        out->type = action == 1 ? A_ATTACK : A_HEAL;
+        out->target = e->order[randbelow(h, e, (uint32_t)e->n_order)];
+    } else {
+        int axis = (int)randbelow(h, e, 2);
+        int sign = randbelow(h, e, 2) ? 1 : -1;
+        out->type = A_MOVE;
+        out->dx = me->x + (axis == 0 ? sign : 0);
+        out->dy = me->y + (axis == 1 ? sign : 0);
+    }
+    return 1;
+}
+
 static void env_step(ZsoHandle* h, Env* e, int env_local, const int32_t* actions, int fmt, int32_t* obs,
                      double* reward, uint8_t* terminated, uint8_t* truncated, uint8_t* agent_mask, int force_auto_reset) {
     const int A = h->A;
@@ -632,6 +652,7 @@ static void env_step(ZsoHandle* h, Env* e, int env_local, const int32_t* actions
             case T_SNIPER: ok = sniper_next_step(h, e, id, &act); break;
             case T_TROLL: ok = troll_next_step(id, &act); break;
             case T_HAMSTER: ok = hamster_next_step(h, e, id, &act); break;
+            case T_RANDOMAN: ok = randoman_next_step(h, e, id, &act); break;
             default: ok = agent_next_step(h, e, id, acts[e->things[id].agent_index], &act); break;
         }
         if (ok) e->actions[n_act++] = act;

@@ -44,12 +44,17 @@ PLAN = {
     "minz_allcells": (2, 80, 0),
     "bots_mixed": (2, 60, 0),
     "bots_hamsters": (2, 100, 0),
+    "bots_randoman": (2, 120, 0),
+    "randoman_crowd": (2, 60, 0),
 }
 
 
 def main():
     total = 0
+    only = set(sys.argv[1:])  # optional: regenerate just the named fixtures
     for name, (E, T, mes) in PLAN.items():
+        if only and name not in only:
+            continue
         cfgd = parity_util.CONFIGS[name]
         out = {"meta": np.array([SEED, BASE, E, T, mes], np.int64)}
         resets = 0

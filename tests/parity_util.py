@@ -56,6 +56,14 @@ CONFIGS = {
     "bots_hamsters": dict(kind="multi", rules_name="survival", player_names=["hamster", "hamster", "sniper"],
                           map_name="hallway", agent_ids=["0", "1"], agent_weapons="knife", initial_zombies=6,
                           minimum_zombies=4, surroundings_width=11),
+    # randoman (players/randoman.py): attack / heal ANY thing of World.things by dict index (boxes and walls included),
+    # 2 or 3 decide-phase draws per bot
+    "bots_randoman": dict(kind="single", rules_name="extermination", player_names=["randoman", "randoman", "hamster"],
+                          map_name="boxed", agent_ids=[0], agent_weapons="gun", initial_zombies=6, minimum_zombies=0,
+                          observation_scope="world", observation_position_encoding="simple"),
+    "randoman_crowd": dict(kind="multi", rules_name="survival", player_names=["randoman", "terminator", "randoman"],
+                           map_name="fort", agent_ids=["0", "1"], agent_weapons="shotgun", initial_zombies=40,
+                           minimum_zombies=30, surroundings_width=9),
     # slot capacity 256: 8 agents + 2 bots + 236 zombies on the biggest stock map with zombie spawns
     "fort_max_slots": dict(kind="multi", rules_name="extermination", player_names=["terminator", "sniper"], map_name="fort",
                            agent_ids=[str(i) for i in range(8)], agent_weapons=["shotgun", "axe"], initial_zombies=236,

@@ -17,6 +17,7 @@ HALF_WARP_CASES = [
     ("gym_v0_alone", 64, 80, 0), ("gym_surroundings", 32, 60, 0), ("surroundings_channels", 32, 80, 0),
     ("safehouse_small", 32, 120, 0), ("multi_boxed_2p", 64, 80, 0), ("survival_minz", 32, 120, 25),
     ("bots_hamsters", 32, 120, 0), ("minz_allcells", 16, 80, 0), ("no_zombies", 16, 30, 0),
+    ("bots_randoman", 64, 150, 0),
 ]
 
 
