@@ -636,8 +636,23 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     int cand = 1;
     if (p.P + p.A > 0) cand = p.n_ps > 0 ? p.n_ps : cells;
     if (p.Z > 0) { int zc = p.n_zs > 0 ? p.n_zs : cells; if (zc > cand) cand = zc; }
+    // the lean world init (initialize_world_lists): one lane per slot, spawn cells for everybody, fixed weapons
+    p.fast_init = p.Mp <= 32 && p.n_ps >= p.P + p.A && p.n_ps > 0 && p.n_zs > 0 && p.n_zs >= p.initial_zombies &&
+                  p.n_ps + p.n_zs <= 256 && p.initial_zombies > 0;
+    for (int i = 0; i < p.P; ++i) if (p.bot_kinds[i] != ZS_KIND_TERMINATOR && p.bot_kinds[i] != ZS_KIND_SNIPER) p.fast_init = 0;
+    for (int i = 0; i < p.A; ++i) if (p.agent_weapons[i] == ZS_WEAPON_RANDOM) p.fast_init = 0;
+    if (getenv("ZS_NO_FAST_INIT")) p.fast_init = 0;
+    if (p.fast_init) cand = p.n_ps + p.n_zs;  // both index lists side by side
     p.cand_cap = cand;
-    p.off_cand = take(cand * 2);
+    // the candidate list is only touched while things are being placed: long ones (a map without spawn cells offers every
+    // cell) live in device memory, so they do not cost resident CTAs
+    if (cand > 256) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, (size_t)p.N * cand * sizeof(uint16_t)) != cudaSuccess) { zs_destroy(h); return fail("out of device memory (spawn candidate lists)"); }
+        h->dev_allocs.push_back(d);
+        p.cand_global = (uint16_t*)d;
+        p.off_cand = take(16);
+    } else p.off_cand = take(cand * 2);
     p.off_spl = take(p.Sp * 4);
     p.off_sidx = take(p.Sp);
     p.smem_per_env = round_up(struct_bytes + off, 16);

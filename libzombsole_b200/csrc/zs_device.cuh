@@ -56,6 +56,7 @@ struct ZsParams {
     int32_t obs_per_agent, max_steps, auto_reset, n_discrete;
     int32_t n_ps, n_zs;
     int32_t has_randoman;     // some bot is a randoman: decide-phase draws are resolved sequentially in dict order
+    int32_t fast_init;        // world inits take initialize_world_lists (spawn cells for everybody, fixed weapons)
     int64_t obs_elems;
     uint8_t agent_weapons[ZS_MAX_AGENTS];
     uint8_t bot_kinds[ZS_MAX_BOTS];
@@ -77,6 +78,8 @@ struct ZsParams {
     // ---- shared memory: run-time sized tail behind EnvS<MPC> (byte offsets from the end of the struct)
     int32_t off_dead, off_sl, off_cand, off_spl, off_sidx;
     int32_t cand_cap;
+    uint16_t* cand_global;         // spawn candidate lists in device memory [N, cand_cap] when they are too long for shared
+                                   // memory (maps without spawn cells: every cell is a candidate); NULL = in shared memory
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
     int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
     int32_t tmpl_planes;           // planes staged there: 1 (simple) or 3 (channels: label, life, zeros)
@@ -185,7 +188,8 @@ struct Env {
     uint8_t* const GRIDP = zs_smem + e.b + sizeof(EnvS<MPC>);                                        \
     uint32_t* const DEADP = reinterpret_cast<uint32_t*>(GRIDP + p.off_dead);                         \
     int16_t* const SLP = reinterpret_cast<int16_t*>(GRIDP + p.off_sl);                               \
-    uint16_t* const CANDP = reinterpret_cast<uint16_t*>(GRIDP + p.off_cand);                         \
+    uint16_t* const CANDP = p.cand_global ? p.cand_global + (size_t)e.env * p.cand_cap                 \
+                                          : reinterpret_cast<uint16_t*>(GRIDP + p.off_cand);             \
     uint32_t* const SPLP = reinterpret_cast<uint32_t*>(GRIDP + p.off_spl);                           \
     uint8_t* const SIDXP = GRIDP + p.off_sidx;                         \
     (void)S; (void)GRIDP; (void)DEADP; (void)SLP; (void)CANDP; (void)SPLP; (void)SIDXP
