@@ -92,6 +92,17 @@ class ZsEngine(object):
                 torch.empty(lead, dtype=torch.uint8, device=self.device),
                 torch.empty(lead, dtype=torch.uint8, device=self.device))
 
+    def new_host_outputs(self):
+        """Observation / reward / flag buffers in PINNED HOST memory.  Under unified addressing the device reaches
+        pinned host memory at the same address, so the step kernel can write its outputs there directly (the
+        device-to-host transfer happens inside the kernel, overlapped with the transition, instead of as separate
+        copies afterwards)."""
+        rshape = (self.N,) + ((self.A,) if self.per_agent else ())
+        return (torch.empty((self.N,) + self.obs_shape, dtype=torch.int32).pin_memory(),
+                torch.empty(rshape, dtype=torch.float64).pin_memory(),
+                torch.empty((self.N,), dtype=torch.uint8).pin_memory(),
+                torch.empty((self.N,), dtype=torch.uint8).pin_memory())
+
     # ------------------------------------------------------------------ the ABI calls
     def reset(self, mask=None, obs=None):
         """zs_reset: re-initialise the masked worlds (all if mask is None)."""

@@ -65,7 +65,7 @@ class ZombsoleVectorEnv(object):
     def __init__(self, rules_name, player_names, map_name, agent_id, initial_zombies=0, minimum_zombies=0,
                  render_mode=None, observation_scope="world", observation_position_encoding="simple",
                  agent_weapon="rifle", debug=False, *, num_envs=1, device="cuda", seed=0, env_index_base=0,
-                 max_episode_steps=None, auto_reset=True):
+                 max_episode_steps=None, auto_reset=True, host_outputs=False):
         if render_mode is not None:
             if render_mode not in self.metadata["render.modes"]:
                 raise ValueError("render_mode={} is not supported".format(render_mode))
@@ -85,8 +85,14 @@ class ZombsoleVectorEnv(object):
         self.observation_space = self.single_observation_space
         self.single_action_space = Discrete(len(self.game_actions))
         self.action_space = self.single_action_space
-        self.obs = self.engine.new_obs()
-        self.reward, self._term, self._trunc = self.engine.new_outputs()
+        # host_outputs: step() returns tensors in pinned host memory that the kernel wrote directly (zero-copy over
+        # PCIe, overlapped with the transition) and has synchronised on — for loops whose policy runs on the host
+        self.host_outputs = bool(host_outputs)
+        if self.host_outputs:
+            self.obs, self.reward, self._term, self._trunc = self.engine.new_host_outputs()
+        else:
+            self.obs = self.engine.new_obs()
+            self.reward, self._term, self._trunc = self.engine.new_outputs()
         self._actions = torch.zeros((num_envs, 1, 3), dtype=torch.int32, device=self.device)
 
     # -- the reference's object protocol for one world of the batch
@@ -108,7 +114,9 @@ class ZombsoleVectorEnv(object):
             self._actions.copy_(torch.from_numpy(rows), non_blocking=True)
             return self._actions, abi.ACTIONS_FULL
         t = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
-        if t.dtype != torch.int32 or t.device != self.device:
+        if self.host_outputs and t.dtype == torch.int32 and t.device.type == "cpu" and t.is_pinned():
+            pass  # the kernel reads a pinned host action tensor in place
+        elif t.dtype != torch.int32 or t.device != self.device:
             t = t.to(device=self.device, dtype=torch.int32, non_blocking=True)
         t = t.contiguous()
         if t.numel() == self.num_envs:
@@ -122,6 +130,8 @@ class ZombsoleVectorEnv(object):
         output buffers: they are overwritten by the next call."""
         a, fmt = self._stage_actions(actions)
         self.engine.step(a, fmt, self.obs, self.reward, self._term, self._trunc)
+        if self.host_outputs:
+            torch.cuda.current_stream(self.device).synchronize()  # the host owns the results when step() returns
         return self.obs, self.reward, self._term.bool(), self._trunc.bool(), {}
 
     def reset(self, seed=None, options=None, mask=None):
@@ -129,6 +139,8 @@ class ZombsoleVectorEnv(object):
         accepted for API compatibility and ignored, as in the reference (it only seeds gymnasium's unused
         np_random): the draw stream is fixed by the constructor's ``seed``."""
         self.engine.reset(mask, self.obs)
+        if self.host_outputs:
+            torch.cuda.current_stream(self.device).synchronize()
         return self.obs, {}
 
     def rollout(self, n_steps, actions=None, first_step_index=0, obs=None, reward=None, terminated=None, truncated=None):

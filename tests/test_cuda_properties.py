@@ -231,3 +231,24 @@ def test_standard_rollout_shape_matches_oracle(name, N, K, lanes, monkeypatch):
     assert np.array_equal(term.cpu().numpy(), te) and np.array_equal(trunc.cpu().numpy(), tr)
     assert np.array_equal(eng.episode_stats().cpu().numpy(), ref.stats())
     eng.close()
+
+
+def test_host_output_mode_matches_device_outputs():
+    """ZombsoleVectorEnv(host_outputs=True): the kernel writes observation / reward / flags straight into pinned host
+    memory and reads the pinned host action tensor in place; same values as the device-output env."""
+    from libzombsole_b200.gym_env import ZombsoleVectorEnv
+    kw = dict(rules_name="extermination", player_names=["terminator", "terminator"], map_name="bridge", agent_id=0,
+              initial_zombies=10, minimum_zombies=0, num_envs=512, seed=9, max_episode_steps=50)
+    dev_env, host_env = ZombsoleVectorEnv(**kw), ZombsoleVectorEnv(host_outputs=True, **kw)
+    o0, _ = dev_env.reset()
+    h0, _ = host_env.reset()
+    assert h0.device.type == "cpu" and h0.is_pinned() and torch.equal(o0.cpu(), h0)
+    g = torch.Generator().manual_seed(1)
+    for t in range(120):
+        a = torch.randint(0, 6, (512,), generator=g, dtype=torch.int32).pin_memory()
+        o, r, te, tr, _ = dev_env.step(a)
+        ho, hr, hte, htr, _ = host_env.step(a)
+        assert torch.equal(o.cpu(), ho) and torch.equal(r.cpu().view(torch.int64), hr.view(torch.int64))
+        assert torch.equal(te.cpu(), hte) and torch.equal(tr.cpu(), htr)
+    dev_env.close()
+    host_env.close()
