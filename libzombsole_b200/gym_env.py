@@ -156,6 +156,10 @@ class ZombsoleVectorEnv(object):
     def render(self):
         raise ValueError("mode={} is not supported".format(self.render_mode))
 
+    def render_text(self, env=0, use_basic_icons=True):
+        """Text frame of world ``env`` laid out like the reference's terminal renderer (renderer.py:45-88); debugging aid."""
+        return self.game(env).draw_text(use_basic_icons)
+
     def close(self):
         self.engine.close()
 

@@ -182,6 +182,8 @@ class Game(object):
         self.map = engine.map
         self.world = World(self)
         self.players = [Terminator(engine, env, i) for i in range(len(player_names))]
+        for pl, name in zip(self.players, self.player_names):
+            pl.name = name  # every scripted player is created with its module's name (players/*.py: create())
         self.agents = [Agent(engine, env, len(player_names) + i, aid) for i, aid in enumerate(agent_ids)]
 
     def _slot_thing(self, s):
@@ -194,6 +196,14 @@ class Game(object):
 
     def get_all_players(self):
         return self.players + self.agents
+
+    def draw_text(self, use_basic_icons=True):
+        """The frame Game.draw() would print (game.py:236-238, renderer.py:45-88), as a string."""
+        from .renderer import TerminalRenderer
+        return TerminalRenderer(use_basic_icons).draw_text(self)
+
+    def draw(self):
+        print(self.draw_text())
 
     def get_agents_health(self):
         return sum(t.life for t in self.agents)
