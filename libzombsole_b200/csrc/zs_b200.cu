@@ -653,8 +653,17 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         p.cand_global = (uint16_t*)d;
         p.off_cand = take(16);
     } else p.off_cand = take(cand * 2);
-    p.off_spl = take(p.Sp * 4);
-    p.off_sidx = take(p.Sp);
+    if (p.mpc > 32 && p.Sp > 512) {  // (only the general kernels look at spl_global)
+        p.spl_pitch = p.Sp + (p.Sp + 3) / 4;  // Sp entries, then Sp index bytes
+        void* d = nullptr;
+        if (cudaMalloc(&d, (size_t)p.N * p.spl_pitch * sizeof(uint32_t)) != cudaSuccess) { zs_destroy(h); return fail("out of device memory (static patch lists)"); }
+        h->dev_allocs.push_back(d);
+        p.spl_global = (uint32_t*)d;
+        p.off_spl = take(16); p.off_sidx = take(16);
+    } else {
+        p.off_spl = take(p.Sp * 4);
+        p.off_sidx = take(p.Sp);
+    }
     p.smem_per_env = round_up(struct_bytes + off, 16);
     // lanes per env: a half warp (two envs per warp, in lock-step) when an env has at most 16 slots, the env count is
     // even and the batch is large enough that the halved instruction count matters more than the few extra cycles a

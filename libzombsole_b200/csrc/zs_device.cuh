@@ -78,6 +78,8 @@ struct ZsParams {
     // ---- shared memory: run-time sized tail behind EnvS<MPC> (byte offsets from the end of the struct)
     int32_t off_dead, off_sl, off_cand, off_spl, off_sidx;
     int32_t cand_cap;
+    uint32_t* spl_global;          // static patch lists + SIDX bytes in device memory [N, spl_pitch words] for the kernels with
+    int32_t spl_pitch;             // more slots than lanes on maps with many boxes/walls (keeps CTAs resident); NULL = shared
     uint16_t* cand_global;         // spawn candidate lists in device memory [N, cand_cap] when they are too long for shared
                                    // memory (maps without spawn cells: every cell is a candidate); NULL = in shared memory
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
@@ -190,8 +192,10 @@ struct Env {
     int16_t* const SLP = reinterpret_cast<int16_t*>(GRIDP + p.off_sl);                               \
     uint16_t* const CANDP = p.cand_global ? p.cand_global + (size_t)e.env * p.cand_cap                 \
                                           : reinterpret_cast<uint16_t*>(GRIDP + p.off_cand);             \
-    uint32_t* const SPLP = reinterpret_cast<uint32_t*>(GRIDP + p.off_spl);                           \
-    uint8_t* const SIDXP = GRIDP + p.off_sidx;                         \
+    uint32_t* const SPLP = (MPC > 32 && p.spl_global) ? p.spl_global + (size_t)e.env * p.spl_pitch       \
+                                                      : reinterpret_cast<uint32_t*>(GRIDP + p.off_spl);  \
+    uint8_t* const SIDXP = (MPC > 32 && p.spl_global) ? reinterpret_cast<uint8_t*>(SPLP + p.Sp)          \
+                                                      : GRIDP + p.off_sidx;                              \
     (void)S; (void)GRIDP; (void)DEADP; (void)SLP; (void)CANDP; (void)SPLP; (void)SIDXP
 #define GRID(i) GRIDP[i]
 #define DEADW(i) DEADP[i]

@@ -1249,28 +1249,49 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
     }
     gsync<G, CV>(e);
     const int placed = count < n ? count : n;
+    // random.shuffle + spawns.pop() (core.py:54-61): only the first `placed` Fisher-Yates iterations decide anything, and
+    // they touch at most 2 * placed positions of the list.  Iteration `it` swaps positions i = n - 1 - it and j = draw;
+    // the value at a position is what the LAST earlier iteration with that j left there, else the list's own entry.
+    // So: read the entries at all i and j up front (in parallel — the list may be in device memory), find every
+    // iteration's predecessors in parallel, and leave only a chain of shared-memory reads to one lane.
+    uint16_t* const Bi = reinterpret_cast<uint16_t*>(S.act);  // [MPC] list entry at i
+    uint16_t* const Bj = Bi + MPC;                            // [MPC] list entry at j
+    uint16_t* const Jp = Bj + MPC;                            // [MPC] j
+    uint16_t* const Vw = Jp + MPC;                            // [MPC] value the iteration writes to position j
+    int16_t* const Pi = reinterpret_cast<int16_t*>(S.draws);  // [MPC] last earlier iteration that wrote position i, or -1
+    int16_t* const Pj = Pi + MPC;                             // [MPC] ... position j
+    uint16_t* const Ch = reinterpret_cast<uint16_t*>(Pj + MPC);  // [MPC] the cell the it-th thing gets
 #pragma unroll 1
     for (int it = e.gl; it < placed; it += G) {
         const int i = n - 1 - it;
-        DRAWS(it) = i >= 1 ? (uint32_t)below(draw_at(p, e, t_word, k + it), i + 1) : 0u;
+        const int j = i >= 1 ? below(draw_at(p, e, t_word, k + it), i + 1) : i;
+        Jp[it] = (uint16_t)j; Bi[it] = CAND(i); Bj[it] = CAND(j);
+    }
+    gsync<G, CV>(e);
+#pragma unroll 1
+    for (int it = e.gl; it < placed; it += G) {
+        const int i = n - 1 - it, j = Jp[it];
+        int pi = -1, pj = -1;
+#pragma unroll 1
+        for (int q = 0; q < it; ++q) { const int jq = Jp[q]; if (jq == i) pi = q; if (jq == j) pj = q; }
+        Pi[it] = (int16_t)pi; Pj[it] = (int16_t)pj;
     }
     gsync<G, CV>(e);
     if (lane == 0) {
-        // the swaps are the only sequential part: iteration `it` takes the candidate at its partner's position and
-        // leaves its own there (positions >= i are never read again); the chosen cell replaces the draw
 #pragma unroll 1
         for (int it = 0; it < placed; ++it) {
-            const int i = n - 1 - it;
-            int c = CAND(i);
-            if (i >= 1) { const int j = (int)DRAWS(it); const int cj = CAND(j); CAND(j) = (uint16_t)c; c = cj; }
-            DRAWS(it) = (uint32_t)c;
+            const int pi = Pi[it], pj = Pj[it];
+            const int vi = pi >= 0 ? (int)Vw[pi] : (int)Bi[it];
+            const int vj = (int)Jp[it] == n - 1 - it ? vi : (pj >= 0 ? (int)Vw[pj] : (int)Bj[it]);
+            Vw[it] = (uint16_t)vi;   // position j now holds what was at i
+            Ch[it] = (uint16_t)vj;   // position i (never read again) holds what was at j: the it-th thing's cell
         }
         SCALW(ZS_S_STAMP_COUNTER) = rank0 + placed;
     }
     gsync<G, CV>(e);
 #pragma unroll 1
     for (int it = e.gl; it < placed; it += G) {  // spawns.pop() for the it-th thing: place it, append it to the dict order
-        const int c = (int)DRAWS(it);
+        const int c = (int)Ch[it];
         const int s = LIST(it);
         const int y = c / p.W;
         TXY(s) = xy_pack(c - y * p.W, y);
