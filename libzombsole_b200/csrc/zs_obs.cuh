@@ -162,35 +162,96 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e
     }
 }
 
-// surroundings window (observation.py:99-119): rows = y, columns = x, centred on the agent's
-// (possibly stale, if dead) position; out-of-bounds cells are a fresh Wall (observation.py:43-44,64-65)
-ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, const Env& e, int32_t* __restrict__ obs) {
+// surroundings window (observation.py:99-119): rows = y, columns = x, centred on the agent's (possibly stale, if
+// dead) position; out-of-bounds cells are a fresh Wall (observation.py:43-44,64-65).  Like the world scope it is
+// written in two passes: the pristine layer of every window straight from the (L1-resident) template planes, then
+// the cells that differ — static patch list, dead bodies, mobile things — stored into the windows they fall in.
+// The occupancy grid says what is on top of a cell, so every patched cell has exactly one writer; one __syncwarp
+// orders the patches after pass 1.
+__device__ __forceinline__ void window_store(const ZsParams& p, int32_t* o, int ww, int idx, int v0, int v1, int v2) {
+    if (p.obs_enc == ZS_OBS_SIMPLE) o[idx] = v0;
+    else { o[idx] = v0; o[ww + idx] = v1; o[2 * ww + idx] = v2; }
+}
+ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, Env& e, int32_t* __restrict__ obs) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl;
     const int w = p.sw, half = p.sw >> 1, ww = p.sw * p.sw;
+    const bool simple = p.obs_enc == ZS_OBS_SIMPLE;
+    const int A = p.obs_count;
+    // ---- pass 1
 #pragma unroll 1
-    for (int a = 0; a < p.obs_count; ++a) {
+    for (int a = 0; a < A; ++a) {
         const uint32_t axy = TXY(p.P + a);
         const int ax = xy_x(axy) - half, ay = xy_y(axy) - half;
         int32_t* o = obs + (size_t)a * p.obs_C * ww;
+        int r = 0, c = lane;
+        while (c >= w) { c -= w; ++r; }
 #pragma unroll 1
         for (int i = lane; i < ww; i += G) {
-            const int r = i / w, c = i - r * w;
             const int x = ax + c, y = ay + r;
-            CellInfo ci;
-            if ((unsigned)x >= (unsigned)p.W || (unsigned)y >= (unsigned)p.H) {
-                ci.label = ZS_LABEL_WALL; ci.life = 200; ci.weapon = 0; ci.agent = -1;
-            } else {
-                const int cell = y * p.W + x;
-                ci = cell_info<MPC, G, CV>(p, e, cell, GRID(cell));
-            }
-            if (p.obs_enc == ZS_OBS_SIMPLE) __stcs(o + i, encode_simple(ci));
+            const bool inb = (unsigned)x < (unsigned)p.W && (unsigned)y < (unsigned)p.H;
+            const int cell = inb ? y * p.W + x : 0;
+            if (simple) __stcs(o + i, inb ? __ldg(p.tmpl_obs + cell) : 256 * ZS_LABEL_WALL + 15);
             else {
-                __stcs(o + i, channel_label(p, ci));
-                __stcs(o + ww + i, ci.life);
-                __stcs(o + 2 * ww + i, ci.weapon);
+                __stcs(o + i, inb ? __ldg(p.tmpl_obs + cell) : ZS_LABEL_WALL);
+                __stcs(o + ww + i, inb ? __ldg(p.tmpl_obs + p.cells + cell) : 200);
+                __stcs(o + 2 * ww + i, 0);
+            }
+            c += G;
+            while (c >= w) { c -= w; ++r; }
+        }
+    }
+    gsync<G, CV>(e);
+    // ---- pass 2: one item (box/wall entry, dead body, mobile thing) per lane, stored into every window that shows it
+    auto into_windows = [&](int cell, int v0, int v1, int v2) {
+        const int y = cell / p.W, x = cell - y * p.W;
+#pragma unroll 1
+        for (int a = 0; a < A; ++a) {
+            const uint32_t axy = TXY(p.P + a);
+            const int wx = x - (xy_x(axy) - half), wy = y - (xy_y(axy) - half);
+            if ((unsigned)wx < (unsigned)w && (unsigned)wy < (unsigned)w)
+                window_store(p, obs + (size_t)a * p.obs_C * ww, ww, wy * w + wx, v0, v1, v2);
+        }
+    };
+    if (e.flags & FL_DMG) {
+        const int n_spl = SPN;
+#pragma unroll 1
+        for (int i = lane; i < n_spl; i += G) {
+            const uint32_t wd = SPL(i);
+            const int cell = wd & 0xffffu, pay = wd >> 16;
+            if (pay == 0 && GRID(cell) != G_EMPTY) continue;  // gone: whatever took the cell shows itself
+            if (simple) into_windows(cell, pay, 0, 0);
+            else into_windows(cell, pay >> 12, (int)((uint32_t)pay << 20) >> 20, 0);
+        }
+    }
+    const int body0 = simple ? 256 * ZS_LABEL_DEAD_BODY : ZS_LABEL_DEAD_BODY;
+    if (!(e.flags & FL_DEAD_OVER)) {
+        const int n_dead = DBL(0);
+#pragma unroll 1
+        for (int i = lane; i < n_dead; i += G) {
+            const int c = DBL(1 + i);
+            if (GRID(c) == G_DEAD) into_windows(c, body0, 0, 0);
+        }
+    } else {
+#pragma unroll 1
+        for (int wd = lane; wd < p.dead_words; wd += G) {
+            uint32_t bits = DEADW(wd);
+            while (bits) {
+                const int c = wd * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (GRID(c) == G_DEAD) into_windows(c, body0, 0, 0);
             }
         }
+    }
+#pragma unroll 1
+    for (int s = lane; s < p.M; s += G) {
+        const int m = TM(s);
+        if (!(m & 0x80)) continue;
+        const CellInfo ci = thing_info(p, s, TL(s), m);
+        const uint32_t xy = TXY(s);
+        const int cell = xy_y(xy) * p.W + xy_x(xy);
+        if (simple) into_windows(cell, encode_simple(ci), 0, 0);
+        else into_windows(cell, channel_label(p, ci), ci.life, ci.weapon);
     }
 }
 
