@@ -142,9 +142,10 @@ template <int MPC>
 struct alignas(16) EnvS {
     static constexpr int GEN = MPC > 32 ? MPC : 1;  // arrays only the general (more slots than lanes) kernels use
     unsigned long long act[MPC];            // the step's action list (packed, see pack_action)
+    unsigned long long act2[GEN];           // general kernels: the list in shuffled order (act holds it in actor order)
     uint32_t txy[MPC];                      // x | y << 16 (int16 each)
     uint32_t bk[MPC];                       // per step: closest-player key of a zombie / heal_closest agent
-    uint32_t draws[3 * MPC + 4];            // per step: the draws, 4 per Philox block
+    alignas(16) uint32_t draws[3 * MPC + 4];  // per step: the draws, 4 per Philox block (stored as uint4)
     uint32_t zb[GEN < ZS_NP_MAX ? GEN : ZS_NP_MAX];  // per step: closest-zombie key of a player slot
     int32_t scal[8];                        // scalar hand-off around out-of-line functions
     int32_t acts[3 * (GEN < ZS_MAX_AGENTS ? GEN : ZS_MAX_AGENTS) + 1];  // agent actions of the step (type, dx, dy)
@@ -161,6 +162,8 @@ struct alignas(16) EnvS {
     uint8_t sor[MPC];                       // slot of a rank
     uint8_t mvq[MPC];                       // order of this step's successful moves, RK_NONE if none
     uint8_t dtype[MPC];
+    uint8_t mvp[GEN];                       // general kernels: list position of the slot's successful move, RK_NONE if none
+    uint8_t mpos[GEN];                      // general kernels: list position of the slot's (valid) move action, RK_NONE if none
     alignas(16) uint8_t fyj[MPC];           // per step: Fisher-Yates partner of every list position (one-lane-per-slot kernels)
 };
 

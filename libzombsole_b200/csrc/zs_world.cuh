@@ -631,74 +631,195 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     for (int i = 1 + e.gl; i < L; i += G) DTYPE(i) = (uint8_t)below(DRAWS(nd + (L - 1 - i)), i + 1);
     gsync<G, CV>(e);
 
-    // ---- random.shuffle (core.py:76) and execute_actions (core.py:103-119): order-dependent by definition, run by
-    // the group's lane 0 on shared memory
+    // ---- random.shuffle (core.py:76): the swaps are a fixed sequence once the partners are known; every lane follows the
+    // list positions it owns (lane, lane + 32, ...) through them in registers, then the words move to their places
     int k = nd + (L > 1 ? L - 1 : 0);
     int nmv = 0;
-    if (lane == 0) {
+    {
+        constexpr int R = MPC / 32;
+        int fp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) fp[r] = lane + 32 * r;
 #pragma unroll 1
         for (int i = L - 1; i >= 1; --i) {
             const int j = DTYPE(i);
-            const unsigned long long tmp = ACT(i); ACT(i) = ACT(j); ACT(j) = tmp;
+#pragma unroll
+            for (int r = 0; r < R; ++r) fp[r] = fp[r] == i ? j : (fp[r] == j ? i : fp[r]);
         }
-        int n_touched = 0, fl = e.flags, deaths = e.deaths;
 #pragma unroll 1
-        for (int i = 0; i < L; ++i) {
-            const unsigned long long pk = ACT(i);
-            const uint32_t lo32 = (uint32_t)pk, hi32 = (uint32_t)(pk >> 32);
-            const int kind = lo32 & 7;
-            if (kind == X_NOP) continue;
-            if (kind == X_MOVE) {  // World.thing_move (core.py:140-166)
-                const int c = lo32 >> 16;
-                if (!g_is_thing(GRID(c))) {
-                    const int actor = (lo32 >> 3) & 0xff;
-                    GRID(hi32 & 0xffffu) = (lo32 & 0x800u) ? G_DEAD : G_EMPTY;
-                    GRID(c) = (uint8_t)(actor + 1);
-                    TXY(actor) = BK(actor);
-                    MVQ(actor) = (uint8_t)nmv++;  // things[dest] = thing; del things[old]: goes last in the dict
-                }
-                continue;
-            }
-            const int dlo = (lo32 >> 18) & 127, dn = (lo32 >> 25) & 63;
-            if (kind <= X_HEAL_M) {  // mobile target: distance between CURRENT positions (core.py:176,194)
-                const int a = (lo32 >> 3) & 0xff;
-                const uint32_t gxy = TXY(a);
-                if (dist2(xy_x(hi32), xy_y(hi32), xy_x(gxy), xy_y(gxy)) > (int)((lo32 >> 11) & 127)) continue;
-                const int amount = dlo + below(DRAWS(k++), dn);
-                if (kind == X_ATTACK_M) TL(a) = (int16_t)(TL(a) - amount);
-                else { const int nl = TL(a) + amount; TL(a) = (int16_t)(nl < 100 ? nl : 100); }
-            } else {
-                const int a = hi32 & 0xffffu;
-                const int amount = dlo + below(DRAWS(k++), dn);
-                if (kind == X_ATTACK_S) SL(a) = (int16_t)(SL(a) - amount);
-                else {
-                    const int mx = dlo == 1 ? 10 : 200;  // MAX_LIFE // 10 is 1 for a Box, 20 for a Wall
-                    const int nl = SL(a) + amount;
-                    SL(a) = (int16_t)(nl < mx ? nl : mx);
-                }
-                LIST(n_touched++) = (uint16_t)a;
-                fl |= FL_SL_DIRTY;
+        for (int s = lane; s < p.Mp; s += G) { S.mpos[s] = RK_NONE; S.mvp[s] = RK_NONE; }
+        gsync<G, CV>(e);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int pre = lane + 32 * r;
+            if (pre < L) {
+                const unsigned long long w = ACT(pre);
+                S.act2[fp[r]] = w;
+                if (((uint32_t)w & 7u) == X_MOVE) S.mpos[((uint32_t)w >> 3) & 0xffu] = (uint8_t)fp[r];
             }
         }
-        // the boxes/walls hit this step: their patch-list entries, and clean_dead_things (core.py:121-138) for the
-        // ones destroyed now (on the first step of a world the clean phase below covers them)
-#pragma unroll 1
-        for (int i = 0; i < n_touched; ++i) {
-            const int si = LIST(i);
-            const int cell = __ldg(p.static_cell + si);
-            const int life = SL(si);
-            const bool fresh = fl & FL_FRESH;
-            if (life <= 0 && !fresh && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
-            spl_update_one<MPC, G, CV>(p, e, si, cell, life, life > 0 || fresh);
-        }
-        if (SPN) fl |= FL_DMG;
-        e.flags = fl; e.deaths = deaths;
+        gsync<G, CV>(e);
     }
-    k = gbcast<G, CV>(e, k, 0);
-    nmv = gbcast<G, CV>(e, nmv, 0);
-    e.deaths = gbcast<G, CV>(e, e.deaths, 0);
-    e.flags = gbcast<G, CV>(e, e.flags, 0);
-    gsync<G, CV>(e);
+    // ---- execute_actions (core.py:103-119) in chunks of 32 list positions: within a chunk the resolution of
+    // world_step_one (first mover per free destination by match.any, hits grouped per target, ballot-prefix draw
+    // indices); a chunk sees the world the chunks before it left.  A move into a cell whose occupant moves earlier in
+    // the SAME chunk sends that chunk through the sequential loop.
+    const unsigned below_l = (1u << lane) - 1u;
+#pragma unroll 1
+    for (int base = 0; base < L; base += 32) {
+        const int q = base + lane;  // list position
+        const unsigned long long pk = q < L ? S.act2[q] : 0ull;
+        const uint32_t lo32 = (uint32_t)pk, hi32 = (uint32_t)(pk >> 32);
+        int kind = lo32 & 7;
+        const int who = (lo32 >> 3) & 0xff;  // the actor of a move, the mobile target of a hit
+        const int c = lo32 >> 16;
+        const int g0 = kind == X_MOVE ? (int)GRID(c) : G_STATIC;
+        bool need_seq = false;
+        if (kind == X_MOVE && g0 >= 1 && g0 <= G_MAX_SLOT) { const int mp = S.mpos[g0 - 1]; need_seq = mp >= base && mp < q; }
+        if (gany<G, CV>(e, need_seq)) {
+            if (lane == 0) {  // this chunk in list order on shared memory
+                int fl = e.flags, deaths = e.deaths, n_touched = 0;
+                const int end = base + 32 < L ? base + 32 : L;
+#pragma unroll 1
+                for (int i = base; i < end; ++i) {
+                    const unsigned long long w = S.act2[i];
+                    const uint32_t l32 = (uint32_t)w, h32 = (uint32_t)(w >> 32);
+                    const int kd = l32 & 7;
+                    if (kd == X_NOP) continue;
+                    if (kd == X_MOVE) {  // World.thing_move (core.py:140-166)
+                        const int cc = l32 >> 16;
+                        if (!g_is_thing(GRID(cc))) {
+                            const int actor = (l32 >> 3) & 0xff;
+                            GRID(h32 & 0xffffu) = (l32 & 0x800u) ? G_DEAD : G_EMPTY;
+                            GRID(cc) = (uint8_t)(actor + 1);
+                            TXY(actor) = BK(actor);
+                            S.mvp[actor] = (uint8_t)i;
+                            MVQ(actor) = (uint8_t)nmv++;  // things[dest] = thing; del things[old]: goes last in the dict
+                        }
+                        continue;
+                    }
+                    const int dlo = (l32 >> 18) & 127, dn = (l32 >> 25) & 63;
+                    if (kd <= X_HEAL_M) {  // mobile target: distance between CURRENT positions (core.py:176,194)
+                        const int a = (l32 >> 3) & 0xff;
+                        const uint32_t gxy = TXY(a);
+                        if (dist2(xy_x(h32), xy_y(h32), xy_x(gxy), xy_y(gxy)) > (int)((l32 >> 11) & 127)) continue;
+                        const int amount = dlo + below(DRAWS(k++), dn);
+                        if (kd == X_ATTACK_M) TL(a) = (int16_t)(TL(a) - amount);
+                        else { const int nl = TL(a) + amount; TL(a) = (int16_t)(nl < 100 ? nl : 100); }
+                    } else {
+                        const int a = h32 & 0xffffu;
+                        const int amount = dlo + below(DRAWS(k++), dn);
+                        if (kd == X_ATTACK_S) SL(a) = (int16_t)(SL(a) - amount);
+                        else {
+                            const int mx = __ldg(p.static_max + a);
+                            const int nl = SL(a) + amount;
+                            SL(a) = (int16_t)(nl < mx ? nl : mx);
+                        }
+                        LIST(n_touched++) = (uint16_t)a;
+                        fl |= FL_SL_DIRTY;
+                    }
+                }
+                // the boxes/walls hit in this chunk: their patch-list entries, and clean_dead_things (core.py:121-138) for
+                // the ones destroyed now (on the first step of a world the clean phase below covers them)
+#pragma unroll 1
+                for (int i = 0; i < n_touched; ++i) {
+                    const int si = LIST(i);
+                    const int cell = __ldg(p.static_cell + si);
+                    const int life = SL(si);
+                    const bool fresh = fl & FL_FRESH;
+                    if (life <= 0 && !fresh && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
+                    spl_update_one<MPC, G, CV>(p, e, si, cell, life, life > 0 || fresh);
+                }
+                if (SPN) fl |= FL_DMG;
+                e.flags = fl; e.deaths = deaths;
+            }
+            k = gbcast<G, CV>(e, k, 0);
+            nmv = gbcast<G, CV>(e, nmv, 0);
+            e.deaths = gbcast<G, CV>(e, e.deaths, 0);
+            e.flags = gbcast<G, CV>(e, e.flags, 0);
+            gsync<G, CV>(e);
+            continue;
+        }
+        // ---- moves (World.thing_move, core.py:140-166)
+        const bool dest_free = kind == X_MOVE && !g_is_thing(g0);
+        const unsigned want = gmatch<G, CV>(e, dest_free ? (uint32_t)c : 0x10000u);
+        const bool success = dest_free && !(want & below_l);
+        const unsigned succ_m = gballot<G, CV>(e, success);
+        if (success) {
+            GRID(hi32 & 0xffffu) = (lo32 & 0x800u) ? G_DEAD : G_EMPTY;
+            GRID(c) = (uint8_t)(who + 1);
+            S.mvp[who] = (uint8_t)q;
+            MVQ(who) = (uint8_t)(nmv + __popc(succ_m & below_l));  // things[dest] = thing; del things[old]: goes last in the dict
+        }
+        nmv += __popc(succ_m);
+        gsync<G, CV>(e);
+        // ---- hits (World.thing_attack / thing_heal, core.py:168-208)
+        const bool on_static = kind >= X_ATTACK_S;
+        bool inrange = on_static;  // boxes/walls do not move: their range was checked when the word was built
+        if (kind == X_ATTACK_M || kind == X_HEAL_M) {  // distance between CURRENT positions (core.py:176,194)
+            uint32_t txy = TXY(who);
+            const int mp = S.mvp[who];
+            if (mp >= base && mp < q) txy = BK(who);  // (moves of earlier chunks are in TXY already)
+            inrange = dist2(xy_x(hi32), xy_y(hi32), xy_x(txy), xy_y(txy)) <= (int)((lo32 >> 11) & 127);
+        }
+        if (gany<G, CV>(e, inrange)) {
+            const unsigned hit_m = gballot<G, CV>(e, inrange);
+            const int si = hi32 & 0xffffu;
+            const bool heal = kind == X_HEAL_M || kind == X_HEAL_S;
+            if (inrange) {
+                const int amount = (int)((lo32 >> 18) & 127) + below(DRAWS(k + __popc(hit_m & below_l)), (int)((lo32 >> 25) & 63));
+                LIST(lane) = (uint16_t)(amount | (heal ? 0x8000 : 0));
+            }
+            k += __popc(hit_m);
+            const uint32_t tid = on_static ? 0x100u + (uint32_t)si : (uint32_t)who;
+            const unsigned grp = gmatch<G, CV>(e, inrange ? tid : 0x20000u);
+            const bool lead = inrange && !(grp & below_l);  // the first hit on a target applies all of them, in order
+            gsync<G, CV>(e);
+            int life = 0;
+            if (lead) {
+                life = on_static ? (int)SL(si) : (int)TL(who);
+                const int mx = on_static ? (int)__ldg(p.static_max + si) : 100;
+                unsigned bits = grp;
+                while (bits) {
+                    const int v = LIST(__ffs(bits) - 1);
+                    bits &= bits - 1;
+                    if (v & 0x8000) { life += v & 0x7fff; life = life < mx ? life : mx; }
+                    else life -= v;
+                }
+                if (on_static) SL(si) = (int16_t)life; else TL(who) = (int16_t)life;
+            }
+            const bool slead = lead && on_static;
+            if (gany<G, CV>(e, slead)) {
+                bool is_new = false, gone = false;
+                int cell = 0, pay = 0, idx = 0;
+                if (slead) {
+                    const int mx = __ldg(p.static_max + si);
+                    const bool fresh = e.flags & FL_FRESH;
+                    cell = __ldg(p.static_cell + si);
+                    gone = life <= 0 && !fresh && g_is_static(GRID(cell));
+                    if (gone) GRID(cell) = G_EMPTY;
+                    pay = static_payload(p, mx, life, life > 0 || fresh);
+                    idx = SIDX(si);
+                    is_new = idx == 0 && pay != static_payload(p, mx, mx, true);
+                }
+                e.deaths += __popc(gballot<G, CV>(e, gone));
+                e.flags |= FL_SL_DIRTY;
+                const unsigned new_m = gballot<G, CV>(e, is_new);
+                const int n0 = SPN;
+                gsync<G, CV>(e);  // (everybody has read the count before lane 0 rewrites it)
+                if (is_new) { idx = n0 + __popc(new_m & below_l) + 1; SIDX(si) = (uint8_t)(idx < SIDX_FAR ? idx : SIDX_FAR); }
+                else if (idx == SIDX_FAR) idx = spl_find_far<MPC, G, CV>(p, e, cell);
+                if (slead && idx) SPL(idx - 1) = (uint32_t)cell | ((uint32_t)pay << 16);
+                if (new_m) {
+                    if (lane == 0) SPN = (uint16_t)(n0 + __popc(new_m));
+                    e.flags |= FL_DMG;
+                }
+            }
+        }
+        gsync<G, CV>(e);
+        if (success) TXY(who) = BK(who);  // the chunk's movers arrive (the hits above needed both positions)
+        gsync<G, CV>(e);
+    }
 
     // ---- clean_dead_things (core.py:121-138)
     int nd_all = 0, nd_z = 0;
