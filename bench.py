@@ -368,6 +368,9 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION and above: stdout carries ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
