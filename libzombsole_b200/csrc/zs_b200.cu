@@ -306,8 +306,11 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
 #endif
 }
 
-template <int MODE, int MPC, int G, bool FAST>
-__global__ void __launch_bounds__(ZS_WPC * 32, G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
+// LOWOCC: a batch that fits the chip at 16 warps per SM is latency-bound — the kernel for it is compiled for 4 resident
+// CTAs (128 registers, nothing spilled or re-derived in the step loop: +10 % at 4,096 envs); larger batches are
+// issue-bound and want the occupancy (80 / 72 registers).
+template <int MODE, int MPC, int G, bool FAST, bool LOWOCC>
+__global__ void __launch_bounds__(ZS_WPC * 32, LOWOCC ? ZS_MIN_CTAS_LOWOCC : (G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS)) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     ZS_CONSTS;
     // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
     constexpr bool CV = MODE == MODE_STEP;
@@ -418,6 +421,7 @@ struct ZsHandle {
     int envs_per_cta;
     int lanes_per_env;
     int warps_per_cta;
+    int low_occ;
     int smem_bytes;
 };
 
@@ -502,30 +506,35 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     const bool fast = MODE == MODE_STEP && pp.mpc <= 32 && pp.A == 1 && !pp.obs_per_agent && pp.minimum_zombies == 0 &&
                       pp.obs_scope == ZS_OBS_WORLD && io.actions && io.fmt == ZS_ACTIONS_DISCRETE && io.obs && io.reward &&
                       io.terminated && io.truncated && !io.draws && !io.agent_mask;
+    const bool low = MODE == MODE_STEP && h->low_occ;
+#define ZS_LAUNCH(MPC_, G_, F_, L_) zs_sim_kernel<MODE, MPC_, G_, (F_) && MODE == MODE_STEP, (L_) && MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io)
+#define ZS_LAUNCH_ONE(MPC_, G_)                                  \
+    do {                                                         \
+        if (fast) { if (low) ZS_LAUNCH(MPC_, G_, true, true); else ZS_LAUNCH(MPC_, G_, true, false); }   \
+        else { if (low) ZS_LAUNCH(MPC_, G_, false, true); else ZS_LAUNCH(MPC_, G_, false, false); }      \
+    } while (0)
     switch (pp.mpc) {
         case 16:
-            if (h->lanes_per_env == 16) {
-                if (fast) zs_sim_kernel<MODE, 16, 16, MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io);
-                else zs_sim_kernel<MODE, 16, 16, false><<<grid, block, h->smem_bytes, st>>>(pp, io);
-            } else {
-                if (fast) zs_sim_kernel<MODE, 16, 32, MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io);
-                else zs_sim_kernel<MODE, 16, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io);
-            }
+            if (h->lanes_per_env == 16) ZS_LAUNCH_ONE(16, 16); else ZS_LAUNCH_ONE(16, 32);
             break;
-        case 32:
-            if (fast) zs_sim_kernel<MODE, 32, 32, MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io);
-            else zs_sim_kernel<MODE, 32, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io);
-            break;
-        case 128: zs_sim_kernel<MODE, 128, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
-        default: zs_sim_kernel<MODE, 256, 32, false><<<grid, block, h->smem_bytes, st>>>(pp, io); break;
+        case 32: ZS_LAUNCH_ONE(32, 32); break;
+        case 128: ZS_LAUNCH(128, 32, false, false); break;
+        default: ZS_LAUNCH(256, 32, false, false); break;
     }
+#undef ZS_LAUNCH_ONE
+#undef ZS_LAUNCH
 }
 template <int MPC, int G>
 static cudaError_t set_smem_attr_for(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess && MPC <= 32) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false, false>, attr, bytes);
+    if (MPC <= 32) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32), false>, attr, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false, (MPC <= 32)>, attr, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32), (MPC <= 32)>, attr, bytes);
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, false, false>, attr, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, false, false>, attr, bytes);
     return e;
 }
 static int set_smem_attr(int mpc, int lanes, int bytes) {
@@ -679,6 +688,9 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     if ((p.N + ZS_WPC * (32 / h->lanes_per_env) - 1) / (ZS_WPC * (32 / h->lanes_per_env)) < prop.multiProcessorCount * 5) h->warps_per_cta = 2;
     if (const char* force = getenv("ZS_WARPS_PER_CTA")) { const int v = atoi(force); if (v == 1 || v == 2 || v == 4) h->warps_per_cta = v; }
     h->envs_per_cta = h->warps_per_cta * (32 / h->lanes_per_env);
+    // the 128-register kernel when all the batch's warps are resident at 16 warps per SM (zs_sim_kernel: LOWOCC)
+    h->low_occ = p.mpc <= 32 && (p.N + (32 / h->lanes_per_env) - 1) / (32 / h->lanes_per_env) <= prop.multiProcessorCount * ZS_MIN_CTAS_LOWOCC * ZS_WPC;
+    if (const char* force = getenv("ZS_LOW_OCC")) h->low_occ = atoi(force) != 0 && p.mpc <= 32;
     h->smem_bytes = p.smem_per_env * h->envs_per_cta;
     p.tmpl_smem_off = -1; p.tmpl_planes = 0;
     if (p.obs_scope == ZS_OBS_WORLD && (p.cells & 3) == 0) {
