@@ -306,11 +306,12 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
 #endif
 }
 
-// LOWOCC: a batch that fits the chip at 16 warps per SM is latency-bound — the kernel for it is compiled for 4 resident
-// CTAs (128 registers, nothing spilled or re-derived in the step loop: +10 % at 4,096 envs); larger batches are
-// issue-bound and want the occupancy (80 / 72 registers).
-template <int MODE, int MPC, int G, bool FAST, bool LOWOCC>
-__global__ void __launch_bounds__(ZS_WPC * 32, LOWOCC ? ZS_MIN_CTAS_LOWOCC : (G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS)) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
+// OCC = resident 4-warp CTAs per SM the kernel is compiled for.  A rollout keeps an env in its CTA for all K steps, so a
+// batch runs in ceil(warps / resident warps) rounds: zs_create picks the OCC with the fewest rounds, and among those the
+// one with the most registers — 4 (128 registers, nothing spilled or re-derived in the step loop: +10 % at 4,096 envs,
+// which are latency-bound), 6 (80) or 7 (72); large batches are issue-bound and take 6 (two envs per warp) or 7.
+template <int MODE, int MPC, int G, bool FAST, int OCC>
+__global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     ZS_CONSTS;
     // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
     constexpr bool CV = MODE == MODE_STEP;
@@ -421,7 +422,7 @@ struct ZsHandle {
     int envs_per_cta;
     int lanes_per_env;
     int warps_per_cta;
-    int low_occ;
+    int occ;
     int smem_bytes;
 };
 
@@ -506,36 +507,62 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     const bool fast = MODE == MODE_STEP && pp.mpc <= 32 && pp.A == 1 && !pp.obs_per_agent && pp.minimum_zombies == 0 &&
                       pp.obs_scope == ZS_OBS_WORLD && io.actions && io.fmt == ZS_ACTIONS_DISCRETE && io.obs && io.reward &&
                       io.terminated && io.truncated && !io.draws && !io.agent_mask;
-    const bool low = MODE == MODE_STEP && h->low_occ;
-#define ZS_LAUNCH(MPC_, G_, F_, L_) zs_sim_kernel<MODE, MPC_, G_, (F_) && MODE == MODE_STEP, (L_) && MODE == MODE_STEP><<<grid, block, h->smem_bytes, st>>>(pp, io)
-#define ZS_LAUNCH_ONE(MPC_, G_)                                  \
-    do {                                                         \
-        if (fast) { if (low) ZS_LAUNCH(MPC_, G_, true, true); else ZS_LAUNCH(MPC_, G_, true, false); }   \
-        else { if (low) ZS_LAUNCH(MPC_, G_, false, true); else ZS_LAUNCH(MPC_, G_, false, false); }      \
-    } while (0)
+    const int occ = MODE == MODE_STEP ? h->occ : ZS_MIN_CTAS;
+#define ZS_LAUNCH(MPC_, G_, F_, O_) zs_sim_kernel<MODE, MPC_, G_, (F_) && MODE == MODE_STEP, MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS><<<grid, block, h->smem_bytes, st>>>(pp, io)
+#define ZS_LAUNCH_F(MPC_, G_, O_) do { if (fast) ZS_LAUNCH(MPC_, G_, true, O_); else ZS_LAUNCH(MPC_, G_, false, O_); } while (0)
     switch (pp.mpc) {
         case 16:
-            if (h->lanes_per_env == 16) ZS_LAUNCH_ONE(16, 16); else ZS_LAUNCH_ONE(16, 32);
+            if (h->lanes_per_env == 16) {
+                if (occ == ZS_MIN_CTAS_LOWOCC) ZS_LAUNCH_F(16, 16, ZS_MIN_CTAS_LOWOCC);
+                else if (occ == ZS_MIN_CTAS_G16) ZS_LAUNCH_F(16, 16, ZS_MIN_CTAS_G16);
+                else ZS_LAUNCH_F(16, 16, ZS_MIN_CTAS);
+            } else {
+                if (occ == ZS_MIN_CTAS_LOWOCC) ZS_LAUNCH_F(16, 32, ZS_MIN_CTAS_LOWOCC); else ZS_LAUNCH_F(16, 32, ZS_MIN_CTAS);
+            }
             break;
-        case 32: ZS_LAUNCH_ONE(32, 32); break;
-        case 128: ZS_LAUNCH(128, 32, false, false); break;
-        default: ZS_LAUNCH(256, 32, false, false); break;
+        case 32:
+            if (occ == ZS_MIN_CTAS_LOWOCC) ZS_LAUNCH_F(32, 32, ZS_MIN_CTAS_LOWOCC); else ZS_LAUNCH_F(32, 32, ZS_MIN_CTAS);
+            break;
+        case 128: ZS_LAUNCH(128, 32, false, ZS_MIN_CTAS); break;
+        default: ZS_LAUNCH(256, 32, false, ZS_MIN_CTAS); break;
     }
-#undef ZS_LAUNCH_ONE
+#undef ZS_LAUNCH_F
 #undef ZS_LAUNCH
+}
+template <int MPC, int G, int OCC>
+static cudaError_t set_smem_attr_step(int bytes) {
+    const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false, OCC>, attr, bytes);
+    if (e == cudaSuccess && MPC <= 32) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32), OCC>, attr, bytes);
+    return e;
 }
 template <int MPC, int G>
 static cudaError_t set_smem_attr_for(int bytes) {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false, false>, attr, bytes);
-    if (MPC <= 32) {
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32), false>, attr, bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false, (MPC <= 32)>, attr, bytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32), (MPC <= 32)>, attr, bytes);
-    }
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, false, false>, attr, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, false, false>, attr, bytes);
+    cudaError_t e = set_smem_attr_step<MPC, G, ZS_MIN_CTAS>(bytes);
+    if (e == cudaSuccess && MPC <= 32) e = set_smem_attr_step<MPC, G, (MPC <= 32 ? ZS_MIN_CTAS_LOWOCC : ZS_MIN_CTAS)>(bytes);
+    if (e == cudaSuccess && G == 16) e = set_smem_attr_step<MPC, G, (G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS)>(bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, false, ZS_MIN_CTAS>, attr, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, false, ZS_MIN_CTAS>, attr, bytes);
     return e;
+}
+// resident warps per SM of the step kernel compiled for OCC CTAs, at this block size and shared-memory footprint
+template <int MPC, int G, int OCC>
+static int resident_warps_of(int block_threads, int smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zs_sim_kernel<MODE_STEP, MPC, G, false, OCC>, block_threads, smem) != cudaSuccess) n = 0;
+    return n * (block_threads / 32);
+}
+static int resident_warps(int mpc, int lanes, int occ, int block_threads, int smem) {
+    if (mpc == 16 && lanes == 16)
+        return occ == ZS_MIN_CTAS_LOWOCC ? resident_warps_of<16, 16, ZS_MIN_CTAS_LOWOCC>(block_threads, smem)
+             : occ == ZS_MIN_CTAS_G16 ? resident_warps_of<16, 16, ZS_MIN_CTAS_G16>(block_threads, smem)
+                                      : resident_warps_of<16, 16, ZS_MIN_CTAS>(block_threads, smem);
+    if (mpc == 16)
+        return occ == ZS_MIN_CTAS_LOWOCC ? resident_warps_of<16, 32, ZS_MIN_CTAS_LOWOCC>(block_threads, smem)
+                                         : resident_warps_of<16, 32, ZS_MIN_CTAS>(block_threads, smem);
+    return occ == ZS_MIN_CTAS_LOWOCC ? resident_warps_of<32, 32, ZS_MIN_CTAS_LOWOCC>(block_threads, smem)
+                                     : resident_warps_of<32, 32, ZS_MIN_CTAS>(block_threads, smem);
 }
 static int set_smem_attr(int mpc, int lanes, int bytes) {
     cudaError_t e;
@@ -688,9 +715,6 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     if ((p.N + ZS_WPC * (32 / h->lanes_per_env) - 1) / (ZS_WPC * (32 / h->lanes_per_env)) < prop.multiProcessorCount * 5) h->warps_per_cta = 2;
     if (const char* force = getenv("ZS_WARPS_PER_CTA")) { const int v = atoi(force); if (v == 1 || v == 2 || v == 4) h->warps_per_cta = v; }
     h->envs_per_cta = h->warps_per_cta * (32 / h->lanes_per_env);
-    // the 128-register kernel when all the batch's warps are resident at 16 warps per SM (zs_sim_kernel: LOWOCC)
-    h->low_occ = p.mpc <= 32 && (p.N + (32 / h->lanes_per_env) - 1) / (32 / h->lanes_per_env) <= prop.multiProcessorCount * ZS_MIN_CTAS_LOWOCC * ZS_WPC;
-    if (const char* force = getenv("ZS_LOW_OCC")) h->low_occ = atoi(force) != 0 && p.mpc <= 32;
     h->smem_bytes = p.smem_per_env * h->envs_per_cta;
     p.tmpl_smem_off = -1; p.tmpl_planes = 0;
     if (p.obs_scope == ZS_OBS_WORLD && (p.cells & 3) == 0) {
@@ -704,6 +728,30 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     }
     if (h->smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
     if (int rc2 = set_smem_attr(p.mpc, h->lanes_per_env, h->smem_bytes)) { zs_destroy(h); return rc2; }
+    // resident CTAs per SM the step kernel is compiled for (zs_sim_kernel: OCC): fewest rounds first, then most registers;
+    // batches of three rounds or more are issue-bound and take the occupancy
+    h->occ = ZS_MIN_CTAS;
+    if (p.mpc <= 32) {
+        const int epw = 32 / h->lanes_per_env;
+        const long long warps = ((long long)p.N + epw - 1) / epw;
+        const int cands16[3] = {ZS_MIN_CTAS_LOWOCC, ZS_MIN_CTAS_G16, ZS_MIN_CTAS}, cands32[2] = {ZS_MIN_CTAS_LOWOCC, ZS_MIN_CTAS};
+        const int* cands = h->lanes_per_env == 16 ? cands16 : cands32;
+        const int nc = h->lanes_per_env == 16 ? 3 : 2;
+        long long rounds[3], best = 0;
+        for (int i = 0; i < nc; ++i) {
+            long long cap = (long long)resident_warps(p.mpc, h->lanes_per_env, cands[i], h->warps_per_cta * 32, h->smem_bytes) * prop.multiProcessorCount;
+            if (cap < 1) cap = 1;
+            rounds[i] = (warps + cap - 1) / cap;
+            if (i == 0 || rounds[i] < best) best = rounds[i];
+        }
+        if (best >= 3) h->occ = h->lanes_per_env == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS;
+        else for (int i = 0; i < nc; ++i) if (rounds[i] == best) { h->occ = cands[i]; break; }
+        if (const char* force = getenv("ZS_OCC")) {
+            const int v = atoi(force);
+            if (v == ZS_MIN_CTAS_LOWOCC || v == ZS_MIN_CTAS || (v == ZS_MIN_CTAS_G16 && h->lanes_per_env == 16)) h->occ = v;
+        }
+    }
+
     *out = h;
     return 0;
 }
