@@ -651,6 +651,27 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     for (int i = 0; i < p.n_ps; ++i) { if (!cell_of(map->player_spawn_xy, i, &c)) { delete h; return fail("spawn outside the map"); } ps[i] = (uint16_t)c; }
     for (int i = 0; i < p.n_zs; ++i) { if (!cell_of(map->zombie_spawn_xy, i, &c)) { delete h; return fail("spawn outside the map"); } zs[i] = (uint16_t)c; }
     int rc = 0;
+    if (cfg->obs_scope == ZS_OBS_SURROUNDINGS) {
+        // the planes the windows are cut from (zs_obs.cuh: window_plane): out-of-bounds cells are a fresh Wall
+        const int sw = p.sw, half = sw >> 1, pw = p.W + sw - 1, ph = p.H + sw - 1;
+        if (sw < 1 || sw * sw > 65535) { delete h; return fail("surroundings width out of range"); }
+        const bool simple = cfg->obs_encoding == ZS_OBS_SIMPLE;
+        std::vector<uint16_t> pad((size_t)(simple ? 1 : 2) * pw * ph);
+        for (int y = 0; y < ph; ++y)
+            for (int x = 0; x < pw; ++x) {
+                const int mx = x - half, my = y - half;
+                const bool inb = mx >= 0 && mx < p.W && my >= 0 && my < p.H;
+                const size_t at = (size_t)y * pw + x;
+                if (simple) pad[at] = (uint16_t)(inb ? tmpl_obs[my * p.W + mx] : 256 * ZS_LABEL_WALL + 15);
+                else {
+                    pad[at] = (uint16_t)(inb ? tmpl_obs[my * p.W + mx] : ZS_LABEL_WALL);
+                    pad[(size_t)pw * ph + at] = (uint16_t)(inb ? tmpl_obs[cells + my * p.W + mx] : 200);
+                }
+            }
+        p.pad_w = pw; p.pad_plane = pw * ph;
+        p.sw_magic = (uint32_t)((0x100000000ull + (unsigned)sw - 1) / (unsigned)sw);
+        rc |= upload(h, pad, &p.tmpl_pad);
+    }
     rc |= upload(h, cell_static, &p.cell_static); rc |= upload(h, static_cell, &p.static_cell);
     rc |= upload(h, static_max, &p.static_max); rc |= upload(h, static_label, &p.static_label);
     rc |= upload(h, tmpl_grid, &p.tmpl_grid); rc |= upload(h, tmpl_obs, &p.tmpl_obs);

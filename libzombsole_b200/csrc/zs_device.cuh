@@ -69,6 +69,9 @@ struct ZsParams {
     const uint8_t* static_label;   // [Sp]
     const uint8_t* tmpl_grid;      // [cells_pad] G_STATIC on box/wall cells, else 0
     const int32_t* tmpl_obs;       // [2][cells] world-scope observation of the pristine static layer
+    const uint16_t* tmpl_pad;      // surroundings scope: the same planes with a border of fresh Walls sw/2 cells wide,
+    int32_t pad_w, pad_plane;      // [1 or 2][H + sw - 1][pad_w = W + sw - 1]; pad_plane = elements per plane
+    uint32_t sw_magic;             // ceil(2^32 / sw): i / sw == umulhi(i, sw_magic) for i < 65536
     const uint32_t* objective_bits;// [dead_words]
     const uint16_t* ps_cells;      // [n_ps] player spawn cells, file order
     const uint16_t* zs_cells;      // [n_zs]

@@ -164,10 +164,47 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e
 
 // surroundings window (observation.py:99-119): rows = y, columns = x, centred on the agent's (possibly stale, if
 // dead) position; out-of-bounds cells are a fresh Wall (observation.py:43-44,64-65).  Like the world scope it is
-// written in two passes: the pristine layer of every window straight from the (L1-resident) template planes, then
+// written in two passes: the pristine layer of every window from the (L1-resident) padded template planes, then
 // the cells that differ — static patch list, dead bodies, mobile things — stored into the windows they fall in.
 // The occupancy grid says what is on top of a cell, so every patched cell has exactly one writer; one __syncwarp
 // orders the patches after pass 1.
+// One plane of one window, pristine layer: ww = sw*sw consecutive int32 whose first element is only 4-byte aligned
+// (a plane is 441 elements at the default width).  The elements up to the first 16-byte boundary and behind the last
+// one go out as one scalar store from a few lanes; the body is 128-bit stores, each lane gathering its four cells
+// from the padded template plane (uint16, out-of-bounds cells are the fresh Wall of observation.py:43-44,64-65, so
+// there is no bounds check): one division per store (multiply by the reciprocal of sw, exact for i < 65536), the
+// row wrap of the three following cells by compare.  src == nullptr: the plane is zero (weapons of the static layer).
+template <int G>
+__device__ __forceinline__ void window_plane(const ZsParams& p, int lane, int32_t* __restrict__ o, const uint16_t* __restrict__ src) {
+    const int w = p.sw, ww = w * w, skip = p.pad_w - w;
+    int head = (int)(((0u - (uint32_t)(uintptr_t)o) >> 2) & 3u);
+    if (head > ww) head = ww;
+    const int nb = (ww - head) >> 2, tail = ww - head - 4 * nb;
+    if (lane < head + tail) {
+        const int i = lane < head ? lane : ww - tail + (lane - head);
+        const int r = (int)__umulhi((uint32_t)i, p.sw_magic);
+        __stcs(o + i, src ? (int)__ldg(src + i + r * skip) : 0);
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(o + head);
+    if (src == nullptr) {
+#pragma unroll 2
+        for (int q = lane; q < nb; q += G) __stcs(o4 + q, make_uint4(0u, 0u, 0u, 0u));
+        return;
+    }
+#pragma unroll 2
+    for (int q = lane; q < nb; q += G) {
+        const int i0 = head + 4 * q;
+        const int r0 = (int)__umulhi((uint32_t)i0, p.sw_magic);
+        const int c0 = i0 - r0 * w;
+        const uint16_t* s0 = src + i0 + r0 * skip;  // == src + r0 * pad_w + c0
+        uint4 v;
+        v.x = __ldg(s0);
+        v.y = __ldg(s0 + 1 + (c0 + 1 >= w ? skip : 0));
+        v.z = __ldg(s0 + 2 + (c0 + 2 >= w ? skip : 0));
+        v.w = __ldg(s0 + 3 + (c0 + 3 >= w ? skip : 0));
+        __stcs(o4 + q, v);
+    }
+}
 __device__ __forceinline__ void window_store(const ZsParams& p, int32_t* o, int ww, int idx, int v0, int v1, int v2) {
     if (p.obs_enc == ZS_OBS_SIMPLE) o[idx] = v0;
     else { o[idx] = v0; o[ww + idx] = v1; o[2 * ww + idx] = v2; }
@@ -182,24 +219,11 @@ ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, En
 #pragma unroll 1
     for (int a = 0; a < A; ++a) {
         const uint32_t axy = TXY(p.P + a);
-        const int ax = xy_x(axy) - half, ay = xy_y(axy) - half;
+        // top-left corner of the window in the padded planes (the padding is `half` cells wide)
+        const uint16_t* src = p.tmpl_pad + xy_y(axy) * p.pad_w + xy_x(axy);
         int32_t* o = obs + (size_t)a * p.obs_C * ww;
-        int r = 0, c = lane;
-        while (c >= w) { c -= w; ++r; }
-#pragma unroll 1
-        for (int i = lane; i < ww; i += G) {
-            const int x = ax + c, y = ay + r;
-            const bool inb = (unsigned)x < (unsigned)p.W && (unsigned)y < (unsigned)p.H;
-            const int cell = inb ? y * p.W + x : 0;
-            if (simple) __stcs(o + i, inb ? __ldg(p.tmpl_obs + cell) : 256 * ZS_LABEL_WALL + 15);
-            else {
-                __stcs(o + i, inb ? __ldg(p.tmpl_obs + cell) : ZS_LABEL_WALL);
-                __stcs(o + ww + i, inb ? __ldg(p.tmpl_obs + p.cells + cell) : 200);
-                __stcs(o + 2 * ww + i, 0);
-            }
-            c += G;
-            while (c >= w) { c -= w; ++r; }
-        }
+        window_plane<G>(p, lane, o, src);
+        if (!simple) { window_plane<G>(p, lane, o + ww, src + p.pad_plane); window_plane<G>(p, lane, o + 2 * ww, nullptr); }
     }
     gsync<G, CV>(e);
     // ---- pass 2: one item (box/wall entry, dead body, mobile thing) per lane, stored into every window that shows it
