@@ -380,6 +380,18 @@ __global__ void zs_init_static_life_kernel(const __grid_constant__ ZsParams p) {
         p.SCAL[i * 8 + ZS_S_EPISODE] = -1;
 }
 
+// win_table (zs_obs.cuh: window_block): the pristine label (and life) planes of the window centred on every cell
+__global__ void zs_build_window_table_kernel(const __grid_constant__ ZsParams p, int32_t* table) {
+    const int ww = p.sw * p.sw;
+    for (int cell = blockIdx.x; cell < p.cells; cell += gridDim.x) {
+        const int y = cell / p.W, x = cell - y * p.W;
+        for (int i = threadIdx.x; i < p.win_ints; i += blockDim.x) {
+            const int pl = i / ww, k = i - pl * ww, r = k / p.sw, c = k - r * p.sw;
+            table[(size_t)cell * p.win_ints + i] = p.tmpl_pad[(size_t)pl * p.pad_plane + (y + r) * p.pad_w + x + c];
+        }
+    }
+}
+
 __global__ void zs_fill_actions_kernel(const __grid_constant__ ZsParams p, uint32_t step_index, int32_t* actions) {
     const int n = p.N * p.A;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -671,6 +683,17 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         p.pad_w = pw; p.pad_plane = pw * ph;
         p.sw_magic = (uint32_t)((0x100000000ull + (unsigned)sw - 1) / (unsigned)sw);
         rc |= upload(h, pad, &p.tmpl_pad);
+        // one pristine window block per cell, as long as the table stays a small part of the L2
+        p.win_ints = (simple ? 1 : 2) * sw * sw;
+        const size_t table_bytes = (size_t)cells * p.win_ints * sizeof(int32_t);
+        if (!rc && table_bytes <= (32u << 20) && !getenv("ZS_NO_WINDOW_TABLE")) {
+            void* d = nullptr;
+            if (cudaMalloc(&d, table_bytes) != cudaSuccess) { zs_destroy(h); return fail("out of device memory (window table)"); }
+            h->dev_allocs.push_back(d);
+            zs_build_window_table_kernel<<<cells < 1024 ? cells : 1024, 256>>>(p, (int32_t*)d);
+            if (cudaDeviceSynchronize() != cudaSuccess) { zs_destroy(h); return fail("window table build failed"); }
+            p.win_table = (const int32_t*)d;
+        }
     }
     rc |= upload(h, cell_static, &p.cell_static); rc |= upload(h, static_cell, &p.static_cell);
     rc |= upload(h, static_max, &p.static_max); rc |= upload(h, static_label, &p.static_label);

@@ -94,3 +94,16 @@ def test_cuda_matches_oracle_lockstep(name, N, T, mes):
 def test_cuda_matches_oracle_discrete_actions(name):
     errs = lockstep(pu.CONFIGS[name], 48, 100, seed=4242, discrete=True)
     assert not errs, "\n".join(errs[:3])
+
+
+SURROUNDINGS_CASES = ["gym_surroundings", "surroundings_channels", "c3_city_evac"]
+
+
+@pytest.mark.parametrize("name", SURROUNDINGS_CASES)
+def test_surroundings_without_window_table(name, monkeypatch):
+    """The surroundings observation has two pristine-layer paths: a straight copy from the per-cell window table
+    (the default, as long as the table is small) and windows cut from the wall-padded template planes.  The
+    other cases run the first; this one forces the second."""
+    monkeypatch.setenv("ZS_NO_WINDOW_TABLE", "1")
+    errs = lockstep(pu.CONFIGS[name], 24, 60, seed=5, base=1)
+    assert not errs, "\n".join(errs[:3])
