@@ -387,7 +387,7 @@ __global__ void zs_build_window_table_kernel(const __grid_constant__ ZsParams p,
         const int y = cell / p.W, x = cell - y * p.W;
         for (int i = threadIdx.x; i < p.win_ints; i += blockDim.x) {
             const int pl = i / ww, k = i - pl * ww, r = k / p.sw, c = k - r * p.sw;
-            table[(size_t)cell * p.win_ints + i] = p.tmpl_pad[(size_t)pl * p.pad_plane + (y + r) * p.pad_w + x + c];
+            table[(size_t)cell * p.win_pitch + i] = p.tmpl_pad[(size_t)pl * p.pad_plane + (y + r) * p.pad_w + x + c];
         }
     }
 }
@@ -685,7 +685,8 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         rc |= upload(h, pad, &p.tmpl_pad);
         // one pristine window block per cell, as long as the table stays a small part of the L2
         p.win_ints = (simple ? 1 : 2) * sw * sw;
-        const size_t table_bytes = (size_t)cells * p.win_ints * sizeof(int32_t);
+        p.win_pitch = round_up(p.win_ints, 32);
+        const size_t table_bytes = (size_t)cells * p.win_pitch * sizeof(int32_t);
         if (!rc && table_bytes <= (32u << 20) && !getenv("ZS_NO_WINDOW_TABLE")) {
             void* d = nullptr;
             if (cudaMalloc(&d, table_bytes) != cudaSuccess) { zs_destroy(h); return fail("out of device memory (window table)"); }

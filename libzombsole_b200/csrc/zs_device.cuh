@@ -72,8 +72,9 @@ struct ZsParams {
     const uint16_t* tmpl_pad;      // surroundings scope: the same planes with a border of fresh Walls sw/2 cells wide,
     int32_t pad_w, pad_plane;      // [1 or 2][H + sw - 1][pad_w = W + sw - 1]; pad_plane = elements per plane
     uint32_t sw_magic;             // ceil(2^32 / sw): i / sw == umulhi(i, sw_magic) for i < 65536
-    const int32_t* win_table;      // [cells][win_ints] pristine window planes (label / label+life) of an agent standing on
-    int32_t win_ints;              // the cell, laid out like the output (L2-resident; NULL when it would be too large)
+    const int32_t* win_table;      // [cells][win_pitch] pristine window planes (label / label+life; win_ints words) of an
+    int32_t win_ints, win_pitch;   // agent standing on the cell, laid out like the output; rows start on 128-byte
+                                   // boundaries (L2-resident; NULL when it would be too large)
     const uint32_t* objective_bits;// [dead_words]
     const uint16_t* ps_cells;      // [n_ps] player spawn cells, file order
     const uint16_t* zs_cells;      // [n_zs]

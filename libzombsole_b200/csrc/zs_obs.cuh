@@ -206,39 +206,23 @@ __device__ __forceinline__ void window_plane(const ZsParams& p, int lane, int32_
     }
 }
 // The pristine window block of one agent as a straight copy: win_table holds, for every cell an agent can stand on,
-// the n_copy = (1 or 2) * sw * sw int32 of its label (and life) planes exactly as they go out; the rest of the block
-// (the weapon plane) is zero.  Source and destination are both only 4-byte aligned, so a lane reads four consecutive
-// words (one address, immediate offsets) and writes one 128-bit store; the few elements in front of the first and
-// behind the last 16-byte boundary of the block go out as one scalar store from a few lanes.
+// the n_copy = (1 or 2) * sw * sw int32 of its label (and life) planes exactly as they go out (rows of the table start
+// on 128-byte boundaries); the rest of the block (the weapon plane) is zero.  A block in the output is only 4-byte
+// aligned, so the copy is word by word with consecutive lanes on consecutive words: every load is one aligned
+// 128-byte line from the L2, every store at most two — cheaper in the L1 than wider accesses that straddle lines.
+// Eight loads per lane are issued back to back.
 template <int G>
 __device__ __forceinline__ void window_block(int lane, int32_t* __restrict__ o, const int32_t* __restrict__ src, int n_copy, int n_all) {
-    int head = (int)(((0u - (uint32_t)(uintptr_t)o) >> 2) & 3u);
-    if (head > n_all) head = n_all;
-    const int nb = (n_all - head) >> 2, tail = n_all - head - 4 * nb;
-    if (lane < head + tail) {
-        const int i = lane < head ? lane : n_all - tail + (lane - head);
-        __stcs(o + i, i < n_copy ? __ldg(src + i) : 0);
+#pragma unroll 1
+    for (int i0 = lane; i0 < n_copy; i0 += 8 * G) {
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (i0 + k * G < n_copy) v[k] = __ldg(src + i0 + k * G);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (i0 + k * G < n_copy) __stcs(o + i0 + k * G, v[k]);
     }
-    uint4* o4 = reinterpret_cast<uint4*>(o + head);
-    const int32_t* s = src + head;
-    const int qc = n_copy > head ? (n_copy - head) >> 2 : 0;  // 128-bit words that lie entirely inside the copied planes
 #pragma unroll 4
-    for (int q = lane; q < qc; q += G) {
-        const int32_t* sq = s + 4 * q;
-        uint4 v;
-        v.x = (uint32_t)__ldg(sq); v.y = (uint32_t)__ldg(sq + 1); v.z = (uint32_t)__ldg(sq + 2); v.w = (uint32_t)__ldg(sq + 3);
-        __stcs(o4 + q, v);
-    }
-#pragma unroll 2
-    for (int q = qc + lane; q < nb; q += G) {  // the word that straddles the end of the planes, then zeros
-        const int i0 = head + 4 * q;
-        uint4 v;
-        v.x = i0 < n_copy ? (uint32_t)__ldg(src + i0) : 0u;
-        v.y = i0 + 1 < n_copy ? (uint32_t)__ldg(src + i0 + 1) : 0u;
-        v.z = i0 + 2 < n_copy ? (uint32_t)__ldg(src + i0 + 2) : 0u;
-        v.w = i0 + 3 < n_copy ? (uint32_t)__ldg(src + i0 + 3) : 0u;
-        __stcs(o4 + q, v);
-    }
+    for (int i = n_copy + lane; i < n_all; i += G) __stcs(o + i, 0);
 }
 __device__ __forceinline__ void window_store(const ZsParams& p, int32_t* o, int ww, int idx, int v0, int v1, int v2) {
     if (p.obs_enc == ZS_OBS_SIMPLE) o[idx] = v0;
@@ -256,7 +240,7 @@ ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, En
         const uint32_t axy = TXY(p.P + a);
         int32_t* o = obs + (size_t)a * p.obs_C * ww;
         if (p.win_table) {
-            window_block<G>(lane, o, p.win_table + (size_t)(xy_y(axy) * p.W + xy_x(axy)) * p.win_ints, p.win_ints, p.obs_C * ww);
+            window_block<G>(lane, o, p.win_table + (size_t)(xy_y(axy) * p.W + xy_x(axy)) * p.win_pitch, p.win_ints, p.obs_C * ww);
             continue;
         }
         // top-left corner of the window in the padded planes (the padding is `half` cells wide)
