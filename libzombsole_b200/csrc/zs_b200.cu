@@ -713,7 +713,10 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     int off = p.cells_pad;  // the grid starts right behind the struct
     auto take = [&](int bytes) { int o = off; off = round_up(off + bytes, 16); return o; };
     p.off_dead = take(p.dead_words * 4);
-    p.off_sl = take(p.Sp * 2);
+    // maps with many boxes/walls under the general kernels: their lives (touched by the odd hit only) stay in the state
+    // buffer instead of costing resident CTAs (zs_device.cuh: SLP)
+    p.sl_global = p.mpc > 32 && p.Sp > 512 && !getenv("ZS_NO_SL_GLOBAL");
+    p.off_sl = take(p.sl_global ? 16 : p.Sp * 2);
     int cand = 1;
     if (p.P + p.A > 0) cand = p.n_ps > 0 ? p.n_ps : cells;
     if (p.Z > 0) { int zc = p.n_zs > 0 ? p.n_zs : cells; if (zc > cand) cand = zc; }

@@ -89,6 +89,7 @@ struct ZsParams {
     int32_t spl_pitch;             // more slots than lanes on maps with many boxes/walls (keeps CTAs resident); NULL = shared
     uint16_t* cand_global;         // spawn candidate lists in device memory [N, cand_cap] when they are too long for shared
                                    // memory (maps without spawn cells: every cell is a candidate); NULL = in shared memory
+    int32_t sl_global;             // same kernels, same maps: box/wall lives are used where they are, in the state buffer
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
     int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
     int32_t tmpl_planes;           // planes staged there: 1 (simple) or 3 (channels: label, life, zeros)
@@ -148,8 +149,7 @@ extern __shared__ __align__(16) unsigned char zs_smem[];
 template <int MPC>
 struct alignas(16) EnvS {
     static constexpr int GEN = MPC > 32 ? MPC : 1;  // arrays only the general (more slots than lanes) kernels use
-    unsigned long long act[MPC];            // the step's action list (packed, see pack_action)
-    unsigned long long act2[GEN];           // general kernels: the list in shuffled order (act holds it in actor order)
+    unsigned long long act[MPC];            // the step's action list (packed, see pack_action): actor order, then shuffled in place
     uint32_t txy[MPC];                      // x | y << 16 (int16 each)
     uint32_t bk[MPC];                       // per step: closest-player key of a zombie / heal_closest agent
     alignas(16) uint32_t draws[3 * MPC + 4];  // per step: the draws, 4 per Philox block (stored as uint4)
@@ -199,7 +199,8 @@ struct Env {
     EnvS<MPC>& S = *reinterpret_cast<EnvS<MPC>*>(zs_smem + e.b);                                     \
     uint8_t* const GRIDP = zs_smem + e.b + sizeof(EnvS<MPC>);                                        \
     uint32_t* const DEADP = reinterpret_cast<uint32_t*>(GRIDP + p.off_dead);                         \
-    int16_t* const SLP = reinterpret_cast<int16_t*>(GRIDP + p.off_sl);                               \
+    int16_t* const SLP = (MPC > 32 && p.sl_global) ? p.SLIFE + (size_t)e.env * p.Sp                    \
+                                                   : reinterpret_cast<int16_t*>(GRIDP + p.off_sl);      \
     uint16_t* const CANDP = p.cand_global ? p.cand_global + (size_t)e.env * p.cand_cap                 \
                                           : reinterpret_cast<uint16_t*>(GRIDP + p.off_cand);             \
     uint32_t* const SPLP = (MPC > 32 && p.spl_global) ? p.spl_global + (size_t)e.env * p.spl_pitch       \

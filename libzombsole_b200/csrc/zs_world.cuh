@@ -193,9 +193,11 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, boo
     for (int w = e.gl; w < p.dead_words; w += G) DEADW(w) = p.DEAD[(size_t)e.env * p.dead_words + w];
 #pragma unroll 1
     for (int a = e.gl; a < p.Ap; a += G) PREVL(a) = p.PREV[(size_t)e.env * p.Ap + a];
-    const uint4* sl4 = (const uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
+    if (!(MPC > 32 && p.sl_global)) {
+        const uint4* sl4 = (const uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
 #pragma unroll 1
-    for (int i = e.gl; i < (p.Sp >> 3); i += G) reinterpret_cast<uint4*>(SLP)[i] = sl4[i];
+        for (int i = e.gl; i < (p.Sp >> 3); i += G) reinterpret_cast<uint4*>(SLP)[i] = sl4[i];
+    }
     scalars_from_lane<G, CV>(e, e.gl < 8 ? p.SCAL[(size_t)e.env * 8 + e.gl] : 0);
     gsync<G, CV>(e);
     e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e));
@@ -218,7 +220,7 @@ ZS_TPL __device__ __forceinline__ void store_state(const ZsParams& p, Env& e) {
     for (int w = e.gl; w < p.dead_words; w += G) p.DEAD[(size_t)e.env * p.dead_words + w] = DEADW(w);
 #pragma unroll 1
     for (int a = e.gl; a < p.Ap; a += G) p.PREV[(size_t)e.env * p.Ap + a] = PREVL(a);
-    if (e.flags & FL_SL_DIRTY) {
+    if ((e.flags & FL_SL_DIRTY) && !(MPC > 32 && p.sl_global)) {
         uint4* sl4 = (uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
 #pragma unroll 1
         for (int i = e.gl; i < (p.Sp >> 3); i += G) sl4[i] = reinterpret_cast<const uint4*>(SLP)[i];
@@ -631,31 +633,69 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     for (int i = 1 + e.gl; i < L; i += G) DTYPE(i) = (uint8_t)below(DRAWS(nd + (L - 1 - i)), i + 1);
     gsync<G, CV>(e);
 
-    // ---- random.shuffle (core.py:76): the swaps are a fixed sequence once the partners are known; every lane follows the
-    // list positions it owns (lane, lane + 32, ...) through them in registers, then the words move to their places
+    // ---- random.shuffle (core.py:76): the swaps are a fixed sequence once the partners are known, and where an element
+    // ends up can be read off them without running it.  Iteration i (i = L-1 .. 1) swaps positions i and j_i <= i and
+    // is the last one to touch position i.  So an element at position q, looked at when the iterations above T have
+    // run: if some iteration i with q < i < T has j_i == q, the largest such i takes it to its final position i; else
+    // iteration q takes it to j_q (final if j_q == q, or q == 0), and the same question is asked again at (j_q, T = q).
+    // The iterations that hit a position are chained in shared memory (head = the largest, next = the next smaller one
+    // with the same partner), built 32 iterations at a time with match.any; every lane then follows its own elements
+    // (lane, lane + 32, ...), a couple of hops each, instead of all L swaps.
     int k = nd + (L > 1 ? L - 1 : 0);
     int nmv = 0;
     {
+        static_assert(G == 32, "the general step function runs one env per warp");
         constexpr int R = MPC / 32;
+        uint8_t* const HITH = S.mpos;   // both arrays are (re)initialised for their own purpose right below
+        uint8_t* const HITN = S.mvp;
+#pragma unroll 1
+        for (int q = lane; q < L; q += 32) HITH[q] = 0;  // 0 = none (an iteration that hits q is > q >= 0)
+        gsync<G, CV>(e);
+#pragma unroll 1
+        for (int i0 = 1; i0 < L; i0 += 32) {  // ascending, so that the head ends up the largest
+            const int i = i0 + lane;
+            const int j = i < L ? (int)DTYPE(i) : i;
+            const bool hit = j != i;  // (a swap with itself moves nothing)
+            const unsigned grp = __match_any_sync(0xffffffffu, hit ? (uint32_t)j : 0xffffu);
+            const unsigned lower = grp & ((1u << lane) - 1u), higher = grp & ~((2u << lane) - 1u);
+            int prev = 0;
+            if (hit) prev = lower ? i0 + 31 - __clz(lower) : (int)HITH[j];
+            gsync<G, CV>(e);
+            if (hit) { HITN[i] = (uint8_t)prev; if (!higher) HITH[j] = (uint8_t)i; }
+            gsync<G, CV>(e);
+        }
         int fp[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) fp[r] = lane + 32 * r;
+        for (int r = 0; r < R; ++r) {
+            int q = lane + 32 * r, T = L;
+            if (q < L) {
 #pragma unroll 1
-        for (int i = L - 1; i >= 1; --i) {
-            const int j = DTYPE(i);
-#pragma unroll
-            for (int r = 0; r < R; ++r) fp[r] = fp[r] == i ? j : (fp[r] == j ? i : fp[r]);
+                while (true) {
+                    int h = HITH[q];
+                    while (h >= T) h = HITN[h];
+                    if (h > q) { q = h; break; }
+                    if (q == 0) break;
+                    const int nq = DTYPE(q);
+                    if (nq == q) break;
+                    T = q; q = nq;
+                }
+            }
+            fp[r] = q;
         }
+        gsync<G, CV>(e);
 #pragma unroll 1
         for (int s = lane; s < p.Mp; s += G) { S.mpos[s] = RK_NONE; S.mvp[s] = RK_NONE; }
         gsync<G, CV>(e);
+        // the words move to their places within the one list (through registers)
+        unsigned long long wr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) wr[r] = lane + 32 * r < L ? ACT(lane + 32 * r) : 0ull;
+        gsync<G, CV>(e);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int pre = lane + 32 * r;
-            if (pre < L) {
-                const unsigned long long w = ACT(pre);
-                S.act2[fp[r]] = w;
-                if (((uint32_t)w & 7u) == X_MOVE) S.mpos[((uint32_t)w >> 3) & 0xffu] = (uint8_t)fp[r];
+            if (lane + 32 * r < L) {
+                ACT(fp[r]) = wr[r];
+                if (((uint32_t)wr[r] & 7u) == X_MOVE) S.mpos[((uint32_t)wr[r] >> 3) & 0xffu] = (uint8_t)fp[r];
             }
         }
         gsync<G, CV>(e);
@@ -668,7 +708,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
 #pragma unroll 1
     for (int base = 0; base < L; base += 32) {
         const int q = base + lane;  // list position
-        const unsigned long long pk = q < L ? S.act2[q] : 0ull;
+        const unsigned long long pk = q < L ? ACT(q) : 0ull;
         const uint32_t lo32 = (uint32_t)pk, hi32 = (uint32_t)(pk >> 32);
         int kind = lo32 & 7;
         const int who = (lo32 >> 3) & 0xff;  // the actor of a move, the mobile target of a hit
@@ -682,7 +722,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                 const int end = base + 32 < L ? base + 32 : L;
 #pragma unroll 1
                 for (int i = base; i < end; ++i) {
-                    const unsigned long long w = S.act2[i];
+                    const unsigned long long w = ACT(i);
                     const uint32_t l32 = (uint32_t)w, h32 = (uint32_t)(w >> 32);
                     const int kd = l32 & 7;
                     if (kd == X_NOP) continue;
