@@ -635,12 +635,12 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
 
     // ---- random.shuffle (core.py:76): the swaps are a fixed sequence once the partners are known, and where an element
     // ends up can be read off them without running it.  Iteration i (i = L-1 .. 1) swaps positions i and j_i <= i and
-    // is the last one to touch position i.  So an element at position q, looked at when the iterations above T have
-    // run: if some iteration i with q < i < T has j_i == q, the largest such i takes it to its final position i; else
-    // iteration q takes it to j_q (final if j_q == q, or q == 0), and the same question is asked again at (j_q, T = q).
-    // The iterations that hit a position are chained in shared memory (head = the largest, next = the next smaller one
-    // with the same partner), built 32 iterations at a time with match.any; every lane then follows its own elements
-    // (lane, lane + 32, ...), a couple of hops each, instead of all L swaps.
+    // is the last one to touch position i.  So an element at position q: the largest iteration i > q with j_i == q takes
+    // it to its final position i; if there is none, iteration q takes it to j_q (final if j_q == q, or q == 0), where
+    // the next smaller iteration with the same partner j_q finds it, and so on.  The iterations that hit a position are
+    // chained in shared memory (head = the largest, next = the next smaller one with the same partner), built 32
+    // iterations at a time with match.any; every lane then follows its own elements (lane, lane + 32, ...), two hops
+    // on average, instead of all L swaps.
     int k = nd + (L > 1 ? L - 1 : 0);
     int nmv = 0;
     {
@@ -667,18 +667,17 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         int fp[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int q = lane + 32 * r, T = L;
+            int q = lane + 32 * r;
             if (q < L) {
+                int h = HITH[q];
 #pragma unroll 1
-                while (true) {
-                    int h = HITH[q];
-                    while (h >= T) h = HITN[h];
-                    if (h > q) { q = h; break; }
-                    if (q == 0) break;
+                while (h == 0 && q != 0) {  // nobody takes it from q: iteration q moves it to j_q ...
                     const int nq = DTYPE(q);
                     if (nq == q) break;
-                    T = q; q = nq;
+                    h = HITN[q];            // ... where the next iteration below q that hits j_q finds it
+                    q = nq;
                 }
+                if (h) q = h;
             }
             fp[r] = q;
         }
