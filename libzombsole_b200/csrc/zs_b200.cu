@@ -328,7 +328,12 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
         uint4* dst = reinterpret_cast<uint4*>(zs_smem + p.tmpl_smem_off);
         const uint4* src = reinterpret_cast<const uint4*>(p.tmpl_obs);
         const int n4 = p.cells >> 2, nsrc = (p.tmpl_planes > 1 ? 2 : 1) * n4;
-        for (int i = threadIdx.x; i < p.tmpl_planes * n4; i += blockDim.x) dst[i] = i < nsrc ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+        const int nrow = p.tmpl_planes * n4;
+        for (int i = threadIdx.x; i < nrow; i += blockDim.x) {
+            const uint4 v = i < nsrc ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+            dst[i] = v;
+            if (p.tmpl_pair) dst[nrow + i] = v;
+        }
         fence_proxy_async_smem();
         __syncthreads();
     }
@@ -767,10 +772,15 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     p.tmpl_smem_off = -1; p.tmpl_planes = 0;
     if (p.obs_scope == ZS_OBS_WORLD && (p.cells & 3) == 0) {
         const int planes = p.obs_enc == ZS_OBS_CHANNELS ? 3 : 1;
-        const int bytes = planes * p.cells * 4;
-        // keep at least 6 CTAs per SM resident
+        int bytes = planes * p.cells * 4;
+        // two envs per warp in a batch that fits the chip at 16 warps per SM: one bulk copy for both (obs_world_template)
+        const bool pair = h->lanes_per_env == 16 && p.N / 2 <= prop.multiProcessorCount * ZS_MIN_CTAS_LOWOCC * ZS_WPC &&
+                          (h->smem_bytes + 2 * bytes + 1024) * (16 / h->warps_per_cta) <= (int)prop.sharedMemPerMultiprocessor &&
+                          !getenv("ZS_NO_TMA_PAIR");
+        if (pair) bytes *= 2;
+        // keep at least 6 CTAs per SM resident (2-warp CTAs are only chosen for batches that need no more)
         if ((h->smem_bytes + bytes + 1024) * 6 <= (int)prop.sharedMemPerMultiprocessor && !getenv("ZS_NO_TMA")) {
-            p.tmpl_smem_off = h->smem_bytes; p.tmpl_planes = planes;
+            p.tmpl_smem_off = h->smem_bytes; p.tmpl_planes = planes; p.tmpl_pair = pair;
             h->smem_bytes += bytes;
         }
     }

@@ -93,6 +93,7 @@ struct ZsParams {
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
     int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
     int32_t tmpl_planes;           // planes staged there: 1 (simple) or 3 (channels: label, life, zeros)
+    int32_t tmpl_pair;             // the planes are staged twice back to back: one bulk copy serves both envs of a warp
     int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
 };
 

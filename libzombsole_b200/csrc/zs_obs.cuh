@@ -51,12 +51,13 @@ ZS_TPL __device__ __forceinline__ void obs_world_template(const ZsParams& p, Env
     if (p.tmpl_smem_off >= 0) {
         // TMA: the group's lane 0 issues one bulk copy per plane from the CTA-shared template to the env's row —
         // no per-lane loads/stores at all.  obs_world_patch waits for the group before it patches cells.
-        if (lane == 0) {
-            const uint32_t plane = (uint32_t)cells * 4u;
-            bulk_store_s(obs, e.tmpl_saddr, plane);
-            for (int c = 1; c < p.tmpl_planes; ++c) bulk_store_s(obs + (size_t)c * cells, e.tmpl_saddr + (uint32_t)c * plane, plane);
-            bulk_commit();
-        }
+        // (issuing a bulk copy costs the lane about a thousand cycles, and the two halves of a warp cannot issue together:
+        // small batches of two envs per warp, which are latency-bound, stage the planes twice and send both rows — they
+        // are neighbours in the output — with one copy)
+        const uint32_t row = (uint32_t)(p.tmpl_planes * cells) * 4u;
+        if (G == 16 && CV && p.tmpl_pair) {
+            if (e.gshift == 0 && lane == 0) { bulk_store_s(obs, e.tmpl_saddr, 2u * row); bulk_commit(); }
+        } else if (lane == 0) { bulk_store_s(obs, e.tmpl_saddr, row); bulk_commit(); }
         return;
     }
     if ((cells & 3) == 0) {
