@@ -44,13 +44,54 @@ ZS_TPL __device__ __forceinline__ void scalars_from_smem(const ZsParams& p, Env&
 
 // Dict-order ranks from arbitrary order-preserving stamps (state import / start of a launch): the rank of
 // a thing in the world is the number of things in the world with a smaller stamp (A.2 of SURVEY.md).
+// store_state writes the ranks themselves as stamps, so in a state this library left behind the stamps of the n
+// things in the world are a permutation of 0 .. n-1 and ARE the ranks: that is checked first (every stamp below n,
+// all n bits set), the counting loop is for imported states.
 ZS_TPL __device__ __noinline__ int ranks_from_stamps(const ZsParams& p, GrpId id) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
     const int env = id.env, lane = e.gl;
     const int32_t* st = p.STAMP + (size_t)env * p.Mp;
+    constexpr int rw = (MPC + 31) / 32;
     int n = 0;
+    bool bad = false;
+    if (lane < rw) MASKW(lane) = 0u;
+#pragma unroll 1
+    for (int s0 = 0; s0 < (ONE ? 1 : (p.Mp)); s0 += G) {
+        const int s = s0 + lane;
+        n += __popc(gballot<G, CV>(e, s < p.Mp && (TM(s) & 0x80)));
+    }
+    gsync<G, CV>(e);
+#pragma unroll 1
+    for (int s0 = 0; s0 < (ONE ? 1 : (p.Mp)); s0 += G) {
+        const int s = s0 + lane;
+        const bool live = s < p.Mp && (TM(s) & 0x80);
+        const int mine = live ? st[s] : 0;
+        if (live) {
+            if ((unsigned)mine < (unsigned)n) atomicOr(&MASKW(mine >> 5), 1u << (mine & 31));
+            else bad = true;
+        }
+        if (s < p.Mp) {  // (provisional: the stamp as the rank)
+            RK(s) = live ? (uint8_t)mine : (uint8_t)RK_NONE;
+            MVQ(s) = RK_NONE;
+        }
+    }
+    gsync<G, CV>(e);
+    if (lane < rw) {
+        const int full = n - 32 * lane;
+        const uint32_t want = full >= 32 ? 0xffffffffu : full <= 0 ? 0u : (1u << full) - 1u;
+        bad |= MASKW(lane) != want;
+    }
+    if (!gany<G, CV>(e, bad)) {
+#pragma unroll 1
+        for (int s0 = 0; s0 < (ONE ? 1 : (p.Mp)); s0 += G) {
+            const int s = s0 + lane;
+            if (s < p.Mp && (TM(s) & 0x80)) SOR(RK(s)) = (uint8_t)s;
+        }
+        gsync<G, CV>(e);
+        return n;
+    }
 #pragma unroll 1
     for (int s0 = 0; s0 < (ONE ? 1 : (p.Mp)); s0 += G) {
         const int s = s0 + lane;
@@ -61,38 +102,64 @@ ZS_TPL __device__ __noinline__ int ranks_from_stamps(const ZsParams& p, GrpId id
         for (int j = 0; j < p.M; ++j) r += ((TM(j) & 0x80) && st[j] < mine);
         if (s < p.Mp) {
             RK(s) = live ? (uint8_t)r : (uint8_t)RK_NONE;
-            MVQ(s) = RK_NONE;
             if (live) SOR(r) = (uint8_t)s;
         }
-        n += __popc(gballot<G, CV>(e, live));
     }
     gsync<G, CV>(e);
     return n;
 }
 
-// Build the static patch list (zs_device.cuh) from the static lives: state import / start of a launch.
+// Build the static patch list (zs_device.cuh) from the static lives: state import / start of a launch.  Eight
+// boxes/walls per lane (one 128-bit word of lives against one of MAX_LIFEs): almost all are pristine, the few lanes
+// that find a difference list theirs behind the lanes before them (prefix sum of the counts).
 ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId id, int fresh) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
+    const uint4* life4 = reinterpret_cast<const uint4*>(SLP);
+    const uint4* max4 = reinterpret_cast<const uint4*>(p.static_max);
+    const int n8 = p.Sp >> 3;
     int n = 0;
 #pragma unroll 1
-    for (int i0 = 0; i0 < p.Sp; i0 += G) {
-        const int i = i0 + e.gl;
-        bool listed = false;
-        int pay = 0;
-        if (i < p.S) {
-            const int life = SL(i), mx = __ldg(p.static_max + i);
-            if (life != mx) {  // (most boxes/walls are pristine)
-                pay = static_payload(p, mx, life, life > 0 || fresh);
-                listed = pay != static_payload(p, mx, mx, true);
+    for (int i0 = 0; i0 < n8; i0 += G) {
+        const int i8 = i0 + e.gl;
+        uint4 lv = make_uint4(0u, 0u, 0u, 0u), mv = lv;
+        if (i8 < n8) { lv = life4[i8]; mv = __ldg(max4 + i8); }
+        const bool differs = ((lv.x ^ mv.x) | (lv.y ^ mv.y) | (lv.z ^ mv.z) | (lv.w ^ mv.w)) != 0u;
+        uint32_t sx0 = 0u, sx1 = 0u;  // the eight SIDX bytes of this lane's boxes/walls
+        if (gany<G, CV>(e, differs)) {
+            const unsigned long long l0 = (unsigned long long)lv.x | ((unsigned long long)lv.y << 32), l1 = (unsigned long long)lv.z | ((unsigned long long)lv.w << 32);
+            const unsigned long long m0 = (unsigned long long)mv.x | ((unsigned long long)mv.y << 32), m1 = (unsigned long long)mv.z | ((unsigned long long)mv.w << 32);
+            auto pay_of = [&](int k, bool& listed) {
+                const int sh = 16 * (k & 3);
+                const int life = (int)(int16_t)((k & 4 ? l1 : l0) >> sh), mx = (int)(int16_t)((k & 4 ? m1 : m0) >> sh);
+                const int pay = static_payload(p, mx, life, life > 0 || fresh);
+                listed = life != mx && pay != static_payload(p, mx, mx, true);
+                return pay;
+            };
+            unsigned lm = 0u;
+            if (differs) {
+#pragma unroll 1
+                for (int k = 0; k < 8; ++k) { bool listed; pay_of(k, listed); if (listed && i8 * 8 + k < p.S) lm |= 1u << k; }
+            }
+            const int c = __popc(lm);
+            int inc = c;
+#pragma unroll
+            for (int d = 1; d < G; d <<= 1) { const int t = __shfl_up_sync(gmask<G, CV>(e), inc, d, G); if (e.gl >= d) inc += t; }
+            int pos = n + inc - c;
+            n += gbcast<G, CV>(e, inc, G - 1);
+#pragma unroll 1
+            for (unsigned mm = lm; mm; mm &= mm - 1u) {
+                const int k = __ffs(mm) - 1;
+                bool listed;
+                const int pay = pay_of(k, listed);
+                SPL(pos) = (uint32_t)__ldg(p.static_cell + i8 * 8 + k) | ((uint32_t)pay << 16);
+                const uint32_t sb = (uint32_t)(pos + 1 < SIDX_FAR ? pos + 1 : SIDX_FAR) << (8 * (k & 3));
+                if (k < 4) sx0 |= sb; else sx1 |= sb;
+                ++pos;
             }
         }
-        const unsigned m = gballot<G, CV>(e, listed);
-        const int pos = n + __popc(m & ((1u << e.gl) - 1u));
-        if (listed) SPL(pos) = (uint32_t)__ldg(p.static_cell + i) | ((uint32_t)pay << 16);
-        if (i < p.Sp) SIDX(i) = listed ? (uint8_t)(pos + 1 < SIDX_FAR ? pos + 1 : SIDX_FAR) : (uint8_t)0;
-        n += __popc(m);
+        if (i8 < n8) *reinterpret_cast<uint2*>(SIDXP + 8 * i8) = make_uint2(sx0, sx1);
     }
     if (e.gl == 0) SPN = (uint16_t)n;
     gsync<G, CV>(e);
