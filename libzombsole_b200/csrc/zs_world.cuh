@@ -137,10 +137,17 @@ ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId
                 listed = life != mx && pay != static_payload(p, mx, mx, true);
                 return pay;
             };
+            // the boxes/walls whose life differs (one bit per 16-bit field), then the ones among them that show
+            const uint32_t x0 = lv.x ^ mv.x, x1 = lv.y ^ mv.y, x2 = lv.z ^ mv.z, x3 = lv.w ^ mv.w;
+            unsigned dm = ((x0 & 0xffffu) ? 1u : 0u) | ((x0 >> 16) ? 2u : 0u) | ((x1 & 0xffffu) ? 4u : 0u) | ((x1 >> 16) ? 8u : 0u) |
+                          ((x2 & 0xffffu) ? 16u : 0u) | ((x2 >> 16) ? 32u : 0u) | ((x3 & 0xffffu) ? 64u : 0u) | ((x3 >> 16) ? 128u : 0u);
             unsigned lm = 0u;
-            if (differs) {
 #pragma unroll 1
-                for (int k = 0; k < 8; ++k) { bool listed; pay_of(k, listed); if (listed && i8 * 8 + k < p.S) lm |= 1u << k; }
+            for (; dm; dm &= dm - 1u) {
+                const int k = __ffs(dm) - 1;
+                bool listed;
+                pay_of(k, listed);
+                if (listed && i8 * 8 + k < p.S) lm |= 1u << k;
             }
             const int c = __popc(lm);
             int inc = c;
@@ -251,21 +258,45 @@ ZS_TPL __device__ __noinline__ int scan_dead_bodies(const ZsParams& p, GrpId id)
 ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, bool with_lists) {
     ZS_CONSTS; ZS_VIEWS;
     const size_t row = (size_t)e.env * p.Mp;
+    // A launch starts with a handful of dependent round trips to memory unless the loads are issued together: the first
+    // round of every field goes out back to back (all a small world has), then the values go to shared memory.
+    const int s0 = e.gl;
+    const bool has_slot = s0 < p.Mp;
+    int x0 = 0, y0 = 0, l0 = 0, m0 = 0;
+    if (has_slot) { x0 = p.X[row + s0]; y0 = p.Y[row + s0]; l0 = p.LIFE[row + s0]; m0 = p.META[row + s0]; }
+    const uint32_t* dead = p.DEAD + (size_t)e.env * p.dead_words;
+    constexpr int DR = 96 / G;  // rounds of the dead-body bitmap issued up front (96 words = 3,072 cells)
+    uint32_t dw[DR];
+#pragma unroll
+    for (int r = 0; r < DR; ++r) dw[r] = e.gl + r * G < p.dead_words ? dead[e.gl + r * G] : 0u;
+    const int pv = e.gl < p.Ap ? (int)p.PREV[(size_t)e.env * p.Ap + e.gl] : 0;
+    const bool sl_here = !(MPC > 32 && p.sl_global);
+    const uint4* sl4 = (const uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
+    constexpr int SR = 32 / G;  // rounds of box/wall lives issued up front (32 words = 256 boxes/walls)
+    uint4 sv[SR];
+#pragma unroll
+    for (int r = 0; r < SR; ++r) sv[r] = (sl_here && e.gl + r * G < (p.Sp >> 3)) ? sl4[e.gl + r * G] : make_uint4(0u, 0u, 0u, 0u);
+    const int sc = e.gl < 8 ? p.SCAL[(size_t)e.env * 8 + e.gl] : 0;
+    if (has_slot) { TXY(s0) = xy_pack(x0, y0); TL(s0) = (int16_t)l0; TM(s0) = (uint8_t)m0; }
 #pragma unroll 1
-    for (int s = e.gl; s < p.Mp; s += G) {
+    for (int s = s0 + G; s < p.Mp; s += G) {
         TXY(s) = xy_pack(p.X[row + s], p.Y[row + s]);
         TL(s) = p.LIFE[row + s]; TM(s) = p.META[row + s];
     }
+#pragma unroll
+    for (int r = 0; r < DR; ++r) if (e.gl + r * G < p.dead_words) DEADW(e.gl + r * G) = dw[r];
 #pragma unroll 1
-    for (int w = e.gl; w < p.dead_words; w += G) DEADW(w) = p.DEAD[(size_t)e.env * p.dead_words + w];
+    for (int w = e.gl + DR * G; w < p.dead_words; w += G) DEADW(w) = dead[w];
+    if (e.gl < p.Ap) PREVL(e.gl) = (int16_t)pv;
 #pragma unroll 1
-    for (int a = e.gl; a < p.Ap; a += G) PREVL(a) = p.PREV[(size_t)e.env * p.Ap + a];
-    if (!(MPC > 32 && p.sl_global)) {
-        const uint4* sl4 = (const uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
+    for (int a = e.gl + G; a < p.Ap; a += G) PREVL(a) = p.PREV[(size_t)e.env * p.Ap + a];
+    if (sl_here) {
+#pragma unroll
+        for (int r = 0; r < SR; ++r) if (e.gl + r * G < (p.Sp >> 3)) reinterpret_cast<uint4*>(SLP)[e.gl + r * G] = sv[r];
 #pragma unroll 1
-        for (int i = e.gl; i < (p.Sp >> 3); i += G) reinterpret_cast<uint4*>(SLP)[i] = sl4[i];
+        for (int i = e.gl + SR * G; i < (p.Sp >> 3); i += G) reinterpret_cast<uint4*>(SLP)[i] = sl4[i];
     }
-    scalars_from_lane<G, CV>(e, e.gl < 8 ? p.SCAL[(size_t)e.env * 8 + e.gl] : 0);
+    scalars_from_lane<G, CV>(e, sc);
     gsync<G, CV>(e);
     e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e));
     e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e), e.flags & FL_FRESH);

@@ -35,5 +35,8 @@ def run(name, N, reps=10):
     eng.close()
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2:
+        run(sys.argv[1], int(sys.argv[2]))
+        sys.exit(0)
     for name, N in (("c1_bridge_ext", 65536), ("c1_bridge_ext", 1 << 20), ("c5_bridge_channels", 1 << 19), ("c3_city_evac", 65536), ("c4_maze_safehouse", 131072)):
         run(name, N)
