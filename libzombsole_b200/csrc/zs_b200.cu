@@ -518,14 +518,18 @@ template <int MODE>
 static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     // staging the observation template for the TMA pays off when a launch runs several steps
     ZsParams pp = h->p;
-    if (MODE != MODE_STEP || io.n_steps < 4) pp.tmpl_smem_off = -1;
+    int smem = h->smem_bytes;
+    if (MODE != MODE_STEP || io.n_steps < 4) {  // (and without the template a CTA more fits an SM)
+        if (pp.tmpl_smem_off >= 0) smem = pp.tmpl_smem_off;
+        pp.tmpl_smem_off = -1;
+    }
     const dim3 grid((pp.N + h->envs_per_cta - 1) / h->envs_per_cta), block(h->warps_per_cta * 32);
     // the standard rollout shape gets the kernel with that shape compiled in (step_loop_one)
     const bool fast = MODE == MODE_STEP && pp.mpc <= 32 && pp.A == 1 && !pp.obs_per_agent && pp.minimum_zombies == 0 &&
                       pp.obs_scope == ZS_OBS_WORLD && io.actions && io.fmt == ZS_ACTIONS_DISCRETE && io.obs && io.reward &&
                       io.terminated && io.truncated && !io.draws && !io.agent_mask;
     const int occ = MODE == MODE_STEP ? h->occ : ZS_MIN_CTAS;
-#define ZS_LAUNCH(MPC_, G_, F_, O_) zs_sim_kernel<MODE, MPC_, G_, (F_) && MODE == MODE_STEP, MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS><<<grid, block, h->smem_bytes, st>>>(pp, io)
+#define ZS_LAUNCH(MPC_, G_, F_, O_) zs_sim_kernel<MODE, MPC_, G_, (F_) && MODE == MODE_STEP, MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS><<<grid, block, smem, st>>>(pp, io)
 #define ZS_LAUNCH_F(MPC_, G_, O_) do { if (fast) ZS_LAUNCH(MPC_, G_, true, O_); else ZS_LAUNCH(MPC_, G_, false, O_); } while (0)
     switch (pp.mpc) {
         case 16:

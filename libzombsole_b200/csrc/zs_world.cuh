@@ -47,7 +47,7 @@ ZS_TPL __device__ __forceinline__ void scalars_from_smem(const ZsParams& p, Env&
 // store_state writes the ranks themselves as stamps, so in a state this library left behind the stamps of the n
 // things in the world are a permutation of 0 .. n-1 and ARE the ranks: that is checked first (every stamp below n,
 // all n bits set), the counting loop is for imported states.
-ZS_TPL __device__ __noinline__ int ranks_from_stamps(const ZsParams& p, GrpId id) {
+ZS_TPL __device__ __noinline__ int ranks_from_stamps(const ZsParams& p, GrpId id, int stamp0) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
@@ -67,7 +67,7 @@ ZS_TPL __device__ __noinline__ int ranks_from_stamps(const ZsParams& p, GrpId id
     for (int s0 = 0; s0 < (ONE ? 1 : (p.Mp)); s0 += G) {
         const int s = s0 + lane;
         const bool live = s < p.Mp && (TM(s) & 0x80);
-        const int mine = live ? st[s] : 0;
+        const int mine = live ? (s0 == 0 ? stamp0 : st[s]) : 0;  // (the first round's stamps came with the state, load_state)
         if (live) {
             if ((unsigned)mine < (unsigned)n) atomicOr(&MASKW(mine >> 5), 1u << (mine & 31));
             else bad = true;
@@ -263,7 +263,8 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, boo
     const int s0 = e.gl;
     const bool has_slot = s0 < p.Mp;
     int x0 = 0, y0 = 0, l0 = 0, m0 = 0;
-    if (has_slot) { x0 = p.X[row + s0]; y0 = p.Y[row + s0]; l0 = p.LIFE[row + s0]; m0 = p.META[row + s0]; }
+    int st0 = 0;
+    if (has_slot) { x0 = p.X[row + s0]; y0 = p.Y[row + s0]; l0 = p.LIFE[row + s0]; m0 = p.META[row + s0]; st0 = p.STAMP[row + s0]; }
     const uint32_t* dead = p.DEAD + (size_t)e.env * p.dead_words;
     constexpr int DR = 96 / G;  // rounds of the dead-body bitmap issued up front (96 words = 3,072 cells)
     uint32_t dw[DR];
@@ -298,7 +299,7 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, boo
     }
     scalars_from_lane<G, CV>(e, sc);
     gsync<G, CV>(e);
-    e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e));
+    e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e), st0);
     e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e), e.flags & FL_FRESH);
     if (ONE && with_lists) e.flags |= scan_dead_bodies<MPC, G, false>(p, id_of(e));
     else e.flags |= FL_DEAD_OVER;
