@@ -519,6 +519,8 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     // staging the observation template for the TMA pays off when a launch runs several steps
     ZsParams pp = h->p;
     int smem = h->smem_bytes;
+    // envs in flight chip-wide, roughly: the distance load_state prefetches ahead (a launch of many short-lived CTAs)
+    pp.prefetch_ahead = (MODE != MODE_STEP || io.n_steps < 4) && !getenv("ZS_NO_PREFETCH") ? h->sm_count * 7 * h->envs_per_cta : 0;
     if (MODE != MODE_STEP || io.n_steps < 4) {  // (and without the template a CTA more fits an SM)
         if (pp.tmpl_smem_off >= 0) smem = pp.tmpl_smem_off;
         pp.tmpl_smem_off = -1;

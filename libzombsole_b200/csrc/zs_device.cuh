@@ -89,6 +89,7 @@ struct ZsParams {
     int32_t spl_pitch;             // more slots than lanes on maps with many boxes/walls (keeps CTAs resident); NULL = shared
     uint16_t* cand_global;         // spawn candidate lists in device memory [N, cand_cap] when they are too long for shared
                                    // memory (maps without spawn cells: every cell is a candidate); NULL = in shared memory
+    int32_t prefetch_ahead;        // load_state also prefetches the state of env + prefetch_ahead into the L2 (0 = off)
     int32_t sl_global;             // same kernels, same maps: box/wall lives are used where they are, in the state buffer
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
     int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
@@ -245,6 +246,7 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 __device__ __forceinline__ void bulk_store_s(void* gdst, uint32_t saddr, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -278,6 +278,20 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, boo
 #pragma unroll
     for (int r = 0; r < SR; ++r) sv[r] = (sl_here && e.gl + r * G < (p.Sp >> 3)) ? sl4[e.gl + r * G] : make_uint4(0u, 0u, 0u, 0u);
     const int sc = e.gl < 8 ? p.SCAL[(size_t)e.env * 8 + e.gl] : 0;
+    // ... and the same lines of the env a later CTA will work on are pulled into the L2 (the launch is a stream of
+    // short-lived CTAs: without this every one of them starts with a trip to DRAM behind the observation writes)
+    if (p.prefetch_ahead > 0 && e.env + p.prefetch_ahead < p.N) {
+        const size_t pe = (size_t)(e.env + p.prefetch_ahead), prow = pe * p.Mp;
+        if (has_slot) { prefetch_l2(p.X + prow + s0); prefetch_l2(p.Y + prow + s0); prefetch_l2(p.LIFE + prow + s0); prefetch_l2(p.META + prow + s0); prefetch_l2(p.STAMP + prow + s0); }
+#pragma unroll
+        for (int r = 0; r < DR; ++r) if (e.gl + r * G < p.dead_words) prefetch_l2(p.DEAD + pe * p.dead_words + e.gl + r * G);
+        if (e.gl < p.Ap) prefetch_l2(p.PREV + pe * p.Ap + e.gl);
+        if (sl_here) {
+#pragma unroll
+            for (int r = 0; r < SR; ++r) if (e.gl + r * G < (p.Sp >> 3)) prefetch_l2((const uint4*)(p.SLIFE + pe * p.Sp) + e.gl + r * G);
+        }
+        if (e.gl < 8) prefetch_l2(p.SCAL + pe * 8 + e.gl);
+    }
     if (has_slot) { TXY(s0) = xy_pack(x0, y0); TL(s0) = (int16_t)l0; TM(s0) = (uint8_t)m0; }
 #pragma unroll 1
     for (int s = s0 + G; s < p.Mp; s += G) {
