@@ -31,12 +31,13 @@ __device__ __forceinline__ void discrete_to_action(const ZsParams& p, int id, in
 }
 
 // ---------------------------------------------------------------- the K-step loop, more slots than lanes
-ZS_TPL __device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO& io, Env& e) {
+template <int MPC, int G, bool CV, bool SURR>
+__device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO& io, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl, env = e.env;
     const int A = p.A, NP = p.P + p.A;
     const int R = p.obs_per_agent ? A : 1;
-    const bool world_obs = p.obs_scope == ZS_OBS_WORLD;
+    constexpr bool world_obs = !SURR;  // (the observation scope is compiled in: see zs_sim_kernel)
     // agent actions for the coming step, fetched one step ahead (Agent.set_action, agent.py:22-25);
     // agent a is handled by lanes a, a + G, ... of the group
     constexpr int AR = ZS_MAX_AGENTS / G > 0 ? ZS_MAX_AGENTS / G : 1;  // agents per lane (1 or 2)
@@ -63,7 +64,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_general(const ZsParams& p, cons
             obs_out = io.obs + ((size_t)oslot * p.N + env) * p.obs_elems;
             if (++oslot >= io.obs_slots) oslot = 0;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
-            if (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
+            if constexpr (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
         }
         // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
         unsigned alive_before = 0;
@@ -161,7 +162,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_general(const ZsParams& p, cons
             scalars_from_smem<MPC, G, false>(p, e);
         }
         if (obs_out) {
-            if (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
+            if constexpr (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
             else encode_surroundings<MPC, G, CV>(p, e, obs_out);
         }
         gsync<G, CV>(e);
@@ -174,7 +175,7 @@ ZS_TPL __device__ __forceinline__ void step_loop_general(const ZsParams& p, cons
 // FAST = the standard rollout shape, fixed at compile time: one agent, one reward per env, world-scope observation,
 // no minimum-zombie respawn, a discrete action tape in, observation / reward / terminated / truncated out and no
 // diagnostics outputs (zs_launch picks it when a launch has that shape).
-template <int MPC, int G, bool CV, bool FAST>
+template <int MPC, int G, bool CV, bool FAST, bool SURR>
 __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl, env = e.env;
@@ -184,7 +185,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
     const bool per_agent = FAST ? false : p.obs_per_agent != 0;
     const bool lane_sum = FAST ? false : (!per_agent && A > 1);  // one reward from the sum of several agents' lives (reward.py:37-41)
     const bool want_mask = FAST ? false : (per_agent || io.agent_mask != nullptr);
-    const bool world_obs = FAST ? true : p.obs_scope == ZS_OBS_WORLD;
+    constexpr bool world_obs = !SURR;
     const bool auto_reset = p.auto_reset || io.force_auto_reset;
     // The agent's action for the coming step is LOADED one step ahead and decoded when its step starts, so the load's
     // latency hides under the previous transition (Agent.set_action, agent.py:22-25).
@@ -209,7 +210,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         if (FAST || obs_out) {
             if (++oslot >= io.obs_slots) { oslot = 0; obs_cur = obs_first; } else obs_cur += obs_stride;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
-            if (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
+            if constexpr (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
         }
         PH(18);
         // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
@@ -289,7 +290,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         }
         PH(10);
         if (FAST || obs_out) {
-            if (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
+            if constexpr (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
             else encode_surroundings<MPC, G, CV>(p, e, obs_out);
         }
         gsync<G, CV>(e);
@@ -310,9 +311,13 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
 // batch runs in ceil(warps / resident warps) rounds: zs_create picks the OCC with the fewest rounds, and among those the
 // one with the most registers — 4 (128 registers, nothing spilled or re-derived in the step loop: +10 % at 4,096 envs,
 // which are latency-bound), 6 (80) or 7 (72); large batches are issue-bound and take 6 (two envs per warp) or 7.
-template <int MODE, int MPC, int G, bool FAST, int OCC>
+// SHAPE: what is compiled in — 0 = world-scope observation, 1 = the standard rollout shape (FAST, world scope),
+// 2 = surroundings observation.  (With both observation encoders in one kernel the step loop of the kernels that
+// never run the window code spilled more registers: 5-8 % on large world-scope batches.)
+template <int MODE, int MPC, int G, int SHAPE, int OCC>
 __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     ZS_CONSTS;
+    constexpr bool FAST = SHAPE == 1, SURR = SHAPE == 2;
     // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
     constexpr bool CV = MODE == MODE_STEP;
     constexpr int EPW = 32 / G;  // envs per warp
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
         const int k = initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
         scalars_from_smem<MPC, G, CV>(p, e);
         if (io.draws && lane == 0) io.draws[env] = k;
-        if (io.obs) encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
+        if (io.obs) encode_obs<MPC, G, CV, SURR>(p, e, io.obs + (size_t)env * p.obs_elems);
         store_state<MPC, G, CV>(p, e);
         return;
     }
@@ -364,15 +369,15 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
     if (!(MODE == MODE_STEP && io.n_steps >= 4)) e.flags |= FL_DEAD_LAUNCH;
     build_grid<MPC, G, false>(p, id_of(e), e.flags);
     if (MODE == MODE_ENCODE) {
-        encode_obs<MPC, G, CV>(p, e, io.obs + (size_t)env * p.obs_elems);
+        encode_obs<MPC, G, CV, SURR>(p, e, io.obs + (size_t)env * p.obs_elems);
         return;
     }
 
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
 #endif
-    if constexpr (ONE) step_loop_one<MPC, G, CV, FAST>(p, io, e);
-    else step_loop_general<MPC, G, CV>(p, io, e);
+    if constexpr (ONE) step_loop_one<MPC, G, CV, FAST, SURR>(p, io, e);
+    else step_loop_general<MPC, G, CV, SURR>(p, io, e);
     store_state<MPC, G, CV>(p, e);
 }
 
@@ -531,8 +536,11 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
                       pp.obs_scope == ZS_OBS_WORLD && io.actions && io.fmt == ZS_ACTIONS_DISCRETE && io.obs && io.reward &&
                       io.terminated && io.truncated && !io.draws && !io.agent_mask;
     const int occ = MODE == MODE_STEP ? h->occ : ZS_MIN_CTAS;
-#define ZS_LAUNCH(MPC_, G_, F_, O_) zs_sim_kernel<MODE, MPC_, G_, (F_) && MODE == MODE_STEP, MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS><<<grid, block, smem, st>>>(pp, io)
-#define ZS_LAUNCH_F(MPC_, G_, O_) do { if (fast) ZS_LAUNCH(MPC_, G_, true, O_); else ZS_LAUNCH(MPC_, G_, false, O_); } while (0)
+    const bool surr = pp.obs_scope == ZS_OBS_SURROUNDINGS;
+    // SH_: 0 world scope, 1 the standard rollout shape (step launches only), 2 surroundings (zs_sim_kernel: SHAPE)
+#define ZS_LAUNCH(MPC_, G_, SH_, O_) zs_sim_kernel<MODE, MPC_, G_, ((SH_) == 1 && MODE != MODE_STEP) ? 0 : (SH_), MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS><<<grid, block, smem, st>>>(pp, io)
+#define ZS_LAUNCH_F(MPC_, G_, O_) do { if (fast) ZS_LAUNCH(MPC_, G_, 1, O_); else if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
+#define ZS_LAUNCH_G(MPC_, G_, O_) do { if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
     switch (pp.mpc) {
         case 16:
             if (h->lanes_per_env == 16) {
@@ -546,17 +554,19 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
         case 32:
             if (occ == ZS_MIN_CTAS_LOWOCC) ZS_LAUNCH_F(32, 32, ZS_MIN_CTAS_LOWOCC); else ZS_LAUNCH_F(32, 32, ZS_MIN_CTAS);
             break;
-        case 128: ZS_LAUNCH(128, 32, false, ZS_MIN_CTAS); break;
-        default: ZS_LAUNCH(256, 32, false, ZS_MIN_CTAS); break;
+        case 128: ZS_LAUNCH_G(128, 32, ZS_MIN_CTAS); break;
+        default: ZS_LAUNCH_G(256, 32, ZS_MIN_CTAS); break;
     }
+#undef ZS_LAUNCH_G
 #undef ZS_LAUNCH_F
 #undef ZS_LAUNCH
 }
 template <int MPC, int G, int OCC>
 static cudaError_t set_smem_attr_step(int bytes) {
     const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, false, OCC>, attr, bytes);
-    if (e == cudaSuccess && MPC <= 32) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32), OCC>, attr, bytes);
+    cudaError_t e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, 0, OCC>, attr, bytes);
+    if (e == cudaSuccess && MPC <= 32) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, (MPC <= 32 ? 1 : 0), OCC>, attr, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, MPC, G, 2, OCC>, attr, bytes);
     return e;
 }
 template <int MPC, int G>
@@ -565,15 +575,17 @@ static cudaError_t set_smem_attr_for(int bytes) {
     cudaError_t e = set_smem_attr_step<MPC, G, ZS_MIN_CTAS>(bytes);
     if (e == cudaSuccess && MPC <= 32) e = set_smem_attr_step<MPC, G, (MPC <= 32 ? ZS_MIN_CTAS_LOWOCC : ZS_MIN_CTAS)>(bytes);
     if (e == cudaSuccess && G == 16) e = set_smem_attr_step<MPC, G, (G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS)>(bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, false, ZS_MIN_CTAS>, attr, bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, false, ZS_MIN_CTAS>, attr, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, 0, ZS_MIN_CTAS>, attr, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, 0, ZS_MIN_CTAS>, attr, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, 2, ZS_MIN_CTAS>, attr, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, 2, ZS_MIN_CTAS>, attr, bytes);
     return e;
 }
 // resident warps per SM of the step kernel compiled for OCC CTAs, at this block size and shared-memory footprint
 template <int MPC, int G, int OCC>
 static int resident_warps_of(int block_threads, int smem) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zs_sim_kernel<MODE_STEP, MPC, G, false, OCC>, block_threads, smem) != cudaSuccess) n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, zs_sim_kernel<MODE_STEP, MPC, G, 0, OCC>, block_threads, smem) != cudaSuccess) n = 0;
     return n * (block_threads / 32);
 }
 static int resident_warps(int mpc, int lanes, int occ, int block_threads, int smem) {
@@ -767,6 +779,14 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     if (const char* force = getenv("ZS_LANES_PER_ENV")) {
         const int v = atoi(force);
         if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) h->lanes_per_env = v;
+    }
+    // two envs per warp: the halves touch the same fields of neighbouring env blocks with the same instruction, so the
+    // blocks are placed half a bank row apart (an odd multiple of 64 bytes): 16 lanes x 4 bytes of one env and of the
+    // other then fall on different banks
+    if (h->lanes_per_env == 16) {
+        int skew = 64;
+        if (const char* force = getenv("ZS_SMEM_SKEW")) skew = atoi(force) & 0x70;
+        while ((p.smem_per_env & 127) != skew) p.smem_per_env += 16;
     }
     // warps per CTA: ZS_WPC, or 2 when the batch is small enough that 4-warp CTAs would spread unevenly over the SMs
     // (a small batch is latency-bound: the most loaded SM sets the pace)

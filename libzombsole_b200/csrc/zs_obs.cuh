@@ -303,7 +303,8 @@ ZS_TPL __device__ __forceinline__ void encode_surroundings(const ZsParams& p, En
     }
 }
 
-ZS_TPL __device__ __forceinline__ void encode_obs(const ZsParams& p, Env& e, int32_t* obs) {
-    if (p.obs_scope == ZS_OBS_WORLD) { obs_world_template<MPC, G, CV>(p, e, obs); obs_world_patch<MPC, G, CV>(p, e, obs); }
+template <int MPC, int G, bool CV, bool SURR>
+__device__ __forceinline__ void encode_obs(const ZsParams& p, Env& e, int32_t* obs) {
+    if constexpr (!SURR) { obs_world_template<MPC, G, CV>(p, e, obs); obs_world_patch<MPC, G, CV>(p, e, obs); }
     else encode_surroundings<MPC, G, CV>(p, e, obs);
 }
