@@ -301,7 +301,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         unsigned long long tot = 0;
         for (int i = 0; i < 13; ++i) tot += zs_ph[i];  // (13.. are inside [10])
         printf("phase cycles/step over %d steps (total %.0f):", io.n_steps, (double)tot / io.n_steps);
-        for (int i = 0; i < 20; ++i) { printf(" [%d] %.0f", i, (double)zs_ph[i] / io.n_steps); zs_ph[i] = 0; }
+        for (int i = 0; i < 24; ++i) { printf(" [%d] %.0f", i, (double)zs_ph[i] / io.n_steps); zs_ph[i] = 0; }
         printf("\n");
     }
 #endif
@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
     e.gshift = wlane & ~(G - 1);
     e.gm = G == 32 ? 0xffffffffu : (0xffffu << e.gshift);
     const int slot = wid * EPW + (wlane / G);
+#ifdef ZS_PHASE_CLOCKS
+    e.ph_last = clock64();
+#endif
     const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;  // (a CTA has ZS_WPC warps, or fewer for small batches)
     if (p.tmpl_smem_off >= 0) {
         // stage the pristine observation planes once per CTA: the source of the per-step TMA bulk copies
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(zs_smem + p.tmpl_smem_off);
         asm volatile("mov.u32 %0, %1;" : "=r"(e.tmpl_saddr) : "r"(a));
     }
+    PH(20);
     e.b = (uint32_t)slot * (uint32_t)p.smem_per_env;
     e.env = env; e.env_global = p.env_base + (uint32_t)env;
     const int lane = e.gl;
@@ -366,8 +370,10 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
         return;
     }
     load_state<MPC, G, CV>(p, e, MODE == MODE_STEP && io.n_steps >= 4);
+    PH(21);
     if (!(MODE == MODE_STEP && io.n_steps >= 4)) e.flags |= FL_DEAD_LAUNCH;
     build_grid<MPC, G, false>(p, id_of(e), e.flags);
+    PH(22);
     if (MODE == MODE_ENCODE) {
         encode_obs<MPC, G, CV, SURR>(p, e, io.obs + (size_t)env * p.obs_elems);
         return;
@@ -378,7 +384,11 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
 #endif
     if constexpr (ONE) step_loop_one<MPC, G, CV, FAST, SURR>(p, io, e);
     else step_loop_general<MPC, G, CV, SURR>(p, io, e);
+#ifdef ZS_PHASE_CLOCKS
+    e.ph_last = clock64();
+#endif
     store_state<MPC, G, CV>(p, e);
+    PH(23);
 }
 
 __global__ void zs_init_static_life_kernel(const __grid_constant__ ZsParams p) {

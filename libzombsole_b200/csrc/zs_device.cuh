@@ -256,7 +256,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // them at the end of the launch (tools/phase_clocks.sh) — the latency chain of one warp, which is what bounds
 // small batches.
 #ifdef ZS_PHASE_CLOCKS
-__device__ unsigned long long zs_ph[20];
+__device__ unsigned long long zs_ph[24];  // 0-19: the step loop; 20-23: staging, load_state, build_grid, store_state
 #define PH(i)                                                                         \
     do {                                                                              \
         if (blockIdx.x == 0 && threadIdx.x == 0) {                                    \
