@@ -118,13 +118,15 @@ ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId
     ZS_VIEWS;
     const uint4* life4 = reinterpret_cast<const uint4*>(SLP);
     const uint4* max4 = reinterpret_cast<const uint4*>(p.static_max);
+    const uint4* cell4 = reinterpret_cast<const uint4*>(p.static_cell);
     const int n8 = p.Sp >> 3;
     int n = 0;
 #pragma unroll 1
     for (int i0 = 0; i0 < n8; i0 += G) {
         const int i8 = i0 + e.gl;
         uint4 lv = make_uint4(0u, 0u, 0u, 0u), mv = lv;
-        if (i8 < n8) { lv = life4[i8]; mv = __ldg(max4 + i8); }
+        uint4 cv = lv;  // the cells of the eight (issued with the lives: an entry then needs no trip of its own)
+        if (i8 < n8) { lv = life4[i8]; mv = __ldg(max4 + i8); cv = __ldg(cell4 + i8); }
         const bool differs = ((lv.x ^ mv.x) | (lv.y ^ mv.y) | (lv.z ^ mv.z) | (lv.w ^ mv.w)) != 0u;
         uint32_t sx0 = 0u, sx1 = 0u;  // the eight SIDX bytes of this lane's boxes/walls
         if (gany<G, CV>(e, differs)) {
@@ -160,7 +162,8 @@ ZS_TPL __device__ __noinline__ int scan_damaged_statics(const ZsParams& p, GrpId
                 const int k = __ffs(mm) - 1;
                 bool listed;
                 const int pay = pay_of(k, listed);
-                SPL(pos) = (uint32_t)__ldg(p.static_cell + i8 * 8 + k) | ((uint32_t)pay << 16);
+                const uint32_t cw = k < 2 ? cv.x : k < 4 ? cv.y : k < 6 ? cv.z : cv.w;
+                SPL(pos) = ((cw >> (16 * (k & 1))) & 0xffffu) | ((uint32_t)pay << 16);
                 const uint32_t sb = (uint32_t)(pos + 1 < SIDX_FAR ? pos + 1 : SIDX_FAR) << (8 * (k & 3));
                 if (k < 4) sx0 |= sb; else sx1 |= sb;
                 ++pos;
