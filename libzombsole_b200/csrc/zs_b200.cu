@@ -792,7 +792,9 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     }
     // two envs per warp: the halves touch the same fields of neighbouring env blocks with the same instruction, so the
     // blocks are placed half a bank row apart (an odd multiple of 64 bytes): 16 lanes x 4 bytes of one env and of the
-    // other then fall on different banks
+    // other then fall on different banks.  (Swept on the bridge map, ZS_SMEM_SKEW = 0 .. 112: no measurable difference
+    // either way — the step is bound by dependent latency, not by shared-memory wavefronts; it fixes the layout so that
+    // a change of sizeof(EnvS) cannot move the two halves onto the same banks.)
     if (h->lanes_per_env == 16) {
         int skew = 64;
         if (const char* force = getenv("ZS_SMEM_SKEW")) skew = atoi(force) & 0x70;
