@@ -105,7 +105,8 @@ class MultiagentZombsoleVectorEnv(object):
         """One transition of every world (multiagent_env.py:111-171); discrete id -1 = key missing."""
         a, fmt = self._stage_actions(actions)
         self.engine.step(a, fmt, self.obs, self.reward, self._term, self._trunc, self._mask)
-        return self.obs, self.reward, self._term.bool(), self._trunc.bool(), {"agent_mask": self._mask.bool()}
+        return (self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool),
+                {"agent_mask": self._mask.view(torch.bool)})  # (0/1 bytes: views, no kernels)
 
     def reset(self, seed=None, options=None, mask=None):
         self.engine.reset(mask, self.obs)

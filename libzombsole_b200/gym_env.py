@@ -132,7 +132,7 @@ class ZombsoleVectorEnv(object):
         self.engine.step(a, fmt, self.obs, self.reward, self._term, self._trunc)
         if self.host_outputs:
             torch.cuda.current_stream(self.device).synchronize()  # the host owns the results when step() returns
-        return self.obs, self.reward, self._term.bool(), self._trunc.bool(), {}
+        return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}  # (0/1 bytes: a view, no kernel)
 
     def reset(self, seed=None, options=None, mask=None):
         """Re-initialise every world (or those selected by ``mask``); gym_env.py:148-164.  ``seed`` is
