@@ -8,7 +8,8 @@ import os
 
 from . import abi
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libzs_b200.so")
+#: ZS_B200_LIB points at another build of the same library (development: comparing two builds on one box)
+LIB_PATH = os.environ.get("ZS_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libzs_b200.so")
 _lib = None
 
 

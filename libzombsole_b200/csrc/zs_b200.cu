@@ -295,6 +295,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         }
         gsync<G, CV>(e);
         PH(11);
+        TR(4 + step);
     }
 #ifdef ZS_PHASE_CLOCKS
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
 #endif
+    if (MODE == MODE_STEP) { TR(0); TR(31); }
     const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;  // (a CTA has ZS_WPC warps, or fewer for small batches)
     if (p.tmpl_smem_off >= 0) {
         // stage the pristine observation planes once per CTA: the source of the per-step TMA bulk copies
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
         asm volatile("mov.u32 %0, %1;" : "=r"(e.tmpl_saddr) : "r"(a));
     }
     PH(20);
+    if (MODE == MODE_STEP) TR(1);
     e.b = (uint32_t)slot * (uint32_t)p.smem_per_env;
     e.env = env; e.env_global = p.env_base + (uint32_t)env;
     const int lane = e.gl;
@@ -371,9 +374,11 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
     }
     load_state<MPC, G, CV>(p, e, MODE == MODE_STEP && io.n_steps >= 4);
     PH(21);
+    if (MODE == MODE_STEP) TR(2);
     if (!(MODE == MODE_STEP && io.n_steps >= 4)) e.flags |= FL_DEAD_LAUNCH;
     build_grid<MPC, G, false>(p, id_of(e), e.flags);
     PH(22);
+    if (MODE == MODE_STEP) TR(3);
     if (MODE == MODE_ENCODE) {
         encode_obs<MPC, G, CV, SURR>(p, e, io.obs + (size_t)env * p.obs_elems);
         return;
@@ -389,6 +394,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
 #endif
     store_state<MPC, G, CV>(p, e);
     PH(23);
+    TR(30);
 }
 
 __global__ void zs_init_static_life_kernel(const __grid_constant__ ZsParams p) {
@@ -444,6 +450,7 @@ static int fail(const char* fmt, const char* a = "") {
     } while (0)
 
 struct ZsHandle {
+    int device;  // the CUDA device the handle was created on: every entry point runs there, whatever is current
     ZsConfig cfg;
     ZsLayout lay;
     ZsParams p;
@@ -456,6 +463,19 @@ struct ZsHandle {
     int warps_per_cta;
     int occ;
     int smem_bytes;
+};
+
+// Makes the handle's device current for the duration of an entry point and puts the caller's back afterwards: the
+// stream, the map tables, the kernels' function attributes and the state buffer all belong to that device.
+struct DeviceGuard {
+    int prev = -1, cur = -1;
+    explicit DeviceGuard(const ZsHandle* h) {
+        if (!h) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        cur = h->device;
+        if (prev != cur) cudaSetDevice(cur);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
 };
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -643,7 +663,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     CU(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10) return fail("this library is built for sm_100a (B200) only");
     ZsHandle* h = new ZsHandle();
-    h->cfg = *cfg; h->lay = lay; h->launches = 0; h->bound_bytes = 0; h->sm_count = prop.multiProcessorCount;
+    h->device = dev; h->cfg = *cfg; h->lay = lay; h->launches = 0; h->bound_bytes = 0; h->sm_count = prop.multiProcessorCount;
     ZsParams& p = h->p;
     memset(&p, 0, sizeof(p));
     p.N = cfg->num_envs; p.env_base = (uint32_t)cfg->env_index_base;
@@ -854,6 +874,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
 
 extern "C" __attribute__((visibility("default"))) int zs_destroy(ZsHandle* h) {
     if (!h) return 0;
+    DeviceGuard guard(h);
     cudaDeviceSynchronize();
     for (void* d : h->dev_allocs) cudaFree(d);
     delete h;
@@ -889,12 +910,14 @@ static int launched(ZsHandle* h) {
 
 extern "C" __attribute__((visibility("default"))) int zs_init_static_life(ZsHandle* h, void* stream) {
     if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
     zs_init_static_life_kernel<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(h->p);
     return launched(h);
 }
 
 extern "C" __attribute__((visibility("default"))) int zs_reset(ZsHandle* h, const uint8_t* env_mask_dev, int32_t* obs_dev, int32_t* draws_dev, void* stream) {
     if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
     ZsIO io;
     memset(&io, 0, sizeof(io));
     io.env_mask = env_mask_dev; io.obs = obs_dev; io.obs_slots = 1; io.draws = draws_dev;
@@ -905,6 +928,7 @@ extern "C" __attribute__((visibility("default"))) int zs_reset(ZsHandle* h, cons
 extern "C" __attribute__((visibility("default"))) int zs_step(ZsHandle* h, const int32_t* actions_dev, int32_t action_format, int32_t* obs_dev, double* reward_dev,
                        uint8_t* terminated_dev, uint8_t* truncated_dev, uint8_t* agent_mask_dev, int32_t* draws_dev, void* stream) {
     if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
     if (!actions_dev) return fail("zs_step needs an action tensor");
     if (action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
     ZsIO io;
@@ -918,6 +942,7 @@ extern "C" __attribute__((visibility("default"))) int zs_step(ZsHandle* h, const
 
 extern "C" __attribute__((visibility("default"))) int zs_encode_obs(ZsHandle* h, int32_t* obs_dev, void* stream) {
     if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
     if (!obs_dev) return fail("null obs");
     ZsIO io;
     memset(&io, 0, sizeof(io));
@@ -930,6 +955,7 @@ extern "C" __attribute__((visibility("default"))) int zs_rollout(ZsHandle* h, in
                           int32_t action_format, int32_t* obs_dev, int32_t obs_slots, double* reward_dev,
                           uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream) {
     if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
     if (n_steps < 1) return fail("n_steps must be >= 1");
     if (obs_dev && obs_slots < 1) return fail("obs_slots must be >= 1");
     if (actions_dev && action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
@@ -945,6 +971,7 @@ extern "C" __attribute__((visibility("default"))) int zs_rollout(ZsHandle* h, in
 extern "C" __attribute__((visibility("default"))) int zs_fill_synthetic_actions(ZsHandle* h, int64_t step_index, int32_t* actions_dev, void* stream) {
     if (!h) return fail("null handle");
     if (!actions_dev) return fail("null actions");
+    DeviceGuard guard(h);
     const int n = h->p.N * h->p.A;
     int blocks = (n + 255) / 256;
     if (blocks > h->sm_count * 8) blocks = h->sm_count * 8;
@@ -955,9 +982,20 @@ extern "C" __attribute__((visibility("default"))) int zs_fill_synthetic_actions(
 extern "C" __attribute__((visibility("default"))) int zs_episode_stats(ZsHandle* h, int64_t* out_dev, int32_t reset, void* stream) {
     if (!h) return fail("null handle");
     if (!out_dev) return fail("null out");
+    DeviceGuard guard(h);
     zs_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->p.stats, out_dev, reset);
     return launched(h);
 }
+
+#ifdef ZS_TRACE
+// development builds: copy the launch trace (zs_device.cuh: TR) to host memory [ZS_TRACE_WARPS][ZS_TRACE_SLOTS] uint64
+extern "C" __attribute__((visibility("default"))) int zs_debug_trace(unsigned long long* out_host, int32_t clear) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out_host, zs_trace_buf, sizeof(unsigned long long) * ZS_TRACE_WARPS * ZS_TRACE_SLOTS));
+    if (clear) { void* d = nullptr; CU(cudaGetSymbolAddress(&d, zs_trace_buf)); CU(cudaMemset(d, 0, sizeof(unsigned long long) * ZS_TRACE_WARPS * ZS_TRACE_SLOTS)); }
+    return 0;
+}
+#endif
 
 extern "C" __attribute__((visibility("default"))) int64_t zs_launch_count(const ZsHandle* h) { return h ? h->launches : 0; }
 extern "C" __attribute__((visibility("default"))) int32_t zs_lanes_per_env(const ZsHandle* h) { return h ? h->lanes_per_env : 0; }

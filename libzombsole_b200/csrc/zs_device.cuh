@@ -269,6 +269,25 @@ __device__ unsigned long long zs_ph[24];  // 0-19: the step loop; 20-23: staging
 #define PH(i) do { } while (0)
 #endif
 
+// ---------------------------------------------------------------- launch trace (development builds only)
+// -DZS_TRACE: lane 0 of every warp of a step launch records the global timer at kernel entry, after each part of the
+// prologue, after each of the first 24 steps and at exit (tools/trace_launch.sh): where a launch's fixed cost goes.
+#ifdef ZS_TRACE
+#define ZS_TRACE_WARPS 8192
+#define ZS_TRACE_SLOTS 32
+__device__ unsigned long long zs_trace_buf[ZS_TRACE_WARPS * ZS_TRACE_SLOTS];
+__device__ __forceinline__ unsigned long long zs_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned zs_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define TR(i)                                                                                         \
+    do {                                                                                              \
+        const int _w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);                           \
+        if ((threadIdx.x & 31) == 0 && _w < ZS_TRACE_WARPS && (i) < ZS_TRACE_SLOTS)                   \
+            zs_trace_buf[_w * ZS_TRACE_SLOTS + (i)] = (i) == 31 ? (unsigned long long)zs_smid() : zs_globaltimer(); \
+    } while (0)
+#else
+#define TR(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- lane-group primitives
 // G = lanes per env.  With G == 16 a *.sync primitive on the half warp's own member mask costs a convergence
 // check (MATCH.ANY + REDUX + VOTEU + branch) in front of every use, which made two envs per warp slower than one.

@@ -633,12 +633,15 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                     } else { type = D_ATTACK; a = tg; }
                 }
             } else {  // Agent.next_step (players/agent.py:28-96)
-                if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + adx; b = y + ady; }
+                // (a step of two cells or more fails whatever its length, core.py:149-153: deltas are clamped to +-2 so
+                // that an unchecked user value can neither overflow nor wrap in the 16-bit hand-off below)
+                if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + max(-2, min(2, adx)); b = y + max(-2, min(2, ady)); }
                 else if (at == ZS_ACT_ATTACK_CLOSEST) { if (tg >= 0) { type = D_ATTACK; a = tg; } }
                 else if (at == ZS_ACT_HEAL_CLOSEST) { type = D_HEAL; a = tg >= 0 ? tg : s; }
                 else if (at == ZS_ACT_ATTACK || at == ZS_ACT_HEAL) {
                     if (at == ZS_ACT_HEAL && adx == 0 && ady == 0) { type = D_HEAL; a = s; }
                     else {
+                        adx = max(-4096, min(4096, adx)); ady = max(-4096, min(4096, ady));  // (off the map either way)
                         const int g = grid_at(p, GRIDP, x + adx, y + ady);
                         // attack: any thing; heal: Player / Box / Wall only (agent.py:69-75)
                         const bool ok = at == ZS_ACT_ATTACK ? g_is_thing(g)
@@ -820,6 +823,8 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     // indices); a chunk sees the world the chunks before it left.  A move into a cell whose occupant moves earlier in
     // the SAME chunk sends that chunk through the sequential loop.
     const unsigned below_l = (1u << lane) - 1u;
+    int16_t* const KILL = S.da;  // boxes/walls whose life fell to <= 0 during this step (DA is free once the words are built;
+    int nk = 0;                  // at most one entry per hit: <= L <= MPC; repeats allowed)
 #pragma unroll 1
     for (int base = 0; base < L; base += 32) {
         const int q = base + lane;  // list position
@@ -833,7 +838,7 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
         if (kind == X_MOVE && g0 >= 1 && g0 <= G_MAX_SLOT) { const int mp = S.mpos[g0 - 1]; need_seq = mp >= base && mp < q; }
         if (gany<G, CV>(e, need_seq)) {
             if (lane == 0) {  // this chunk in list order on shared memory
-                int fl = e.flags, deaths = e.deaths, n_touched = 0;
+                int fl = e.flags, n_touched = 0;
                 const int end = base + 32 < L ? base + 32 : L;
 #pragma unroll 1
                 for (int i = base; i < end; ++i) {
@@ -874,23 +879,24 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                         fl |= FL_SL_DIRTY;
                     }
                 }
-                // the boxes/walls hit in this chunk: their patch-list entries, and clean_dead_things (core.py:121-138) for
-                // the ones destroyed now (on the first step of a world the clean phase below covers them)
+                // the boxes/walls hit in this chunk: their patch-list entries.  A box/wall destroyed now stays in
+                // World.things — later movers still bump into it, a heal may bring it back — until clean_dead_things
+                // (core.py:121-138): it is only remembered here (KILL) and leaves in the clean phase below.
 #pragma unroll 1
                 for (int i = 0; i < n_touched; ++i) {
                     const int si = LIST(i);
                     const int cell = __ldg(p.static_cell + si);
                     const int life = SL(si);
                     const bool fresh = fl & FL_FRESH;
-                    if (life <= 0 && !fresh && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; deaths++; }
+                    if (life <= 0 && !fresh && g_is_static(GRID(cell))) KILL[nk++] = (int16_t)si;
                     spl_update_one<MPC, G, CV>(p, e, si, cell, life, life > 0 || fresh);
                 }
                 if (SPN) fl |= FL_DMG;
-                e.flags = fl; e.deaths = deaths;
+                e.flags = fl;
             }
             k = gbcast<G, CV>(e, k, 0);
             nmv = gbcast<G, CV>(e, nmv, 0);
-            e.deaths = gbcast<G, CV>(e, e.deaths, 0);
+            nk = gbcast<G, CV>(e, nk, 0);
             e.flags = gbcast<G, CV>(e, e.flags, 0);
             gsync<G, CV>(e);
             continue;
@@ -951,13 +957,14 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
                     const int mx = __ldg(p.static_max + si);
                     const bool fresh = e.flags & FL_FRESH;
                     cell = __ldg(p.static_cell + si);
-                    gone = life <= 0 && !fresh && g_is_static(GRID(cell));
-                    if (gone) GRID(cell) = G_EMPTY;
+                    gone = life <= 0 && !fresh && g_is_static(GRID(cell));  // (leaves in the clean phase: see KILL above)
                     pay = static_payload(p, mx, life, life > 0 || fresh);
                     idx = SIDX(si);
                     is_new = idx == 0 && pay != static_payload(p, mx, mx, true);
                 }
-                e.deaths += __popc(gballot<G, CV>(e, gone));
+                const unsigned gone_m = gballot<G, CV>(e, gone);
+                if (gone) KILL[nk + __popc(gone_m & below_l)] = (int16_t)si;
+                nk += __popc(gone_m);
                 e.flags |= FL_SL_DIRTY;
                 const unsigned new_m = gballot<G, CV>(e, is_new);
                 const int n0 = SPN;
@@ -981,6 +988,21 @@ ZS_TPL __device__ __forceinline__ int world_step(const ZsParams& p, Env& e) {
     if (e.flags & FL_FRESH) {  // first step of this world: every box/wall with life <= 0 leaves now
         if (e.flags & FL_DMG) nd_all = spl_clean_fresh<MPC, G, CV>(p, e);
         e.flags &= ~FL_FRESH;
+    } else if (nk > 0) {
+        // the boxes/walls destroyed during execute_actions leave now, unless a later heal brought them back (rare: one
+        // lane walks the few candidates; a box/wall listed twice is gone from the grid the second time)
+        if (lane == 0) {
+#pragma unroll 1
+            for (int i = 0; i < nk; ++i) {
+                const int si = KILL[i];
+                const int cell = __ldg(p.static_cell + si);
+                const int life = SL(si);
+                if (life <= 0 && g_is_static(GRID(cell))) { GRID(cell) = G_EMPTY; ++nd_all; }
+                // (the patch-list payload follows the final life: a hit wrote "gone" while the life was <= 0)
+                else if (life > 0) spl_update_one<MPC, G, CV>(p, e, si, cell, life, true);
+            }
+        }
+        gsync<G, CV>(e);
     }
     for (int w = e.gl; w < 2 * rw; w += G) MASKW(w) = 0u;
     gsync<G, CV>(e);
@@ -1229,12 +1251,14 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
                 type = D_RANDOM;
             }
         } else {  // Agent.next_step (players/agent.py:28-96)
-            if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + adx; b = y + ady; }
+            // (a step of two cells or more fails whatever its length, core.py:149-153: clamped, so nothing can overflow)
+            if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + max(-2, min(2, adx)); b = y + max(-2, min(2, ady)); }
             else if (at == ZS_ACT_ATTACK_CLOSEST) { if (tg >= 0) { type = D_ATTACK; a = tg; } }
             else if (at == ZS_ACT_HEAL_CLOSEST) { type = D_HEAL; a = tg >= 0 ? tg : s; }
             else if (at == ZS_ACT_ATTACK || at == ZS_ACT_HEAL) {
                 if (at == ZS_ACT_HEAL && adx == 0 && ady == 0) { type = D_HEAL; a = s; }
                 else {
+                    adx = max(-4096, min(4096, adx)); ady = max(-4096, min(4096, ady));  // (off the map either way)
                     const int g = grid_at(p, GRIDP, x + adx, y + ady);
                     // attack: any thing; heal: Player / Box / Wall only (agent.py:69-75)
                     const bool ok = at == ZS_ACT_ATTACK ? g_is_thing(g)

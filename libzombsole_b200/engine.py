@@ -103,30 +103,73 @@ class ZsEngine(object):
                 torch.empty((self.N,), dtype=torch.uint8).pin_memory(),
                 torch.empty((self.N,), dtype=torch.uint8).pin_memory())
 
+    # ------------------------------------------------------------------ the ABI boundary: what the kernels may be handed
+    _FLAG_DTYPES = (torch.uint8, torch.bool)
+
+    def _arg(self, t, dtypes, numel, name):
+        """Pointer of a tensor argument after checking that the kernels can take it as it is: on this engine's device
+        (or pinned host memory, which the device reaches at the same address), the right element type, contiguous, and
+        at least as large as what the launch reads or writes.  The C ABI sees raw pointers; a wrong tensor would be
+        misread or overrun."""
+        if t is None:
+            return None
+        if not isinstance(t, torch.Tensor):
+            raise ValueError("%s must be a torch tensor, got %s" % (name, type(t).__name__))
+        if not isinstance(dtypes, tuple):
+            dtypes = (dtypes,)
+        if t.dtype not in dtypes:
+            raise ValueError("%s must be %s, got %s" % (name, " or ".join(str(d) for d in dtypes), t.dtype))
+        if t.device != self.device and not (t.device.type == "cpu" and t.is_pinned()):
+            raise ValueError("%s must live on %s (or in pinned host memory), got %s" % (name, self.device, t.device))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous" % name)
+        if t.numel() < numel:
+            raise ValueError("%s must hold at least %d elements, got %d (shape %s)" % (name, numel, t.numel(), tuple(t.shape)))
+        return t.data_ptr()
+
+    def _action_arg(self, actions, fmt, n_steps):
+        if fmt not in (abi.ACTIONS_DISCRETE, abi.ACTIONS_FULL):
+            raise ValueError("bad action format %r" % (fmt,))
+        per = 3 if fmt == abi.ACTIONS_FULL else 1
+        return self._arg(actions, torch.int32, n_steps * self.N * self.A * per, "actions")
+
     # ------------------------------------------------------------------ the ABI calls
     def reset(self, mask=None, obs=None):
         """zs_reset: re-initialise the masked worlds (all if mask is None)."""
         if mask is not None:
-            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        check(self.L.zs_reset(self.h, _ptr(mask), _ptr(obs), _ptr(self.reset_draws), self._stream()))
+            mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self.L.zs_reset(self.h, self._arg(mask, torch.uint8, self.N, "mask"),
+                              self._arg(obs, torch.int32, self.N * self.obs_elems, "obs"), _ptr(self.reset_draws),
+                              self._stream()))
         return obs
 
     def step(self, actions, fmt, obs, reward, terminated, truncated, agent_mask=None, draws=None):
-        check(self.L.zs_step(self.h, _ptr(actions), fmt, _ptr(obs), _ptr(reward), _ptr(terminated), _ptr(truncated),
-                             _ptr(agent_mask), _ptr(draws), self._stream()))
+        N = self.N
+        check(self.L.zs_step(self.h, self._action_arg(actions, fmt, 1), fmt,
+                             self._arg(obs, torch.int32, N * self.obs_elems, "obs"),
+                             self._arg(reward, torch.float64, N * self.R, "reward"),
+                             self._arg(terminated, self._FLAG_DTYPES, N, "terminated"),
+                             self._arg(truncated, self._FLAG_DTYPES, N, "truncated"),
+                             self._arg(agent_mask, self._FLAG_DTYPES, N * self.A, "agent_mask"),
+                             self._arg(draws, torch.int32, N, "draws"), self._stream()))
 
     def encode_obs(self, obs):
-        check(self.L.zs_encode_obs(self.h, _ptr(obs), self._stream()))
+        check(self.L.zs_encode_obs(self.h, self._arg(obs, torch.int32, self.N * self.obs_elems, "obs"), self._stream()))
         return obs
 
     def rollout(self, n_steps, first_step_index=0, actions=None, fmt=abi.ACTIONS_DISCRETE, obs=None, reward=None,
                 terminated=None, truncated=None):
+        n_steps, N = int(n_steps), self.N
         slots = 0 if obs is None else (obs.shape[0] if obs.dim() == len(self.obs_shape) + 2 else 1)
-        check(self.L.zs_rollout(self.h, int(n_steps), int(first_step_index), _ptr(actions), fmt, _ptr(obs), slots,
-                                _ptr(reward), _ptr(terminated), _ptr(truncated), self._stream()))
+        check(self.L.zs_rollout(self.h, n_steps, int(first_step_index), self._action_arg(actions, fmt, n_steps), fmt,
+                                self._arg(obs, torch.int32, max(1, slots) * N * self.obs_elems, "obs"), slots,
+                                self._arg(reward, torch.float64, n_steps * N * self.R, "reward"),
+                                self._arg(terminated, self._FLAG_DTYPES, n_steps * N, "terminated"),
+                                self._arg(truncated, self._FLAG_DTYPES, n_steps * N, "truncated"), self._stream()))
 
     def fill_synthetic_actions(self, step_index, actions):
-        check(self.L.zs_fill_synthetic_actions(self.h, int(step_index), _ptr(actions), self._stream()))
+        check(self.L.zs_fill_synthetic_actions(self.h, int(step_index),
+                                               self._arg(actions, torch.int32, self.N * self.A, "actions"), self._stream()))
         return actions
 
     def episode_stats(self, reset=False):

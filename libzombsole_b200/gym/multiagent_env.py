@@ -72,6 +72,7 @@ class MultiagentZombsoleVectorEnv(object):
         self.reward, self._term, self._trunc = self.engine.new_outputs()
         self._mask = torch.ones((num_envs, self.num_agents), dtype=torch.uint8, device=self.device)
         self._actions = torch.zeros((num_envs, self.num_agents, 3), dtype=torch.int32, device=self.device)
+        self._h2d_done, self._h2d_pending = None, False
 
     def game(self, env=0):
         rules_name, player_names, agent_ids, iz, mz = self._ctor
@@ -93,7 +94,12 @@ class MultiagentZombsoleVectorEnv(object):
             return self._actions, abi.ACTIONS_FULL
         t = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
         if t.dtype != torch.int32 or t.device != self.device:
+            pinned_src = t.device.type == "cpu" and t.is_pinned()
             t = t.to(device=self.device, dtype=torch.int32, non_blocking=True)
+            if pinned_src:  # the copy is in flight: step() waits for it before the caller may refill the buffer
+                self._h2d_done = self._h2d_done or torch.cuda.Event()
+                self._h2d_done.record(torch.cuda.current_stream(self.device))
+                self._h2d_pending = True
         t = t.contiguous()
         if t.numel() == N * A:
             return t.view(N, A), abi.ACTIONS_DISCRETE
@@ -105,6 +111,9 @@ class MultiagentZombsoleVectorEnv(object):
         """One transition of every world (multiagent_env.py:111-171); discrete id -1 = key missing."""
         a, fmt = self._stage_actions(actions)
         self.engine.step(a, fmt, self.obs, self.reward, self._term, self._trunc, self._mask)
+        if self._h2d_pending:  # a pinned host action buffer is the caller's again when step() returns
+            self._h2d_done.synchronize()
+            self._h2d_pending = False
         return (self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool),
                 {"agent_mask": self._mask.view(torch.bool)})  # (0/1 bytes: views, no kernels)
 

@@ -94,6 +94,7 @@ class ZombsoleVectorEnv(object):
             self.obs = self.engine.new_obs()
             self.reward, self._term, self._trunc = self.engine.new_outputs()
         self._actions = torch.zeros((num_envs, 1, 3), dtype=torch.int32, device=self.device)
+        self._h2d_done, self._h2d_pending = None, False
 
     # -- the reference's object protocol for one world of the batch
     def game(self, env=0):
@@ -117,7 +118,12 @@ class ZombsoleVectorEnv(object):
         if self.host_outputs and t.dtype == torch.int32 and t.device.type == "cpu" and t.is_pinned():
             pass  # the kernel reads a pinned host action tensor in place
         elif t.dtype != torch.int32 or t.device != self.device:
+            pinned_src = t.device.type == "cpu" and t.is_pinned()
             t = t.to(device=self.device, dtype=torch.int32, non_blocking=True)
+            if pinned_src:  # the copy is in flight: step() waits for it before the caller may refill the buffer
+                self._h2d_done = self._h2d_done or torch.cuda.Event()
+                self._h2d_done.record(torch.cuda.current_stream(self.device))
+                self._h2d_pending = True
         t = t.contiguous()
         if t.numel() == self.num_envs:
             return t.view(self.num_envs, 1), abi.ACTIONS_DISCRETE
@@ -130,6 +136,9 @@ class ZombsoleVectorEnv(object):
         output buffers: they are overwritten by the next call."""
         a, fmt = self._stage_actions(actions)
         self.engine.step(a, fmt, self.obs, self.reward, self._term, self._trunc)
+        if self._h2d_pending:  # a pinned host action buffer is the caller's again when step() returns
+            self._h2d_done.synchronize()
+            self._h2d_pending = False
         if self.host_outputs:
             torch.cuda.current_stream(self.device).synchronize()  # the host owns the results when step() returns
         return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}  # (0/1 bytes: a view, no kernel)

@@ -46,6 +46,7 @@ PLAN = {
     "bots_hamsters": (2, 100, 0),
     "bots_randoman": (2, 120, 0),
     "randoman_crowd": (2, 60, 0),
+    "box_arena": (2, 60, 0),
 }
 
 

@@ -1,7 +1,12 @@
 """Shared helpers of the parity tests: config dicts, action tapes, record comparison."""
+import os
+
 import numpy as np
 
 from libzombsole_b200 import abi
+
+#: test-only maps (the reference takes an absolute path as map_name: os.path.join keeps it, gym_env.py:54-56)
+MAPS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "maps")
 
 #: parity configurations: BASELINE.json's five configs at small N, plus edge-case variants
 CONFIGS = {
@@ -72,6 +77,13 @@ CONFIGS = {
     "no_zombies": dict(kind="single", rules_name="extermination", player_names=["terminator"], map_name="hallway",
                        agent_ids=[0], agent_weapons="axe", initial_zombies=0, minimum_zombies=0,
                        observation_scope="world", observation_position_encoding="channels"),
+    # boxes destroyed and healed back in the middle of execute_actions with more than 32 actions per step (two chunks of
+    # the general kernel): 24 agents with knives (a box survives a hit or two), axes and shotguns on a checkerboard of boxes
+    # and spawn cells, 30 zombies; the tape is attacks / moves / heals at adjacent offsets (tape="adjacent").  A destroyed
+    # box stays in World.things until clean_dead_things (core.py:121-138): later movers bump into it, a heal revives it.
+    "box_arena": dict(kind="multi", rules_name="survival", player_names=[], map_name=os.path.join(MAPS_DIR, "box_arena.txt"),
+                      agent_ids=[str(i) for i in range(24)], agent_weapons=["knife", "axe", "knife", "shotgun"],
+                      initial_zombies=30, minimum_zombies=0, surroundings_width=5, tape="adjacent"),
     "minz_allcells": dict(kind="multi", rules_name="extermination", player_names=[], map_name="village_for_evacuation",
                           agent_ids=["0", "1"], agent_weapons="random", initial_zombies=4, minimum_zombies=6,
                           surroundings_width=21),
@@ -102,6 +114,22 @@ def action_tape(cfgd, T, seed, wild=0.25):
     multi = cfgd["kind"] == "multi"
     A = len(cfgd["agent_ids"])
     acts = np.zeros((T, A, 3), np.int32)
+    if cfgd.get("tape") == "adjacent":
+        adj = [(0, 1), (0, -1), (1, 0), (-1, 0)]
+        for t in range(T):
+            for a in range(A):
+                u = rs.rand()
+                dx, dy = adj[rs.randint(0, 4)]
+                if u < 0.35:
+                    acts[t, a] = (abi.ACT_ATTACK, dx, dy)
+                elif u < 0.70:
+                    acts[t, a] = (abi.ACT_MOVE, dx, dy)
+                elif u < 0.90:
+                    k = rs.randint(1, 3)  # heal reaches three cells (core.py:8): the box next door or the one behind it
+                    acts[t, a] = (abi.ACT_HEAL, k * dx, k * dy)
+                else:
+                    acts[t, a] = (abi.ACT_ATTACK_CLOSEST, 0, 0)
+        return acts
     for t in range(T):
         for a in range(A):
             if rs.rand() < wild:

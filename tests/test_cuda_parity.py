@@ -79,7 +79,7 @@ CASES = [
     ("c3_city_evac", 32, 120, 0), ("village_evac_mixed", 16, 100, 0), ("c4_maze_safehouse", 8, 40, 0),
     ("safehouse_small", 32, 120, 0), ("multi_boxed_2p", 64, 80, 0), ("multi_fort_32p", 4, 30, 0),
     ("survival_minz", 32, 120, 25), ("minz_allcells", 16, 80, 0), ("bots_mixed", 16, 60, 0), ("bots_hamsters", 32, 120, 0), ("fort_max_slots", 3, 25, 0), ("no_zombies", 16, 30, 0),
-    ("bots_randoman", 64, 150, 0), ("randoman_crowd", 12, 60, 0),
+    ("bots_randoman", 64, 150, 0), ("randoman_crowd", 12, 60, 0), ("box_arena", 96, 60, 0),
 ]
 
 

@@ -13,6 +13,7 @@ CASES = [
     ("gym_surroundings", 80, 0), ("surroundings_channels", 120, 0), ("c3_city_evac", 150, 0),
     ("village_evac_mixed", 120, 0), ("c4_maze_safehouse", 40, 0), ("safehouse_small", 150, 0),
     ("multi_boxed_2p", 120, 0), ("multi_fort_32p", 30, 0), ("survival_minz", 150, 33), ("minz_allcells", 100, 0), ("bots_mixed", 80, 0), ("bots_hamsters", 150, 0), ("fort_max_slots", 12, 0), ("no_zombies", 30, 0),
+    ("box_arena", 50, 0),
 ]
 
 

@@ -1,0 +1,71 @@
+"""Reads the -DZS_TRACE stamps of one K-step launch (tools/trace_launch.sh): per-warp global-timer values at kernel
+entry, after staging / load_state / build_grid, after each of the first steps and at exit."""
+import ctypes as C
+import sys
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import numpy as np
+import torch
+import parity_util as pu
+from libzombsole_b200 import abi, _native
+from libzombsole_b200.engine import ZsEngine
+
+W, S = 8192, 32
+
+
+def grab(L, clear=True):
+    buf = np.zeros((W, S), np.uint64)
+    L.zs_debug_trace.argtypes = [C.c_void_p, C.c_int32]
+    rc = L.zs_debug_trace(buf.ctypes.data, 1 if clear else 0)
+    assert rc == 0
+    return buf
+
+
+def q(a):
+    return "min %7.2f  p50 %7.2f  p90 %7.2f  p99 %7.2f  max %7.2f" % tuple(np.percentile(a, [0, 50, 90, 99, 100]) / 1e3)
+
+
+def main():
+    Ks = [int(a) for a in sys.argv[1:]] or [1, 4, 20]
+    N = 4096
+    cfg, m = pu.build(pu.CONFIGS["c1_bridge_ext"], N, 0, auto_reset=True, max_episode_steps=1000)
+    eng = ZsEngine(cfg, m)
+    L = _native.lib()
+    obs = eng.new_obs(13)
+    KM = max(Ks + [200])
+    rew, term, trunc = eng.new_outputs(KM)
+    acts = torch.zeros((KM, N, 1), dtype=torch.int32, device=eng.device)
+    for s in range(KM):
+        eng.fill_synthetic_actions(s, acts[s])
+    eng.rollout(200, 0, acts, abi.ACTIONS_DISCRETE, obs, rew, term, trunc)
+    torch.cuda.synchronize()
+    for K in Ks:
+        for _ in range(5):  # back to back; the trace keeps the last launch
+            eng.rollout(K, 0, acts, abi.ACTIONS_DISCRETE, obs, rew, term, trunc)
+        torch.cuda.synchronize()
+        t = grab(L)
+        used = t[:, 0] > 0
+        t = t[used].astype(np.int64)
+        t0 = t[:, 0].min()
+        print("K=%d: %d warps on %d SMs; all times in us" % (K, len(t), len(set(t[:, 31].tolist()))))
+        print("  entry after first entry   ", q(t[:, 0] - t0))
+        print("  staging                   ", q(t[:, 1] - t[:, 0]))
+        print("  load_state                ", q(t[:, 2] - t[:, 1]))
+        print("  build_grid                ", q(t[:, 3] - t[:, 2]))
+        prev = t[:, 3]
+        for s in range(min(K, 24)):
+            cur = t[:, 4 + s]
+            print("  step %2d                   " % s, q(cur - prev))
+            prev = cur
+        print("  last traced step -> exit  ", q(t[:, 30] - prev))
+        print("  exit after first entry    ", q(t[:, 30] - t0), "  (kernel span %.2f us)" % ((t[:, 30].max() - t0) / 1e3))
+        # per SM: warps, span
+        sm = t[:, 31]
+        per = [(int(i), int((sm == i).sum()), (t[sm == i, 30].max() - t0) / 1e3) for i in sorted(set(sm.tolist()))]
+        cnt = np.array([p[1] for p in per]); end = np.array([p[2] for p in per])
+        print("  warps per SM: min %d max %d; SM finish time: min %.2f p50 %.2f max %.2f" % (cnt.min(), cnt.max(), end.min(), np.median(end), end.max()))
+        print("  finish time by warps-per-SM:", {int(c): round(float(end[cnt == c].mean()), 2) for c in sorted(set(cnt.tolist()))})
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
