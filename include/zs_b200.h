@@ -170,6 +170,13 @@ int zs_destroy(ZsHandle* h);
 /* Bind the caller-allocated state buffer (>= layout.state_bytes, 16-byte aligned, device). */
 int zs_bind_state(ZsHandle* h, void* state_dev, int64_t bytes);
 
+/* The caller has written into the state buffer (imported a state, edited a life, ...): the handle's parked on-chip
+ * images of the envs (a launch leaves them in device memory and the next one starts from them) are stale, the next
+ * launch re-derives everything from the state buffer.  Not needed after zs_bind_state / zs_init_static_life.
+ * (The reference's counterpart is mutating World.things / thing.life between steps, as its tests do:
+ * tests/test_game.py:41-66.) */
+int zs_state_written(ZsHandle* h);
+
 /* zs_init_static_life: what constructing a new env does before its first world init — every
  * box/wall gets its MAX_LIFE (Map.from_file builds the objects once, game.py:76-79) and the
  * episode counter is set so that the next zs_reset is world initialisation #0 (game.py:138).
@@ -207,6 +214,35 @@ int zs_encode_obs(ZsHandle* h, int32_t* obs_dev, void* stream);
 int zs_rollout(ZsHandle* h, int32_t n_steps, int64_t first_step_index, const int32_t* actions_dev,
                int32_t action_format, int32_t* obs_dev, int32_t obs_slots, double* reward_dev,
                uint8_t* terminated_dev, uint8_t* truncated_dev, void* stream);
+
+/* ---- compact host outputs (world-scope observation, one agent's reward per env)
+ * The world observation of an env is the map's pristine layer (the same for every env and step) plus a few dozen cells
+ * that differ: the mobile things, damaged or destroyed boxes/walls, dead bodies.  zs_step_compact runs one transition
+ * like zs_step but emits, instead of the int32 [N, C, H, W] observation, one fixed-size RECORD per env:
+ *   word 0      bits 0-15 number of entries, bit 16 terminated, bit 17 truncated, bit 18 overflow
+ *   word 1      reserved
+ *   words 2-3   the reward (float64 bits, little endian)
+ *   words 4..   the entries: simple encoding — cell | value << 16; channels — two words: cell | thing << 16, then
+ *               (life & 0xffff) | weapon << 16
+ * so that a step costs about 0.5 KB per env over PCIe instead of 5-16 KB.  An env with more differing cells than a
+ * record holds (or a value that does not fit) sets the overflow bit and gets its full row written to obs_dev, which the
+ * caller fetches for that env alone.  zs_expand_compact (HOST code, threaded) turns the records the caller copied to
+ * host memory into the reference's observation tensor, byte-identical to what zs_step writes: it keeps the previous
+ * records in `prev_host` and only rewrites the cells that changed.  (Reference: observation.py:83-89, 122-142 builds
+ * the same tensor cell by cell; gym_env.py:99-145 returns it with reward and flags.) */
+#define ZS_COMPACT_HEADER 4
+/* words per record for this handle (0 if the configuration has no compact form: surroundings scope, per-agent
+ * observations, more than 32 slots) */
+int32_t zs_compact_words(const ZsHandle* h);
+int zs_step_compact(ZsHandle* h, const int32_t* actions_dev, int32_t action_format, uint32_t* compact_dev,
+                    int32_t* obs_dev, void* stream);
+/* compact_host, prev_host: uint32 [N, zs_compact_words]; obs_host int32 [N, obs_elems_per_env]; reward_host float64 [N];
+ * terminated_host / truncated_host uint8 [N]; overflow_envs_host int32 [N] receives the indices of the envs whose rows
+ * the caller must copy from obs_dev, *n_overflow their number.  first_call != 0: prev_host / obs_host hold nothing yet.
+ * n_threads <= 0: all the host threads of the process. */
+int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t* prev_host, int32_t* obs_host,
+                      double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                      int32_t* overflow_envs_host, int32_t* n_overflow, int32_t first_call, int32_t n_threads);
 
 /* actions_dev int32 [N, A]: uniform discrete ids for step `step_index` (Philox action stream). */
 int zs_fill_synthetic_actions(ZsHandle* h, int64_t step_index, int32_t* actions_dev, void* stream);

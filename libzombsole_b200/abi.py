@@ -72,6 +72,11 @@ PROTOTYPES = {
     "zs_create": (C.c_int, [C.POINTER(ZsConfig), C.POINTER(ZsMap), C.POINTER(C.c_void_p)]),
     "zs_destroy": (C.c_int, [C.c_void_p]),
     "zs_bind_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "zs_state_written": (C.c_int, [C.c_void_p]),
+    "zs_compact_words": (C.c_int32, [C.c_void_p]),
+    "zs_step_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zs_expand_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "zs_init_static_life": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -8,7 +8,8 @@ LIB = os.path.join(CSRC, "libzs_b200.so")
 SOURCES = ["zs_b200.cu"]
 HEADERS = ["zs_device.cuh", "zs_world.cuh", "zs_obs.cuh", os.path.join("..", "..", "include", "zs_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--fmad=false", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--fmad=false", "-cudart", "static",
+              "-Xcompiler", "-fopenmp", "-lgomp"]  # (OpenMP: the host-side expansion of compact observation records)
 
 
 def nvcc_path():

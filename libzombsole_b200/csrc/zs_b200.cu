@@ -2,6 +2,7 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 // No CPU fallback: every entry point that computes launches CUDA kernels.
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -210,9 +211,10 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         if (FAST || obs_out) {
             if (++oslot >= io.obs_slots) { oslot = 0; obs_cur = obs_first; } else obs_cur += obs_stride;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
-            if constexpr (world_obs) obs_world_template<MPC, G, CV>(p, e, obs_out);
+            if constexpr (world_obs) { if (FAST || io.compact == nullptr) obs_world_template<MPC, G, CV>(p, e, obs_out); }
         }
         PH(18);
+        if (step == io.n_steps - 1) TR(24);
         // agents alive before the step: the keys of the reference's per-agent dicts (multiagent_env.py:88-97)
         unsigned alive_before = 0;
         if (want_mask) alive_before = gballot<G, CV>(e, is_agent && TL(is_agent ? lane : 0) > 0) >> P;
@@ -229,6 +231,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
 
         int k = world_step_one<MPC, G, CV>(p, e, my_at, my_dx, my_dy);
         e.ep_steps += 1;
+        if (step == io.n_steps - 1) TR(25);
 
         // ---- reward tracker update (reward.py:30-41, 77-92), float64 in the reference's operation order.
         // A tracker whose inputs did not change yields exactly +0.0.
@@ -277,25 +280,46 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         }
 
         PH(9);
-        // ---- same-step auto-reset (rare, and possibly only one env of the warp: the divergent flavour)
-        if ((done || trunc) && auto_reset) {
-            if (lane == 0) {
+        if (step == io.n_steps - 1) TR(26);
+        // ---- same-step auto-reset
+        const bool need_init = (done || trunc) && auto_reset;
+        if (wany<G, CV>(e, need_init)) {
+            if (need_init && lane == 0) {
                 atomicAdd(p.stats + 0, 1ull);
                 if (done && won) atomicAdd(p.stats + 1, 1ull);
                 atomicAdd(p.stats + 2, (unsigned long long)e.ep_steps);
                 atomicAdd(p.stats + 3, (unsigned long long)e.zd);
             }
-            initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
-            scalars_from_smem<MPC, G, false>(p, e);
+            if (p.fast_init) initialize_world_fast<MPC, G, CV>(p, e, need_init);  // both envs of the warp, converged
+            else if (need_init) {  // possibly only one env of the warp: the divergent flavour
+                initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
+                scalars_from_smem<MPC, G, false>(p, e);
+            }
         }
         PH(10);
-        if (FAST || obs_out) {
+        if (step == io.n_steps - 1) TR(27);
+        bool compacted = false;
+        if constexpr (!FAST && world_obs) {
+            if (io.compact) {  // the observation as a compact record (include/zs_b200.h: zs_step_compact), reward and flags with it
+                compacted = true;
+                uint32_t* const rec = io.compact + (size_t)env * io.compact_words;
+                int n_ent = 0;
+                const bool over = obs_world_compact<MPC, G, CV>(p, e, rec, io.compact_words - ZS_COMPACT_HEADER, n_ent);
+                if (lane == 0) rec[0] = (uint32_t)n_ent | (done ? 1u << 16 : 0u) | (trunc ? 1u << 17 : 0u) | (over ? 1u << 18 : 0u);
+                if (lane_sum ? lane == 0 : aidx == 0) { rec[2] = (uint32_t)__double2loint(rew); rec[3] = (uint32_t)__double2hiint(rew); }
+                if (wany<G, CV>(e, over) && obs_out) {  // rare: the full row, for the caller to fetch
+                    obs_world_template<MPC, G, CV>(p, e, obs_out);
+                    obs_world_patch<MPC, G, CV>(p, e, obs_out);
+                }
+            }
+        }
+        if (!compacted && (FAST || obs_out)) {
             if constexpr (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
             else encode_surroundings<MPC, G, CV>(p, e, obs_out);
         }
         gsync<G, CV>(e);
         PH(11);
-        TR(4 + step);
+        if (step < 20) TR(4 + step);
     }
 #ifdef ZS_PHASE_CLOCKS
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -333,19 +357,18 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
 #endif
     if (MODE == MODE_STEP) { TR(0); TR(31); }
     const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;  // (a CTA has ZS_WPC warps, or fewer for small batches)
+    unsigned long long* const tmpl_bar = reinterpret_cast<unsigned long long*>(zs_smem + p.tmpl_smem_off + (p.tmpl_pair ? 2 : 1) * p.tmpl_bytes);
     if (p.tmpl_smem_off >= 0) {
-        // stage the pristine observation planes once per CTA: the source of the per-step TMA bulk copies
-        uint4* dst = reinterpret_cast<uint4*>(zs_smem + p.tmpl_smem_off);
-        const uint4* src = reinterpret_cast<const uint4*>(p.tmpl_obs);
-        const int n4 = p.cells >> 2, nsrc = (p.tmpl_planes > 1 ? 2 : 1) * n4;
-        const int nrow = p.tmpl_planes * n4;
-        for (int i = threadIdx.x; i < nrow; i += blockDim.x) {
-            const uint4 v = i < nsrc ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
-            dst[i] = v;
-            if (p.tmpl_pair) dst[nrow + i] = v;
+        // stage the pristine observation planes once per CTA, the source of the per-step TMA bulk copies: one thread
+        // asks the TMA for them (global -> shared behind an mbarrier) and the launch goes on; whoever issues the first
+        // observation copy waits for the barrier first
+        if (threadIdx.x == 0) {
+            mbar_init(tmpl_bar, 1);
+            mbar_expect_tx(tmpl_bar, (uint32_t)((p.tmpl_pair ? 2 : 1) * p.tmpl_bytes));
+            bulk_load(zs_smem + p.tmpl_smem_off, p.tmpl_obs, (uint32_t)p.tmpl_bytes, tmpl_bar);
+            if (p.tmpl_pair) bulk_load(zs_smem + p.tmpl_smem_off + p.tmpl_bytes, p.tmpl_obs, (uint32_t)p.tmpl_bytes, tmpl_bar);
         }
-        fence_proxy_async_smem();
-        __syncthreads();
+        __syncthreads();  // (the barrier exists before anybody waits on it)
     }
     if (env >= p.N) return;
     e.tmpl_saddr = 0;
@@ -359,30 +382,45 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
     e.env = env; e.env_global = p.env_base + (uint32_t)env;
     const int lane = e.gl;
     ZS_VIEWS;
+    // the dead-body list is kept (instead of scanning the bitmap) when it lives on: in the parked image, or for a
+    // launch of several steps
+    const bool keep_lists = p.img != nullptr || (MODE == MODE_STEP && io.n_steps >= 4);
 
     if (MODE == MODE_RESET) {
         if (io.env_mask && !io.env_mask[env]) return;
         // slots keep their last position/life until re-placed; bring them in so the store is complete
-        load_state<MPC, G, CV>(p, e, false);
-        e.flags |= FL_DEAD_LAUNCH;
+        if (p.img_load) { load_image_issue<MPC, G, CV>(p, e); load_image_wait<MPC, G, CV>(p, e); }
+        else load_state<MPC, G, CV>(p, e, false);
+        if (!p.img) e.flags |= FL_DEAD_LAUNCH;
         const int k = initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
         scalars_from_smem<MPC, G, CV>(p, e);
         if (io.draws && lane == 0) io.draws[env] = k;
         if (io.obs) encode_obs<MPC, G, CV, SURR>(p, e, io.obs + (size_t)env * p.obs_elems);
         store_state<MPC, G, CV>(p, e);
+        if (p.img) { store_image<MPC, G, CV>(p, e); image_store_drain(e); }
         return;
     }
-    load_state<MPC, G, CV>(p, e, MODE == MODE_STEP && io.n_steps >= 4);
-    PH(21);
-    if (MODE == MODE_STEP) TR(2);
-    if (!(MODE == MODE_STEP && io.n_steps >= 4)) e.flags |= FL_DEAD_LAUNCH;
-    build_grid<MPC, G, false>(p, id_of(e), e.flags);
-    PH(22);
-    if (MODE == MODE_STEP) TR(3);
+    if (p.img_load) {
+        load_image_issue<MPC, G, CV>(p, e);
+        load_image_wait<MPC, G, CV>(p, e);
+        PH(21);
+        if (MODE == MODE_STEP) { TR(2); TR(3); }
+    } else {
+        load_state<MPC, G, CV>(p, e, keep_lists);
+        PH(21);
+        if (MODE == MODE_STEP) TR(2);
+        if (!keep_lists) e.flags |= FL_DEAD_LAUNCH;
+        build_grid<MPC, G, false>(p, id_of(e), e.flags);
+        PH(22);
+        if (MODE == MODE_STEP) TR(3);
+    }
     if (MODE == MODE_ENCODE) {
         encode_obs<MPC, G, CV, SURR>(p, e, io.obs + (size_t)env * p.obs_elems);
         return;
     }
+    // the staged observation planes have landed before the first bulk copy out of them is issued
+    if (p.tmpl_smem_off >= 0 && lane == 0) mbar_wait(tmpl_bar, 0u);
+    if (MODE == MODE_STEP) TR(29);
 
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
@@ -392,7 +430,9 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
 #endif
+    if (p.img) store_image<MPC, G, CV>(p, e);
     store_state<MPC, G, CV>(p, e);
+    if (p.img) image_store_drain(e);
     PH(23);
     TR(30);
 }
@@ -463,6 +503,10 @@ struct ZsHandle {
     int warps_per_cta;
     int occ;
     int smem_bytes;
+    int compact_words;     // words per compact observation record, 0 = this configuration has no compact form
+    std::vector<int32_t> tmpl_obs_host;  // the pristine observation planes [obs_C][cells] (zs_expand_compact)
+    int tmpl_single_step;  // launches of fewer than four steps stage the observation template for the TMA as well
+    bool img_valid;  // the parked images (ZsParams::img) match the canonical state of every env
 };
 
 // Makes the handle's device current for the duration of an entry point and puts the caller's back afterwards: the
@@ -556,10 +600,12 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     int smem = h->smem_bytes;
     // envs in flight chip-wide, roughly: the distance load_state prefetches ahead (a launch of many short-lived CTAs)
     pp.prefetch_ahead = (MODE != MODE_STEP || io.n_steps < 4) && !getenv("ZS_NO_PREFETCH") ? h->sm_count * 7 * h->envs_per_cta : 0;
-    if (MODE != MODE_STEP || io.n_steps < 4) {  // (and without the template a CTA more fits an SM)
+    if (MODE != MODE_STEP || (io.n_steps < 4 && h->tmpl_single_step == 0)) {  // (and without the template a CTA more fits an SM)
         if (pp.tmpl_smem_off >= 0) smem = pp.tmpl_smem_off;
         pp.tmpl_smem_off = -1;
     }
+    // start from the parked images when they are current; a launch that goes through every env leaves them current
+    pp.img_load = pp.img != nullptr && h->img_valid;
     const dim3 grid((pp.N + h->envs_per_cta - 1) / h->envs_per_cta), block(h->warps_per_cta * 32);
     // the standard rollout shape gets the kernel with that shape compiled in (step_loop_one)
     const bool fast = MODE == MODE_STEP && pp.mpc <= 32 && pp.A == 1 && !pp.obs_per_agent && pp.minimum_zombies == 0 &&
@@ -590,6 +636,7 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
 #undef ZS_LAUNCH_G
 #undef ZS_LAUNCH_F
 #undef ZS_LAUNCH
+    if (pp.img != nullptr && (MODE == MODE_STEP || (MODE == MODE_RESET && io.env_mask == nullptr))) const_cast<ZsHandle*>(h)->img_valid = true;
 }
 template <int MPC, int G, int OCC>
 static cudaError_t set_smem_attr_step(int bytes) {
@@ -688,7 +735,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     std::vector<int16_t> cell_static(cells, -1), static_max(p.Sp, 0);
     std::vector<uint16_t> static_cell(p.Sp, 0), ps(p.n_ps), zs(p.n_zs);
     std::vector<uint8_t> static_label(p.Sp, 0), tmpl_grid(p.cells_pad, 0);
-    std::vector<int32_t> tmpl_obs(2 * (size_t)cells, 0);
+    std::vector<int32_t> tmpl_obs(3 * (size_t)cells, 0);  // label (or simple value), life, weapon (zeros) planes
     std::vector<uint32_t> objective_bits(p.dead_words, 0);
     auto cell_of = [&](const int16_t* xy, int i, int* c) {
         int x = xy[2 * i], y = xy[2 * i + 1];
@@ -752,6 +799,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     rc |= upload(h, cell_static, &p.cell_static); rc |= upload(h, static_cell, &p.static_cell);
     rc |= upload(h, static_max, &p.static_max); rc |= upload(h, static_label, &p.static_label);
     rc |= upload(h, tmpl_grid, &p.tmpl_grid); rc |= upload(h, tmpl_obs, &p.tmpl_obs);
+    h->tmpl_obs_host = tmpl_obs;
     rc |= upload(h, objective_bits, &p.objective_bits); rc |= upload(h, ps, &p.ps_cells); rc |= upload(h, zs, &p.zs_cells);
     std::vector<unsigned long long> zero(4, 0ull);
     const unsigned long long* st = nullptr;
@@ -770,6 +818,18 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     // buffer instead of costing resident CTAs (zs_device.cuh: SLP)
     p.sl_global = p.mpc > 32 && p.Sp > 512 && !getenv("ZS_NO_SL_GLOBAL");
     p.off_sl = take(p.sl_global ? 16 : p.Sp * 2);
+    if (p.mpc > 32 && p.Sp > 512) {  // (only the general kernels look at spl_global)
+        p.spl_pitch = p.Sp + (p.Sp + 3) / 4;  // Sp entries, then Sp index bytes
+        void* d = nullptr;
+        if (cudaMalloc(&d, (size_t)p.N * p.spl_pitch * sizeof(uint32_t)) != cudaSuccess) { zs_destroy(h); return fail("out of device memory (static patch lists)"); }
+        h->dev_allocs.push_back(d);
+        p.spl_global = (uint32_t*)d;
+        p.off_spl = take(16); p.off_sidx = take(16);
+    } else {
+        p.off_spl = take(p.Sp * 4);
+        p.off_sidx = take(p.Sp);
+    }
+    // (the spawn candidate list comes last: everything in front of it is the parked image, zs_device.cuh: EnvS)
     int cand = 1;
     if (p.P + p.A > 0) cand = p.n_ps > 0 ? p.n_ps : cells;
     if (p.Z > 0) { int zc = p.n_zs > 0 ? p.n_zs : cells; if (zc > cand) cand = zc; }
@@ -790,18 +850,24 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         p.cand_global = (uint16_t*)d;
         p.off_cand = take(16);
     } else p.off_cand = take(cand * 2);
-    if (p.mpc > 32 && p.Sp > 512) {  // (only the general kernels look at spl_global)
-        p.spl_pitch = p.Sp + (p.Sp + 3) / 4;  // Sp entries, then Sp index bytes
-        void* d = nullptr;
-        if (cudaMalloc(&d, (size_t)p.N * p.spl_pitch * sizeof(uint32_t)) != cudaSuccess) { zs_destroy(h); return fail("out of device memory (static patch lists)"); }
-        h->dev_allocs.push_back(d);
-        p.spl_global = (uint32_t*)d;
-        p.off_spl = take(16); p.off_sidx = take(16);
-    } else {
-        p.off_spl = take(p.Sp * 4);
-        p.off_sidx = take(p.Sp);
-    }
     p.smem_per_env = round_up(struct_bytes + off, 16);
+    // the parked images: kept when all of them together stay a modest part of the L2 (a launch then starts with one bulk
+    // copy per env out of the L2 instead of re-deriving ranks, grid and lists; larger batches hide that latency behind
+    // their other CTAs and would pay for the extra bytes in HBM bandwidth)
+    {
+        const int img_off_bytes = p.mpc == 16 ? img_off<16>() : p.mpc == 32 ? img_off<32>() : p.mpc == 128 ? img_off<128>() : img_off<256>();
+        p.img_bytes = struct_bytes - img_off_bytes + p.off_cand;
+        p.img_pitch = round_up(p.img_bytes, 128);
+        long long budget = 64ll << 20;
+        if (const char* force = getenv("ZS_IMAGE_MB")) budget = (long long)atoll(force) << 20;
+        if ((long long)p.N * p.img_pitch <= budget) {
+            void* d = nullptr;
+            if (cudaMalloc(&d, (size_t)p.N * p.img_pitch) != cudaSuccess) { zs_destroy(h); return fail("out of device memory (parked images)"); }
+            h->dev_allocs.push_back(d);
+            p.img = (unsigned char*)d;
+        }
+        h->img_valid = false;
+    }
     // lanes per env: a half warp (two envs per warp, in lock-step) when an env has at most 16 slots, the env count is
     // even and the batch is large enough that the halved instruction count matters more than the few extra cycles a
     // two-env warp needs per step (measured cross-over: about 16 envs per SM)
@@ -838,10 +904,13 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         if (pair) bytes *= 2;
         // keep at least 6 CTAs per SM resident (2-warp CTAs are only chosen for batches that need no more)
         if ((h->smem_bytes + bytes + 1024) * 6 <= (int)prop.sharedMemPerMultiprocessor && !getenv("ZS_NO_TMA")) {
-            p.tmpl_smem_off = h->smem_bytes; p.tmpl_planes = planes; p.tmpl_pair = pair;
-            h->smem_bytes += bytes;
+            p.tmpl_smem_off = h->smem_bytes; p.tmpl_planes = planes; p.tmpl_pair = pair; p.tmpl_bytes = planes * p.cells * 4;
+            h->smem_bytes += bytes + 16;  // (+ the mbarrier of the staging copy)
         }
     }
+    h->tmpl_single_step = getenv("ZS_NO_TMA_SINGLE") ? 0 : 1;
+    h->compact_words = (p.mpc <= 32 && p.obs_scope == ZS_OBS_WORLD && !p.obs_per_agent)
+                           ? (p.obs_enc == ZS_OBS_SIMPLE ? 128 : 256) : 0;
     if (h->smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
     if (int rc2 = set_smem_attr(p.mpc, h->lanes_per_env, h->smem_bytes)) { zs_destroy(h); return rc2; }
     // resident CTAs per SM the step kernel is compiled for (zs_sim_kernel: OCC): fewest rounds first, then most registers;
@@ -893,6 +962,13 @@ extern "C" __attribute__((visibility("default"))) int zs_bind_state(ZsHandle* h,
     p.SLIFE = (int16_t*)(b + h->lay.offset[ZS_F_STATIC_LIFE]); p.DEAD = (uint32_t*)(b + h->lay.offset[ZS_F_DEAD_BODY]);
     p.SCAL = (int32_t*)(b + h->lay.offset[ZS_F_SCALARS]);
     h->bound_bytes = bytes;
+    h->img_valid = false;
+    return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_state_written(ZsHandle* h) {
+    if (!h) return fail("null handle");
+    h->img_valid = false;
     return 0;
 }
 
@@ -911,6 +987,7 @@ static int launched(ZsHandle* h) {
 extern "C" __attribute__((visibility("default"))) int zs_init_static_life(ZsHandle* h, void* stream) {
     if (int rc = check_bound(h)) return rc;
     DeviceGuard guard(h);
+    h->img_valid = false;
     zs_init_static_life_kernel<<<h->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(h->p);
     return launched(h);
 }
@@ -938,6 +1015,88 @@ extern "C" __attribute__((visibility("default"))) int zs_step(ZsHandle* h, const
     io.n_steps = 1;
     launch_sim<MODE_STEP>(h, io, (cudaStream_t)stream);
     return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int32_t zs_compact_words(const ZsHandle* h) { return h ? h->compact_words : 0; }
+
+extern "C" __attribute__((visibility("default"))) int zs_step_compact(ZsHandle* h, const int32_t* actions_dev, int32_t action_format, uint32_t* compact_dev,
+                                                                       int32_t* obs_dev, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
+    if (!h->compact_words) return fail("this configuration has no compact observation form (world scope, one reward per env, at most 32 slots)");
+    if (!actions_dev || !compact_dev) return fail("zs_step_compact needs an action tensor and a record buffer");
+    if (action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
+    ZsIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1;
+    io.compact = compact_dev; io.compact_words = h->compact_words;
+    io.n_steps = 1;
+    launch_sim<MODE_STEP>(h, io, (cudaStream_t)stream);
+    return launched(h);
+}
+
+// HOST code: records -> the reference's observation tensor (include/zs_b200.h).  Incremental: the cells the previous
+// record of an env patched go back to the pristine value, the new record's cells are written; a full row is only
+// rewritten on the first call and after an overflow.
+extern "C" __attribute__((visibility("default"))) int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t* prev_host, int32_t* obs_host,
+                                                                         double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                                                                         int32_t* overflow_envs_host, int32_t* n_overflow, int32_t first_call, int32_t n_threads) {
+    if (!h) return fail("null handle");
+    if (!h->compact_words) return fail("this configuration has no compact observation form");
+    if (!compact_host || !prev_host || !obs_host || !overflow_envs_host || !n_overflow) return fail("null argument");
+    const int N = h->p.N, words = h->compact_words, cells = h->p.cells, C = h->p.obs_C;
+    const bool simple = h->p.obs_enc == ZS_OBS_SIMPLE;
+    const int wpe = simple ? 1 : 2;
+    const int32_t* T = h->tmpl_obs_host.data();
+    const size_t row = (size_t)C * cells;
+    if (n_threads <= 0) {
+        cpu_set_t set;
+        n_threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
+    }
+    if (n_threads > N) n_threads = N;
+    int n_over = 0;
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+    for (int e = 0; e < N; ++e) {
+        const uint32_t* r = compact_host + (size_t)e * words;
+        uint32_t* pv = prev_host + (size_t)e * words;
+        int32_t* o = obs_host + (size_t)e * row;
+        const uint32_t h0 = r[0];
+        const int n = (int)(h0 & 0xffffu);
+        if (terminated_host) terminated_host[e] = (uint8_t)((h0 >> 16) & 1u);
+        if (truncated_host) truncated_host[e] = (uint8_t)((h0 >> 17) & 1u);
+        if (reward_host) memcpy(reward_host + e, r + 2, sizeof(double));
+        const bool prev_unknown = first_call || ((pv[0] >> 18) & 1u);
+        if ((h0 >> 18) & 1u) {  // the record could not hold this env: the caller copies its row from the device
+            int at;
+#pragma omp atomic capture
+            at = n_over++;
+            overflow_envs_host[at] = e;
+            pv[0] = h0;
+            continue;
+        }
+        if (prev_unknown) memcpy(o, T, row * sizeof(int32_t));
+        else {
+            const int pn = (int)(pv[0] & 0xffffu);
+            for (int i = 0; i < pn; ++i) {
+                const int cell = (int)(pv[ZS_COMPACT_HEADER + i * wpe] & 0xffffu);
+                for (int c = 0; c < C; ++c) o[(size_t)c * cells + cell] = T[(size_t)c * cells + cell];
+            }
+        }
+        if (simple) {
+            for (int i = 0; i < n; ++i) { const uint32_t w = r[ZS_COMPACT_HEADER + i]; o[w & 0xffffu] = (int32_t)(w >> 16); }
+        } else {
+            for (int i = 0; i < n; ++i) {
+                const uint32_t w0 = r[ZS_COMPACT_HEADER + 2 * i], w1 = r[ZS_COMPACT_HEADER + 2 * i + 1];
+                const int cell = (int)(w0 & 0xffffu);
+                o[cell] = (int32_t)(w0 >> 16);
+                o[(size_t)cells + cell] = (int32_t)(int16_t)(w1 & 0xffffu);
+                o[2 * (size_t)cells + cell] = (int32_t)(w1 >> 16);
+            }
+        }
+        memcpy(pv, r, (size_t)(ZS_COMPACT_HEADER + n * wpe) * sizeof(uint32_t));
+    }
+    *n_overflow = n_over;
+    return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int zs_encode_obs(ZsHandle* h, int32_t* obs_dev, void* stream) {

@@ -16,6 +16,7 @@
 // reference defines sequentially (execute_actions) are run by the group's lane 0 on shared memory.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/zs_b200.h"
@@ -91,10 +92,14 @@ struct ZsParams {
                                    // memory (maps without spawn cells: every cell is a candidate); NULL = in shared memory
     int32_t prefetch_ahead;        // load_state also prefetches the state of env + prefetch_ahead into the L2 (0 = off)
     int32_t sl_global;             // same kernels, same maps: box/wall lives are used where they are, in the state buffer
+    unsigned char* img;            // the parked on-chip images [N, img_pitch bytes] (EnvS: "the IMAGE"), NULL = not kept
+    int32_t img_pitch, img_bytes;  // bytes between two envs' images / bytes of one (multiples of 16)
+    int32_t img_load;              // the images are current: a launch starts from them instead of load_state + build_grid
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
     int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
     int32_t tmpl_planes;           // planes staged there: 1 (simple) or 3 (channels: label, life, zeros)
     int32_t tmpl_pair;             // the planes are staged twice back to back: one bulk copy serves both envs of a warp
+    int32_t tmpl_bytes;            // bytes of one staged copy of the planes (tmpl_planes * cells * 4)
     int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
 };
 
@@ -108,6 +113,8 @@ struct ZsIO {
     uint8_t* truncated;
     uint8_t* agent_mask;      // [n_steps, N, A] or NULL
     int32_t* draws;           // [n_steps, N] or NULL
+    uint32_t* compact;        // [N, compact_words] compact observation records (zs_obs.cuh: obs_world_compact) or NULL
+    int32_t compact_words;    // words per record: ZS_COMPACT_HEADER + entry words
     const uint8_t* env_mask;  // reset only
     int32_t n_steps;
     int64_t first_step;
@@ -151,18 +158,29 @@ extern __shared__ __align__(16) unsigned char zs_smem[];
 template <int MPC>
 struct alignas(16) EnvS {
     static constexpr int GEN = MPC > 32 ? MPC : 1;  // arrays only the general (more slots than lanes) kernels use
+    // ---- scratch: lives for a step (or a launch)
     unsigned long long act[MPC];            // the step's action list (packed, see pack_action): actor order, then shuffled in place
-    uint32_t txy[MPC];                      // x | y << 16 (int16 each)
     uint32_t bk[MPC];                       // per step: closest-player key of a zombie / heal_closest agent
     alignas(16) uint32_t draws[3 * MPC + 4];  // per step: the draws, 4 per Philox block (stored as uint4)
     uint32_t zb[GEN < ZS_NP_MAX ? GEN : ZS_NP_MAX];  // per step: closest-zombie key of a player slot
     int32_t scal[8];                        // scalar hand-off around out-of-line functions
     int32_t acts[3 * (GEN < ZS_MAX_AGENTS ? GEN : ZS_MAX_AGENTS) + 1];  // agent actions of the step (type, dx, dy)
     uint32_t masks[2 * ((MPC + 31) / 32) + 2];  // rank bit-masks: stayers, then movers
-    int16_t tl[MPC];                        // life
+    alignas(8) unsigned long long mbar;     // mbarrier of the image load (one phase per launch)
     int16_t da[GEN];
     int16_t db[GEN];
     uint16_t list[MPC];
+    uint8_t dtype[MPC];
+    uint8_t mvp[GEN];                       // general kernels: list position of the slot's successful move, RK_NONE if none
+    uint8_t mpos[GEN];                      // general kernels: list position of the slot's (valid) move action, RK_NONE if none
+    alignas(16) uint8_t fyj[MPC];           // per step: Fisher-Yates partner of every list position (one-lane-per-slot kernels)
+    // ---- the IMAGE: everything from here to the end of the struct, and the run-time tail behind it up to the spawn
+    // candidate list, is what an env needs on chip between two steps.  A launch leaves it in device memory as one
+    // contiguous block next to the canonical state (ZsParams::img) and the next launch brings it back with ONE bulk copy
+    // (cp.async.bulk global -> shared behind `mbar`) instead of re-deriving ranks, grid and lists from the state.
+    alignas(16) uint32_t txy[MPC];          // x | y << 16 (int16 each)
+    int32_t pscal[8];                       // the scalars (ZS_S_*; flags with the launch-lifetime bits) while the env is parked
+    int16_t tl[MPC];                        // life
     int16_t prev[MPC < ZS_MAX_AGENTS ? MPC : ZS_MAX_AGENTS];  // reward tracker's agents_life
     uint16_t spn[8];                        // spn[0] = entries of the static patch list (SPL, in the run-time tail)
     uint16_t dbl[ZS_DEAD_CAP + 2];          // dbl[0] = count, dbl[1..] = cells that got a dead body in this world (repeats allowed)
@@ -170,11 +188,8 @@ struct alignas(16) EnvS {
     uint8_t rk[MPC];                        // dict-order rank among the things in the world (RK_NONE if absent)
     uint8_t sor[MPC];                       // slot of a rank
     uint8_t mvq[MPC];                       // order of this step's successful moves, RK_NONE if none
-    uint8_t dtype[MPC];
-    uint8_t mvp[GEN];                       // general kernels: list position of the slot's successful move, RK_NONE if none
-    uint8_t mpos[GEN];                      // general kernels: list position of the slot's (valid) move action, RK_NONE if none
-    alignas(16) uint8_t fyj[MPC];           // per step: Fisher-Yates partner of every list position (one-lane-per-slot kernels)
 };
+template <int MPC> __host__ __device__ constexpr int img_off() { return (int)offsetof(EnvS<MPC>, txy); }
 
 // The env a lane group is working on (warp-uniform within the group).
 struct Env {
@@ -246,6 +261,34 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 __device__ __forceinline__ void bulk_store_s(void* gdst, uint32_t saddr, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
 }
+// ---------------------------------------------------------------- TMA bulk copies (global -> shared) behind an mbarrier
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // (visible to the async proxy before a copy names it)
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst), a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ZS_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra ZS_MBAR_DONE_%=;\n"
+        "bra ZS_MBAR_WAIT_%=;\n"
+        "ZS_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefetch.global.L2 [%0];" ::"l"(g)); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

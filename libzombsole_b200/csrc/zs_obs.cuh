@@ -163,6 +163,90 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e
     }
 }
 
+// World scope as a compact record (include/zs_b200.h: zs_step_compact): the cells pass 2 would patch, as entries of the
+// env's record instead of stores into its observation row.  Every patched cell has exactly one writer, so the entries
+// need no order; their positions come from ballot prefix sums (all rounds run on warp-level bounds: the primitives are
+// full-mask when two envs share a warp).  Returns true when the record cannot hold the env (too many entries, or a
+// value outside the entry's fields): the caller then writes the full row.  n_out: the entry count (0 on overflow).
+ZS_TPL __device__ __forceinline__ bool obs_world_compact(const ZsParams& p, Env& e, uint32_t* __restrict__ rec, int cap_words, int& n_out) {
+    ZS_CONSTS; ZS_VIEWS;
+    const int lane = e.gl;
+    const unsigned below_l = (1u << lane) - 1u;
+    const bool simple = p.obs_enc == ZS_OBS_SIMPLE;
+    const int cap = simple ? cap_words : (cap_words >> 1);
+    int n = 0;
+    bool bad = false;
+    auto emit = [&](bool on, int cell, int v0, int v1, int v2) {
+        const unsigned m = gballot<G, CV>(e, on);
+        const int pos = n + __popc(m & below_l);
+        if (on) {
+            if (simple) {
+                bad |= (unsigned)v0 > 0xffffu;
+                if (pos < cap) rec[ZS_COMPACT_HEADER + pos] = (uint32_t)cell | ((uint32_t)v0 << 16);
+            } else {
+                bad |= (unsigned)v0 > 0xffffu || (unsigned)v2 > 0xffffu || v1 < -32768 || v1 > 32767;
+                if (pos < cap) {
+                    rec[ZS_COMPACT_HEADER + 2 * pos] = (uint32_t)cell | ((uint32_t)v0 << 16);
+                    rec[ZS_COMPACT_HEADER + 2 * pos + 1] = ((uint32_t)v1 & 0xffffu) | ((uint32_t)v2 << 16);
+                }
+            }
+        }
+        n += __popc(m);
+    };
+    const int n_spl = (e.flags & FL_DMG) ? (int)SPN : 0;
+    const int r_spl = wmax<G, CV>(e, n_spl);
+#pragma unroll 1
+    for (int i0 = 0; i0 < r_spl; i0 += G) {
+        const int i = i0 + lane;
+        const uint32_t w = i < n_spl ? SPL(i) : 0xffff0000u;
+        const int cell = w & 0xffffu, pay = w >> 16;
+        // gone from World.things (payload 0): whatever took the cell shows itself; else the cell reads as empty
+        const bool on = i < n_spl && (pay != 0 || GRID(cell) == G_EMPTY);
+        int v0 = pay, v1 = 0;
+        if (!simple) { v0 = pay >> 12; v1 = (int)((uint32_t)pay << 20) >> 20; }
+        emit(on, cell, v0, v1, 0);
+    }
+    const int body0 = simple ? 256 * ZS_LABEL_DEAD_BODY : ZS_LABEL_DEAD_BODY;
+    const bool dead_over = (e.flags & FL_DEAD_OVER) != 0;
+    const int n_dead = dead_over ? 0 : (int)DBL(0);
+    const int r_dead = wmax<G, CV>(e, n_dead);
+#pragma unroll 1
+    for (int i0 = 0; i0 < r_dead; i0 += G) {
+        const int i = i0 + lane;
+        const int c = i < n_dead ? (int)DBL(1 + i) : 0;
+        emit(i < n_dead && GRID(c) == G_DEAD, c, body0, 0, 0);  // (a cell listed twice makes two equal entries)
+    }
+    if (wany<G, CV>(e, dead_over)) {  // the list is not complete: walk the dead-body bitmap
+        const int words = dead_over ? p.dead_words : 0;
+        const int r_w = wmax<G, CV>(e, words);
+#pragma unroll 1
+        for (int w0 = 0; w0 < r_w; w0 += G) {
+            const int w = w0 + lane;
+            uint32_t bits = w < words ? DEADW(w) : 0u;
+            int left = (int)__reduce_max_sync(gmask<G, CV>(e), (unsigned)__popc(bits));
+#pragma unroll 1
+            for (; left > 0; --left) {
+                const int c = bits ? w * 32 + __ffs(bits) - 1 : 0;
+                const bool on = bits != 0u && GRID(c) == G_DEAD;
+                bits &= bits - 1u;
+                emit(on, c, body0, 0, 0);
+            }
+        }
+    }
+    {
+        const bool in_cap = G == MPC || lane < MPC;
+        const int m = in_cap ? (int)TM(lane) : 0;
+        const bool on = (m & 0x80) != 0;
+        const uint32_t xy = in_cap ? TXY(lane) : 0u;
+        const CellInfo ci = thing_info(p, lane, in_cap ? (int)TL(lane) : 0, m);
+        if (simple) emit(on, xy_y(xy) * p.W + xy_x(xy), encode_simple(ci), 0, 0);
+        else emit(on, xy_y(xy) * p.W + xy_x(xy), channel_label(p, ci), ci.life, ci.weapon);
+    }
+    const bool over = gany<G, CV>(e, bad) || n > cap;
+    n_out = over ? 0 : n;
+    return over;
+}
+
 // surroundings window (observation.py:99-119): rows = y, columns = x, centred on the agent's (possibly stale, if
 // dead) position; out-of-bounds cells are a fresh Wall (observation.py:43-44,64-65).  Like the world scope it is
 // written in two passes: the pristine layer of every window from the (L1-resident) padded template planes, then

@@ -347,6 +347,42 @@ ZS_TPL __device__ __forceinline__ void store_state(const ZsParams& p, Env& e) {
     e.flags = keep;
 }
 
+// ---------------------------------------------------------------- the parked image (zs_device.cuh: EnvS, "the IMAGE")
+// Start of a launch: the group's lane 0 arms the env's mbarrier and issues ONE bulk copy of the whole image; the wait
+// comes later (the caller puts independent work in between).  The canonical state is not read at all.
+ZS_TPL __device__ __forceinline__ void load_image_issue(const ZsParams& p, const Env& e) {
+    ZS_VIEWS;
+    if (e.gl == 0) {
+        mbar_init(&S.mbar, 1);
+        mbar_expect_tx(&S.mbar, (uint32_t)p.img_bytes);
+        bulk_load(zs_smem + e.b + img_off<MPC>(), p.img + (size_t)e.env * p.img_pitch, (uint32_t)p.img_bytes, &S.mbar);
+    }
+}
+ZS_TPL __device__ __forceinline__ void load_image_wait(const ZsParams& p, Env& e) {
+    ZS_VIEWS;
+    __syncwarp(e.gm);  // (lane 0's mbarrier.init comes before anybody's wait)
+    mbar_wait(&S.mbar, 0u);
+    e.t = S.pscal[ZS_S_T]; e.episode = S.pscal[ZS_S_EPISODE]; e.deaths = S.pscal[ZS_S_DEATHS]; e.zd = S.pscal[ZS_S_ZOMBIE_DEATHS];
+    e.nlive = S.pscal[ZS_S_STAMP_COUNTER]; e.prev_zd = S.pscal[ZS_S_PREV_ZOMBIE_DEATHS]; e.ep_steps = S.pscal[ZS_S_EPISODE_STEPS];
+    e.flags = (S.pscal[ZS_S_FLAGS] & (FL_FRESH | FL_DEAD_OVER)) | (SPN ? FL_DMG : 0);
+}
+// End of a launch: the scalars join the image, the lanes' shared-memory writes are handed to the async proxy and lane 0
+// sends the block back with one bulk copy (it must have been READ before the CTA may go: image_store_drain).
+ZS_TPL __device__ __forceinline__ void store_image(const ZsParams& p, Env& e) {
+    ZS_VIEWS;
+    const int keep = e.flags;
+    e.flags &= FL_FRESH | FL_DEAD_OVER;
+    if (e.gl < 8) S.pscal[e.gl] = scalar_of_lane(e);
+    e.flags = keep;
+    fence_proxy_async_smem();
+    __syncwarp(e.gm);
+    if (e.gl == 0) {
+        bulk_store(p.img + (size_t)e.env * p.img_pitch, zs_smem + e.b + img_off<MPC>(), (uint32_t)p.img_bytes);
+        bulk_commit();
+    }
+}
+__device__ __forceinline__ void image_store_drain(const Env& e) { if (e.gl == 0) bulk_wait_read_all(); }
+
 // Rebuild the occupancy grid from the compact state.  FL_FRESH = first step after a world init:
 // boxes/walls whose life is already <= 0 are still in World.things (game.py:154-155) until the
 // first clean_dead_things.
@@ -1641,119 +1677,91 @@ ZS_TPL __device__ __noinline__ int spawn_zombies(const ZsParams& p, GrpId id, in
 // player AND zombie spawn cells and room for everybody, fixed weapons.  Nothing can stand on a spawn cell of a new
 // world (boxes/walls never do, and the two kinds of spawn cells are different cells), so World.spawn_in_random's
 // filter (core.py:47-52) keeps the whole list for the bots and the zombies, and the list minus the bots' cells for
-// the agents; every draw index is known up front, so ALL draws of the init come from one pass of Philox; the three
-// partial Fisher-Yates shuffles run on list indices (the zombies' independent of the players'), and the things are
-// placed in parallel: thing s gets dict rank s.  Same results as initialize_world below, in a third of the time.
-ZS_TPL __device__ __noinline__ int initialize_world_lists(const ZsParams& p, GrpId id, int episode, int flags_in) {
-    ZS_CONSTS;
-    Env e = env_of(p, id);
+// the agents; every draw index is known up front.  Lane = slot = dict rank of the new thing, and everything stays in
+// registers:
+//   * each lane evaluates Philox for its own placement draw (and its life draw: zombies, things.py:62);
+//   * random.shuffle + spawns.pop() (core.py:54-61): iteration `it` of a group takes the candidate at position
+//     j_it = randbelow(n - it) and leaves the one from position n - 1 - it there.  What iteration `it` finds at j_it is
+//     read off the earlier iterations' partners with shuffles: walking t = it-1 .. 0, a t with j_t == q means the
+//     content of q came from position n - 1 - t at iteration t, so the search goes on for that position (one
+//     descending pass, the three groups at once);
+//   * the agents' candidates are the player spawn cells the bots did not take, in list order: the f-th of them is the
+//     smallest x with x - #{bot picks <= x} == f.
+// Runs CONVERGED (CV): both envs of a warp go through it when either ends an episode, the writes predicated on
+// `need`.  Same results as the general initialize_world below.  Returns the draws consumed; the scalars of the new
+// world go straight into e.
+ZS_TPL __device__ __forceinline__ int initialize_world_fast(const ZsParams& p, Env& e, bool need) {
     ZS_VIEWS;
-    const int lane = e.gl;
+    const int s = e.gl;
     const int P = p.P, A = p.A, NP = P + A, Z0 = p.initial_zombies;
-    const int flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH | ((flags_in & FL_DEAD_LAUNCH) ? (FL_DEAD_OVER | FL_DEAD_LAUNCH) : 0);
-    e.episode = episode;
-#ifdef ZS_PHASE_CLOCKS
-    e.ph_last = clock64();
-#endif
+    const uint32_t episode = (uint32_t)(e.episode + 1);
     // draw indices (A.7 of SURVEY.md): players shuffle, agents shuffle, zombie lives, zombies shuffle; a shuffle of n
     // candidates consumes n - 1 draws whatever is placed
     const int n1 = p.n_ps, n2 = p.n_ps - P, n3 = p.n_zs;
     const int K1 = n1 > 1 ? n1 - 1 : 0, K2 = K1 + (n2 > 1 ? n2 - 1 : 0), K3 = K2 + Z0, K4 = K3 + (n3 > 1 ? n3 - 1 : 0);
-    // ---- all the draws that decide something: item j = bot j | agent | zombie life | zombie placement
-    const int n_items = NP + 2 * Z0;
+    const bool in_cap = G == MPC || s < MPC;
+    const bool is_bot = s < P, is_agent = !is_bot && s < NP, placed = s < NP + Z0;
+    const int base = is_bot ? 0 : is_agent ? P : NP;
+    const int it = placed ? s - base : 0;
+    const int n = is_bot ? n1 : is_agent ? n2 : n3;
+    const int kp = (is_bot ? 0 : is_agent ? K1 : K3) + it;  // this thing's placement draw: randbelow(n - it)
+    const int kl = K2 + it;                                  // a zombie's life draw
+    const uint4 o1 = philox_draws(p, e.env_global, episode, 0u, (uint32_t)(kp >> 2));
+    const uint4 o2 = philox_draws(p, e.env_global, episode, 0u, (uint32_t)(kl >> 2));
+    const int j = n - it > 1 ? below(word_of(o1, kp & 3), n - it) : 0;
+    const int life = s < NP ? 100 : 50 + below(word_of(o2, kl & 3), 51);
+    int q = placed ? j : -1;
+    const int tmax = max(max(P, A), Z0);
 #pragma unroll 1
-    for (int j = lane; j < n_items; j += G) {
-        int k, bound;
-        if (j < P) { k = j; bound = n1 - j; }                               // iteration it: i = n - 1 - it, randbelow(i + 1)
-        else if (j < NP) { k = K1 + (j - P); bound = n2 - (j - P); }
-        else if (j < NP + Z0) { k = K2 + (j - NP); bound = 51; }            // Zombie.__init__: randint(50, 100) (things.py:62)
-        else { k = K3 + (j - NP - Z0); bound = n3 - (j - NP - Z0); }
-        const uint4 o = philox_draws(p, e.env_global, (uint32_t)episode, 0u, (uint32_t)(k >> 2));
-        DRAWS(j) = bound > 1 ? (uint32_t)below(word_of(o, k & 3), bound) : 0u;
+    for (int t = tmax - 1; t >= 0; --t) {
+        const int jt = gbcast<G, CV>(e, j, base + t);
+        if (t < it && jt == q) q = n - 1 - t;
     }
-    // ---- per-slot init, decorations, the grid of a new world (= the pristine template: every box/wall is back)
+    if (P > 0) {  // (an agent's q counts the player spawn cells the bots left)
+        int x = q;
 #pragma unroll 1
-    for (int w = lane; w < p.dead_words; w += G) DEADW(w) = 0;
-    if (lane == 0) DBL(0) = 0;
-    if (G == MPC || lane < MPC) {
-        const int s = lane;
-        int w = ZS_WEAPON_CLAWS;
-        if (s < P) w = p.bot_kinds[s] == ZS_KIND_SNIPER ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN;  // sniper.py:23-24, terminator.py:41-42
-        else if (s < NP) w = p.agent_weapons[s - P];
-        TM(s) = (uint8_t)w;
-        RK(s) = RK_NONE; MVQ(s) = RK_NONE;
-        if (s < NP) TL(s) = 100;
+        for (int r = 0; r < P; ++r) {
+            int c = 0;
+#pragma unroll 1
+            for (int b = 0; b < P; ++b) c += gbcast<G, CV>(e, q, b) <= x;
+            x = q + c;
+        }
+        if (is_agent) q = x;
     }
-    {
+    const int c = placed ? (int)(s < NP ? __ldg(p.ps_cells + q) : __ldg(p.zs_cells + q)) : 0;
+    const int flags_in = e.flags;
+    if (need) {
+        // decorations and the grid of a new world (= the pristine template: every box/wall is back)
+#pragma unroll 1
+        for (int w = s; w < p.dead_words; w += G) DEADW(w) = 0;
+        if (s == 0) DBL(0) = 0;
         const uint4* tg = (const uint4*)p.tmpl_grid;
-#pragma unroll 4
-        for (int i = lane; i < (p.cells_pad >> 4); i += G) reinterpret_cast<uint4*>(GRIDP)[i] = __ldg(tg + i);
+#pragma unroll 6
+        for (int i = s; i < (p.cells_pad >> 4); i += G) reinterpret_cast<uint4*>(GRIDP)[i] = __ldg(tg + i);
+        if (flags_in & FL_DMG) spl_refresh_present<MPC, G, CV>(p, e);
     }
-    if (flags & FL_DMG) spl_refresh_present<MPC, G, CV>(p, e);
-    // ---- candidate lists as list indices: players' at CAND[0, n1), zombies' at CAND[n1, n1 + n3)
-#pragma unroll 4
-    for (int i = lane; i < n1 + n3; i += G) CAND(i) = (uint16_t)(i < n1 ? i : i - n1);
     gsync<G, CV>(e);
-    PH(13);
-    if (lane == 0) {
-        // the swaps: iteration `it` takes the candidate at its partner's position and leaves its own there
-#pragma unroll 1
-        for (int it = 0; it < P; ++it) {
-            const int i = n1 - 1 - it;
-            int c = CAND(i);
-            if (i >= 1) { const int j = (int)DRAWS(it); const int cj = CAND(j); CAND(j) = (uint16_t)c; c = cj; }
-            LIST(it) = (uint16_t)c;
-        }
-#pragma unroll 1
-        for (int it = 0; it < Z0; ++it) {
-            const int i = n3 - 1 - it;
-            int c = CAND(n1 + i);
-            if (i >= 1) { const int j = (int)DRAWS(NP + Z0 + it); const int cj = CAND(n1 + j); CAND(n1 + j) = (uint16_t)c; c = cj; }
-            LIST(NP + it) = (uint16_t)c;
+    if (need && in_cap) {
+        int w = ZS_WEAPON_CLAWS;
+        if (is_bot) w = p.bot_kinds[s] == ZS_KIND_SNIPER ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN;  // sniper.py:23-24, terminator.py:41-42
+        else if (is_agent) w = p.agent_weapons[s - P];
+        TM(s) = (uint8_t)(placed ? (w | 0x80) : w);
+        RK(s) = placed ? (uint8_t)s : (uint8_t)RK_NONE;
+        MVQ(s) = RK_NONE;
+        if (placed) {  // spawns.pop() for every thing: thing s of the new world gets dict rank s
+            const int y = c / p.W;
+            TXY(s) = xy_pack(c - y * p.W, y);
+            TL(s) = (int16_t)life;
+            SOR(s) = (uint8_t)s;
+            GRID(c) = (uint8_t)(s + 1);
+            if (is_agent) PREVL(s - P) = 100;  // reward_tracker.reset (reward.py:26-28)
         }
     }
-    gsync<G, CV>(e);
-    PH(14);
-    // the agents' candidates: the player spawn cells the bots did not take, in list order
-#pragma unroll 1
-    for (int i = lane; i < n1; i += G) {
-        int below_i = 0;
-        bool taken = false;
-        for (int b = 0; b < P; ++b) { const int cb = LIST(b); below_i += cb < i; taken |= cb == i; }
-        if (!taken) CAND(i - below_i) = (uint16_t)i;
+    if (need) {
+        e.t = -1; e.episode = (int)episode; e.deaths = 0; e.zd = 0; e.nlive = NP + Z0; e.prev_zd = 0; e.ep_steps = 0;
+        e.flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH | ((flags_in & FL_DEAD_LAUNCH) ? (FL_DEAD_OVER | FL_DEAD_LAUNCH) : 0);
     }
     gsync<G, CV>(e);
-    if (lane == 0) {
-#pragma unroll 1
-        for (int it = 0; it < A; ++it) {
-            const int i = n2 - 1 - it;
-            int c = CAND(i);
-            if (i >= 1) { const int j = (int)DRAWS(P + it); const int cj = CAND(j); CAND(j) = (uint16_t)c; c = cj; }
-            LIST(P + it) = (uint16_t)c;
-        }
-    }
-    gsync<G, CV>(e);
-    PH(15);
-    // ---- spawns.pop() for every thing, in parallel: thing s of the new world gets dict rank s
-    if ((G == MPC || lane < MPC) && lane < NP + Z0) {
-        const int s = lane;
-        const int c = s < NP ? (int)__ldg(p.ps_cells + LIST(s)) : (int)__ldg(p.zs_cells + LIST(s));
-        const int y = c / p.W;
-        TXY(s) = xy_pack(c - y * p.W, y);
-        TM(s) |= 0x80;
-        RK(s) = (uint8_t)s;
-        SOR(s) = (uint8_t)s;
-        GRID(c) = (uint8_t)(s + 1);
-        if (s >= NP) TL(s) = (int16_t)(50 + (int)DRAWS(s));  // (item NP + z is zombie z's life draw, and slot NP + z is zombie z)
-        else if (s >= P) PREVL(s - P) = 100;                  // reward_tracker.reset (reward.py:26-28)
-    }
-    if (lane == 0) {
-        SCALW(ZS_S_T) = -1; SCALW(ZS_S_EPISODE) = episode; SCALW(ZS_S_DEATHS) = 0; SCALW(ZS_S_ZOMBIE_DEATHS) = 0;
-        SCALW(ZS_S_STAMP_COUNTER) = NP + Z0; SCALW(ZS_S_FLAGS) = flags; SCALW(ZS_S_PREV_ZOMBIE_DEATHS) = 0;
-        SCALW(ZS_S_EPISODE_STEPS) = 0;
-    }
-    gsync<G, CV>(e);
-    PH(16);
     return K4;
 }
 
@@ -1763,7 +1771,17 @@ ZS_TPL __device__ __noinline__ int initialize_world_lists(const ZsParams& p, Grp
 // damage flags survive a world init (the damage itself does, game.py:154-155).  Returns the draws consumed.
 ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id, int episode, int flags_in) {
     ZS_CONSTS;
-    if (ONE && p.fast_init) return initialize_world_lists<MPC, G, CV>(p, id, episode, flags_in);
+    if constexpr (ONE) {
+        if (p.fast_init) {
+            Env e = env_of(p, id);
+            ZS_VIEWS;
+            e.episode = episode - 1; e.flags = flags_in;
+            const int k = initialize_world_fast<MPC, G, CV>(p, e, true);
+            if (e.gl < 8) SCALW(e.gl) = scalar_of_lane(e);
+            gsync<G, CV>(e);
+            return k;
+        }
+    }
     Env e = env_of(p, id);
     ZS_VIEWS;
     const int lane = e.gl;

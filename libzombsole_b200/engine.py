@@ -70,6 +70,12 @@ class ZsEngine(object):
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def state_written(self):
+        """Call after writing into ``fields`` (the views are the live state buffer): the engine keeps a parked on-chip
+        image of every env next to the state and starts launches from it; this marks the images stale, so the next
+        launch re-derives everything from the state buffer (zs_state_written)."""
+        check(self.L.zs_state_written(self.h))
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h:
             self.L.zs_destroy(self.h)
@@ -152,6 +158,28 @@ class ZsEngine(object):
                              self._arg(truncated, self._FLAG_DTYPES, N, "truncated"),
                              self._arg(agent_mask, self._FLAG_DTYPES, N * self.A, "agent_mask"),
                              self._arg(draws, torch.int32, N, "draws"), self._stream()))
+
+    # ---- compact host outputs (include/zs_b200.h: zs_step_compact / zs_expand_compact)
+    def compact_words(self):
+        """Words per compact observation record, 0 if this configuration has no compact form."""
+        return int(self.L.zs_compact_words(self.h))
+
+    def step_compact(self, actions, fmt, records, obs=None):
+        """One transition whose observation / reward / flags come out as one small record per env (device tensor
+        ``records`` int32 [N, compact_words]); ``obs`` receives the full row of the rare env a record cannot hold."""
+        check(self.L.zs_step_compact(self.h, self._action_arg(actions, fmt, 1), fmt,
+                                     self._arg(records, torch.int32, self.N * self.compact_words(), "records"),
+                                     self._arg(obs, torch.int32, self.N * self.obs_elems, "obs"), self._stream()))
+
+    def expand_compact(self, records_host, prev_host, obs_host, reward_host, term_host, trunc_host, overflow_host,
+                       first_call, n_threads=0):
+        """HOST side: records (already copied to host memory) -> the reference's observation tensor, reward, flags.
+        Returns the indices of the envs whose rows must be fetched from the device observation tensor."""
+        n_over = C.c_int32(0)
+        check(self.L.zs_expand_compact(self.h, records_host.data_ptr(), prev_host.data_ptr(), obs_host.data_ptr(),
+                                       reward_host.data_ptr(), term_host.data_ptr(), trunc_host.data_ptr(),
+                                       overflow_host.data_ptr(), C.addressof(n_over), 1 if first_call else 0, int(n_threads)))
+        return overflow_host[:n_over.value]
 
     def encode_obs(self, obs):
         check(self.L.zs_encode_obs(self.h, self._arg(obs, torch.int32, self.N * self.obs_elems, "obs"), self._stream()))

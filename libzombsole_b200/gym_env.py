@@ -65,7 +65,7 @@ class ZombsoleVectorEnv(object):
     def __init__(self, rules_name, player_names, map_name, agent_id, initial_zombies=0, minimum_zombies=0,
                  render_mode=None, observation_scope="world", observation_position_encoding="simple",
                  agent_weapon="rifle", debug=False, *, num_envs=1, device="cuda", seed=0, env_index_base=0,
-                 max_episode_steps=None, auto_reset=True, host_outputs=False):
+                 max_episode_steps=None, auto_reset=True, host_outputs=False, host_threads=0):
         if render_mode is not None:
             if render_mode not in self.metadata["render.modes"]:
                 raise ValueError("render_mode={} is not supported".format(render_mode))
@@ -87,8 +87,26 @@ class ZombsoleVectorEnv(object):
         self.action_space = self.single_action_space
         # host_outputs: step() returns tensors in pinned host memory that the kernel wrote directly (zero-copy over
         # PCIe, overlapped with the transition) and has synchronised on — for loops whose policy runs on the host
+        # host_outputs="compact": the same host tensors, but what crosses PCIe every step is one small record per env
+        # (the cells that differ from the map's pristine layer, the reward, the flags: about 0.5 KB instead of the
+        # 5-16 KB observation row) which a threaded host routine of the library expands in place into the env's host
+        # observation tensor — byte-identical results (zs_step_compact / zs_expand_compact, include/zs_b200.h)
+        self.compact = host_outputs == "compact"
         self.host_outputs = bool(host_outputs)
-        if self.host_outputs:
+        self.host_threads = int(host_threads)
+        if self.compact:
+            words = self.engine.compact_words()
+            if not words:
+                raise ValueError("host_outputs='compact' needs a world-scope observation and at most 32 things per env")
+            self.obs, self.reward, self._term, self._trunc = self.engine.new_host_outputs()
+            self._dev_obs = self.engine.new_obs()  # full rows of the rare envs a record cannot hold
+            self._records = torch.zeros((num_envs, words), dtype=torch.int32, device=self.device)
+            self._records_host = torch.zeros((num_envs, words), dtype=torch.int32).pin_memory()
+            self._records_prev = torch.zeros((num_envs, words), dtype=torch.int32)
+            self._overflow = torch.zeros(num_envs, dtype=torch.int32)
+            self._compact_first = True
+            self.compact_overflows = 0
+        elif self.host_outputs:
             self.obs, self.reward, self._term, self._trunc = self.engine.new_host_outputs()
         else:
             self.obs = self.engine.new_obs()
@@ -102,7 +120,12 @@ class ZombsoleVectorEnv(object):
         return Game(self.engine, env, rules_name, player_names, agent_ids, iz, mz)
 
     def get_observation(self):
-        return self.engine.encode_obs(self.obs)
+        self.engine.encode_obs(self.obs)
+        if self.host_outputs:  # (pinned host tensor written by the kernel: the host owns it when this returns)
+            torch.cuda.current_stream(self.device).synchronize()
+        if self.compact:
+            self._compact_first = True  # the rows are complete again: the next step's records start from scratch
+        return self.obs
 
     def get_frame_size(self):
         return tuple(self.observation_space.shape[1:3])
@@ -115,7 +138,7 @@ class ZombsoleVectorEnv(object):
             self._actions.copy_(torch.from_numpy(rows), non_blocking=True)
             return self._actions, abi.ACTIONS_FULL
         t = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
-        if self.host_outputs and t.dtype == torch.int32 and t.device.type == "cpu" and t.is_pinned():
+        if self.host_outputs and not self.compact and t.dtype == torch.int32 and t.device.type == "cpu" and t.is_pinned():
             pass  # the kernel reads a pinned host action tensor in place
         elif t.dtype != torch.int32 or t.device != self.device:
             pinned_src = t.device.type == "cpu" and t.is_pinned()
@@ -135,6 +158,8 @@ class ZombsoleVectorEnv(object):
         """One transition of every world (gym_env.py:99-145).  The returned tensors are the env's own
         output buffers: they are overwritten by the next call."""
         a, fmt = self._stage_actions(actions)
+        if self.compact:
+            return self._step_compact(a, fmt)
         self.engine.step(a, fmt, self.obs, self.reward, self._term, self._trunc)
         if self._h2d_pending:  # a pinned host action buffer is the caller's again when step() returns
             self._h2d_done.synchronize()
@@ -143,10 +168,37 @@ class ZombsoleVectorEnv(object):
             torch.cuda.current_stream(self.device).synchronize()  # the host owns the results when step() returns
         return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}  # (0/1 bytes: a view, no kernel)
 
+    def _step_compact(self, a, fmt):
+        eng = self.engine
+        eng.step_compact(a, fmt, self._records, self._dev_obs)
+        self._records_host.copy_(self._records, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device)
+        stream.synchronize()
+        self._h2d_pending = False
+        over = eng.expand_compact(self._records_host, self._records_prev, self.obs, self.reward, self._term, self._trunc,
+                                  self._overflow, self._compact_first, self.host_threads)
+        self._compact_first = False
+        if len(over):  # rare: more differing cells than a record holds — fetch those rows as they are
+            self.compact_overflows += len(over)
+            for e in over.tolist():
+                self.obs[e].copy_(self._dev_obs[e], non_blocking=True)
+            stream.synchronize()
+        return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}
+
     def reset(self, seed=None, options=None, mask=None):
         """Re-initialise every world (or those selected by ``mask``); gym_env.py:148-164.  ``seed`` is
         accepted for API compatibility and ignored, as in the reference (it only seeds gymnasium's unused
         np_random): the draw stream is fixed by the constructor's ``seed``."""
+        if self.compact:  # (resets are rare next to steps: the full rows come over, and the next step starts afresh)
+            self.engine.reset(mask, self._dev_obs)
+            if mask is None:
+                self.obs.copy_(self._dev_obs, non_blocking=True)
+            else:
+                sel = torch.as_tensor(mask).to(torch.bool).cpu()
+                self.obs[sel] = self._dev_obs.cpu()[sel]
+            torch.cuda.current_stream(self.device).synchronize()
+            self._compact_first = True
+            return self.obs, {}
         self.engine.reset(mask, self.obs)
         if self.host_outputs:
             torch.cuda.current_stream(self.device).synchronize()

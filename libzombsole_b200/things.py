@@ -42,6 +42,7 @@ class _Static(Thing):
     @life.setter
     def life(self, value):
         self._eng.fields["static_life"][self._env, self._index] = int(value)
+        self._eng.state_written()
 
 
 class Box(_Static):
@@ -80,6 +81,7 @@ class FightingThing(Thing):
     @life.setter
     def life(self, value):
         self._eng.fields["life"][self._env, self._index] = int(value)
+        self._eng.state_written()
 
     @property
     def in_world(self):

@@ -1,0 +1,72 @@
+"""host_outputs="compact": what crosses PCIe per step is one small record per env (the cells that differ from the map's
+pristine layer, reward, flags); a threaded host routine of the library expands the records into the reference's
+observation tensor.  The result must be byte-identical to the device tensors of a plain env on the same inputs, step
+after step (the expansion is incremental: it undoes the previous record's cells), across auto-resets, masked resets,
+and for envs whose differing cells do not fit a record (overflow: the full row is fetched)."""
+import numpy as np
+import pytest
+import torch
+
+from libzombsole_b200.gym_env import ZombsoleVectorEnv
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(rules_name="extermination", player_names=["terminator", "terminator"], map_name="bridge", agent_id=0,
+          initial_zombies=10, minimum_zombies=0, observation_scope="world", agent_weapon="rifle")
+
+
+@pytest.mark.parametrize("enc,N,threads", [("simple", 4096, 0), ("simple", 333, 3), ("channels", 1024, 0)])
+def test_compact_outputs_equal_device_outputs(enc, N, threads):
+    plain = ZombsoleVectorEnv(num_envs=N, seed=9, max_episode_steps=30, observation_position_encoding=enc, **KW)
+    comp = ZombsoleVectorEnv(num_envs=N, seed=9, max_episode_steps=30, observation_position_encoding=enc,
+                             host_outputs="compact", host_threads=threads, **KW)
+    o0, _ = plain.reset()
+    c0, _ = comp.reset()
+    assert torch.equal(o0.cpu(), c0)
+    rs = np.random.RandomState(0)
+    acts = torch.from_numpy(rs.randint(0, 6, size=(70, N)).astype(np.int32))
+    for t in range(70):
+        o, r, te, tr, _ = plain.step(acts[t].cuda())
+        co, cr, cte, ctr, _ = comp.step(acts[t].pin_memory())
+        assert co.device.type == "cpu"
+        assert torch.equal(o.cpu(), co), "observation differs at step %d" % t
+        assert torch.equal(r.cpu().view(torch.int64), cr.view(torch.int64)), "reward bits differ at step %d" % t
+        assert torch.equal(te.cpu(), cte) and torch.equal(tr.cpu(), ctr)
+        if t == 40:  # a masked reset in the middle, then an observation refresh
+            mask = torch.from_numpy((rs.rand(N) < 0.25).astype(np.uint8))
+            ro, _ = plain.reset(mask=mask)
+            rc, _ = comp.reset(mask=mask)
+            sel = mask.bool()
+            assert torch.equal(ro.cpu()[sel], rc[sel])
+        if t == 55:
+            assert torch.equal(plain.get_observation().cpu(), comp.get_observation())
+    assert comp.compact_overflows == 0
+    plain.close()
+    comp.close()
+
+
+def test_compact_overflow_fetches_the_full_row():
+    """More differing cells than a record holds (here: 150 damaged walls in some envs): those envs come over as full rows."""
+    N = 64
+    plain = ZombsoleVectorEnv(num_envs=N, seed=2, **KW)
+    comp = ZombsoleVectorEnv(num_envs=N, seed=2, host_outputs="compact", **KW)
+    for env in (plain, comp):
+        sl = env.engine.fields["static_life"]
+        sl[::5, :150] = torch.where(sl[::5, :150] == 200, torch.full_like(sl[::5, :150], 55), sl[::5, :150])
+        env.engine.state_written()
+    rs = np.random.RandomState(1)
+    for t in range(12):
+        a = torch.from_numpy(rs.randint(0, 6, size=N).astype(np.int32))
+        o, r, te, tr, _ = plain.step(a.cuda())
+        co, cr, cte, ctr, _ = comp.step(a)
+        assert torch.equal(o.cpu(), co), "observation differs at step %d" % t
+        assert torch.equal(r.cpu().view(torch.int64), cr.view(torch.int64))
+        assert torch.equal(te.cpu(), cte) and torch.equal(tr.cpu(), ctr)
+    assert comp.compact_overflows >= 12 * len(range(0, N, 5)) - N  # (an env may finish and reset; the damage persists)
+    plain.close()
+    comp.close()
+
+
+def test_compact_needs_a_world_observation():
+    with pytest.raises(ValueError):
+        ZombsoleVectorEnv(num_envs=8, host_outputs="compact", **dict(KW, observation_scope="surroundings:11"))

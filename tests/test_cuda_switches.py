@@ -23,6 +23,10 @@ CASES = [
     ("ZS_NO_SL_GLOBAL", "1", "c4_maze_safehouse", 128, 24),
     ("ZS_WARPS_PER_CTA", "2", "c4_maze_safehouse", 128, 24),
     ("ZS_NO_WINDOW_TABLE", "1", "c3_city_evac", 256, 40),
+    # without the parked images every launch re-derives ranks, grid and lists from the state buffer (large batches)
+    ("ZS_IMAGE_MB", "0", "c1_bridge_ext", 2048, 48),
+    ("ZS_IMAGE_MB", "0", "c3_city_evac", 256, 40),
+    ("ZS_IMAGE_MB", "0", "c4_maze_safehouse", 128, 24),
 ]
 
 

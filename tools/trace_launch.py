@@ -51,13 +51,34 @@ def main():
         print("  staging                   ", q(t[:, 1] - t[:, 0]))
         print("  load_state                ", q(t[:, 2] - t[:, 1]))
         print("  build_grid                ", q(t[:, 3] - t[:, 2]))
-        prev = t[:, 3]
-        for s in range(min(K, 24)):
+        print("  wait for the obs template  ", q(t[:, 29] - t[:, 3]))
+        prev = t[:, 29]
+        for s in range(min(K, 20)):
             cur = t[:, 4 + s]
             print("  step %2d                   " % s, q(cur - prev))
             prev = cur
         print("  last traced step -> exit  ", q(t[:, 30] - prev))
+        last0 = t[:, 4 + K - 2] if 2 <= K <= 20 else t[:, 29]
+        if K <= 20:
+            print("  LAST step: template issue  ", q(t[:, 24] - last0))
+            print("  LAST step: world_step      ", q(t[:, 25] - t[:, 24]))
+            print("  LAST step: reward/rules/out", q(t[:, 26] - t[:, 25]))
+            print("  LAST step: world init      ", q(t[:, 27] - t[:, 26]), " (%d warps > 1 us)" % int(((t[:, 27] - t[:, 26]) > 1000).sum()))
+            print("  LAST step: obs patches     ", q(t[:, 4 + K - 1] - t[:, 27]))
         print("  exit after first entry    ", q(t[:, 30] - t0), "  (kernel span %.2f us)" % ((t[:, 30].max() - t0) / 1e3))
+        if K <= 20:  # is the slow tail of the first step made of each SM's FIRST warps (cold instruction / data caches)?
+            ws = t[:, 25] - t[:, 24]
+            smv = t[:, 31]
+            by_rank = {}
+            for i in set(smv.tolist()):
+                idx = np.nonzero(smv == i)[0]
+                order = idx[np.argsort(t[idx, 0], kind="stable")]
+                for r, w in enumerate(order):
+                    by_rank.setdefault(r, []).append(ws[w])
+            print("  LAST step world_step by entry order within the SM (mean us):",
+                  {r: round(float(np.mean(v)) / 1e3, 2) for r, v in sorted(by_rank.items())})
+            slow = ws > 2 * np.median(ws)
+            print("  slow warps (> 2 x median): %d of %d; on %d SMs" % (int(slow.sum()), len(ws), len(set(smv[slow].tolist()))))
         # per SM: warps, span
         sm = t[:, 31]
         per = [(int(i), int((sm == i).sum()), (t[sm == i, 30].max() - t0) / 1e3) for i in sorted(set(sm.tolist()))]
