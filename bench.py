@@ -428,7 +428,27 @@ def run_ours(args, rank, world, local_rank):
     e2e_host_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_host_ms = max_over_ranks(max(ev[0].elapsed_time(ev[1]), e2e_host_wall_ms))
     env_h.close()
-    e2e_ms = min(e2e_copy_ms, e2e_host_ms)
+
+    # compact host outputs: one small record per env crosses PCIe (the cells that differ from the map's pristine layer,
+    # reward, flags); the library's threaded host routine expands it into the same pinned host observation tensor
+    threads_per_rank = max(1, host_threads() // max(1, world))
+    env_c = ZombsoleVectorEnv(num_envs=N, device=dev, seed=args.seed, env_index_base=rank * N, max_episode_steps=1000,
+                              auto_reset=True, host_outputs="compact", host_threads=threads_per_rank, **ENV_KW)
+    for s in range(W):
+        env_c.step(h_actions[s])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        o, r, te, tr, _ = env_c.step(h_actions[W + s])   # returns host tensors the host owns
+        sink += int(o[0, 0, 0, 0]) + int(te[0])
+    torch.cuda.synchronize(dev)
+    e2e_compact_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_compact_ms = max_over_ranks(e2e_compact_wall_ms)  # (host work is part of the step: wall clock, max over ranks)
+    compact_bytes = env_c._records.numel() * 4
+    compact_overflows = env_c.compact_overflows
+    env_c.close()
+    e2e_ms = min(e2e_copy_ms, e2e_host_ms, e2e_compact_ms)
+    e2e_best = "compact" if e2e_ms == e2e_compact_ms else ("host" if e2e_ms == e2e_host_ms else "copy")
 
     stats = eng.episode_stats()
     if world > 1:  # the only collective: episode statistics, off the step path
@@ -473,12 +493,18 @@ def run_ours(args, rank, world, local_rank):
             "per_step": {"value": total_envs * n_single / (per_step_ms * 1e-3), "unit": "env-steps/s",
                          "ms_per_step": per_step_ms / n_single, "launches": n_single},
             "e2e": {"value": total_envs * Ke / (e2e_ms * 1e-3), "unit": "env-steps/s", "steps": Ke,
-                    "h2d_bytes_per_step": N * 4, "d2h_bytes_per_step": obs_bytes + N * 8 + 2 * N,
-                    "api": ("ZombsoleVectorEnv(host_outputs=True).step(pinned host actions) -> pinned host obs/reward/flags "
-                            "written by the kernel over PCIe (zero-copy), stream synchronised before step() returns"
-                            if e2e_host_ms <= e2e_copy_ms else
-                            "ZombsoleVectorEnv.step(pinned host actions) + obs/reward/flags copied to pinned host"),
-                    "copy_variant": {"value": total_envs * Ke / (e2e_copy_ms * 1e-3),
+                    "h2d_bytes_per_step": N * 4,
+                    "d2h_bytes_per_step": compact_bytes if e2e_best == "compact" else obs_bytes + N * 8 + 2 * N,
+                    "api": {"compact": "ZombsoleVectorEnv(host_outputs='compact').step(pinned host actions) -> host int32 obs "
+                                       "(N,1,12,111) / float64 reward / flags: one 512-byte record per env copied device->host, "
+                                       "expanded in place by the library's host routine on %d threads; timed by the host "
+                                       "clock around the loop" % threads_per_rank,
+                            "host": "ZombsoleVectorEnv(host_outputs=True).step(pinned host actions) -> pinned host obs/reward/flags "
+                                    "written by the kernel over PCIe (zero-copy), stream synchronised before step() returns",
+                            "copy": "ZombsoleVectorEnv.step(pinned host actions) + obs/reward/flags copied to pinned host"}[e2e_best],
+                    "compact_variant": {"value": total_envs * Ke / (e2e_compact_ms * 1e-3), "d2h_bytes_per_step": compact_bytes,
+                                        "host_threads": threads_per_rank, "rows_fetched_in_full": compact_overflows},
+                    "copy_variant": {"value": total_envs * Ke / (e2e_copy_ms * 1e-3), "d2h_bytes_per_step": obs_bytes + N * 8 + 2 * N,
                                      "api": "ZombsoleVectorEnv.step(pinned host actions) + obs/reward/flags copied to pinned host"},
                     "host_outputs_variant": {"value": total_envs * Ke / (e2e_host_ms * 1e-3),
                                              "api": "ZombsoleVectorEnv(host_outputs=True).step(pinned host actions)"}},

@@ -201,6 +201,14 @@ int zs_step(ZsHandle* h, const int32_t* actions_dev, int32_t action_format, int3
             double* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
             uint8_t* agent_mask_dev, int32_t* draws_dev, void* stream);
 
+/* zs_step for the worlds selected by env_mask_dev (uint8 [N], NULL = all) only: the others are not touched — no
+ * transition, no outputs written.  This is what serving N independent clients from one batch needs (one client's
+ * GameAction advances that client's world, zombsole/interactive_json.py:317-325).  Needs a handle with one warp per
+ * env (zs_lanes_per_env == 32). */
+int zs_step_masked(ZsHandle* h, const uint8_t* env_mask_dev, const int32_t* actions_dev, int32_t action_format,
+                   int32_t* obs_dev, double* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                   uint8_t* agent_mask_dev, void* stream);
+
 /* Encode the observation of the current state only. */
 int zs_encode_obs(ZsHandle* h, int32_t* obs_dev, void* stream);
 

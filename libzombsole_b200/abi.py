@@ -73,6 +73,8 @@ PROTOTYPES = {
     "zs_destroy": (C.c_int, [C.c_void_p]),
     "zs_bind_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "zs_state_written": (C.c_int, [C.c_void_p]),
+    "zs_step_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_compact_words": (C.c_int32, [C.c_void_p]),
     "zs_step_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_expand_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -400,6 +400,8 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
         if (p.img) { store_image<MPC, G, CV>(p, e); image_store_drain(e); }
         return;
     }
+    // a masked step (zs_step_masked: one lane group = one whole warp) leaves the other worlds exactly as they are
+    if (MODE == MODE_STEP && io.env_mask && !io.env_mask[env]) return;
     if (p.img_load) {
         load_image_issue<MPC, G, CV>(p, e);
         load_image_wait<MPC, G, CV>(p, e);
@@ -636,7 +638,7 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
 #undef ZS_LAUNCH_G
 #undef ZS_LAUNCH_F
 #undef ZS_LAUNCH
-    if (pp.img != nullptr && (MODE == MODE_STEP || (MODE == MODE_RESET && io.env_mask == nullptr))) const_cast<ZsHandle*>(h)->img_valid = true;
+    if (pp.img != nullptr && (MODE == MODE_STEP || MODE == MODE_RESET) && io.env_mask == nullptr) const_cast<ZsHandle*>(h)->img_valid = true;
 }
 template <int MPC, int G, int OCC>
 static cudaError_t set_smem_attr_step(int bytes) {
@@ -1012,6 +1014,25 @@ extern "C" __attribute__((visibility("default"))) int zs_step(ZsHandle* h, const
     memset(&io, 0, sizeof(io));
     io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1; io.reward = reward_dev;
     io.terminated = terminated_dev; io.truncated = truncated_dev; io.agent_mask = agent_mask_dev; io.draws = draws_dev;
+    io.n_steps = 1;
+    launch_sim<MODE_STEP>(h, io, (cudaStream_t)stream);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_step_masked(ZsHandle* h, const uint8_t* env_mask_dev, const int32_t* actions_dev, int32_t action_format,
+                                                                      int32_t* obs_dev, double* reward_dev, uint8_t* terminated_dev, uint8_t* truncated_dev,
+                                                                      uint8_t* agent_mask_dev, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
+    if (!actions_dev) return fail("zs_step_masked needs an action tensor");
+    if (action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
+    if (env_mask_dev && h->lanes_per_env != 32)
+        return fail("masked steps need one warp per env: this handle packs two envs per warp (batches of more than 16 envs per SM "
+                    "of at most 16 things; set ZS_LANES_PER_ENV=32 before zs_create)");
+    ZsIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1; io.reward = reward_dev;
+    io.terminated = terminated_dev; io.truncated = truncated_dev; io.agent_mask = agent_mask_dev; io.env_mask = env_mask_dev;
     io.n_steps = 1;
     launch_sim<MODE_STEP>(h, io, (cudaStream_t)stream);
     return launched(h);

@@ -293,6 +293,9 @@ __device__ __forceinline__ void prefetch_l2(const void* g) { asm volatile("prefe
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// generic-proxy stores to global memory (observation patches) before later async-proxy stores to the same addresses
+// (the next bulk copy of the pristine planes into that row): without it the bulk copy can overtake them
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 // ---------------------------------------------------------------- phase clocks (development builds only)
 // -DZS_PHASE_CLOCKS: thread 0 of CTA 0 accumulates the cycles it spends in each phase of the step loop and prints

@@ -161,6 +161,10 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e
             }
         }
     }
+    // These patches went through the generic proxy; the next write to this row may be a bulk copy (async proxy: a later
+    // step of this launch reusing the ring slot).  Each lane orders its own stores before whatever the async proxy does
+    // later; the sync at the end of the step then puts them before lane 0's next issue.
+    if (p.tmpl_smem_off >= 0) fence_proxy_async_global();
 }
 
 // World scope as a compact record (include/zs_b200.h: zs_step_compact): the cells pass 2 would patch, as entries of the

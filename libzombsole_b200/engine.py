@@ -159,6 +159,17 @@ class ZsEngine(object):
                              self._arg(agent_mask, self._FLAG_DTYPES, N * self.A, "agent_mask"),
                              self._arg(draws, torch.int32, N, "draws"), self._stream()))
 
+    def step_masked(self, mask, actions, fmt, obs, reward, terminated, truncated, agent_mask=None):
+        """zs_step_masked: one transition of the worlds selected by ``mask`` (uint8 [N]); the others are not touched."""
+        N = self.N
+        mask = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
+        check(self.L.zs_step_masked(self.h, self._arg(mask, torch.uint8, N, "mask"), self._action_arg(actions, fmt, 1), fmt,
+                                    self._arg(obs, torch.int32, N * self.obs_elems, "obs"),
+                                    self._arg(reward, torch.float64, N * self.R, "reward"),
+                                    self._arg(terminated, self._FLAG_DTYPES, N, "terminated"),
+                                    self._arg(truncated, self._FLAG_DTYPES, N, "truncated"),
+                                    self._arg(agent_mask, self._FLAG_DTYPES, N * self.A, "agent_mask"), self._stream()))
+
     # ---- compact host outputs (include/zs_b200.h: zs_step_compact / zs_expand_compact)
     def compact_words(self):
         """Words per compact observation record, 0 if this configuration has no compact form."""

@@ -75,7 +75,10 @@ def test_launches_from_image_equal_launches_from_state(monkeypatch, name, N):
     for (tag, ta, sa), (_, tb, sb) in zip(with_img, without):
         for i, (x, y) in enumerate(zip(ta, tb)):
             xv, yv = (x.view(torch.int64), y.view(torch.int64)) if x.dtype == torch.float64 else (x, y)
-            assert torch.equal(xv, yv), "%s: output %d differs" % (tag, i)
+            if not torch.equal(xv, yv):
+                bad = (xv != yv).nonzero()
+                raise AssertionError("%s: output %d differs at %d places, first %s: %s vs %s" % (
+                    tag, i, len(bad), bad[0].tolist(), xv[tuple(bad[0].tolist())].item(), yv[tuple(bad[0].tolist())].item()))
         assert_same_state(sa, sb, M)
 
 

@@ -4,6 +4,7 @@ epilogue, ramp), the slope the steady-state cost of a fused step.
 
     python tools/probe_launch_cost.py [config] [N]
 """
+import os
 import sys
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import torch
@@ -29,7 +30,8 @@ def main():
     eng.rollout(200, 0, acts, abi.ACTIONS_DISCRETE, obs, rew, term, trunc)  # desynchronise the episodes
     torch.cuda.synchronize()
     rows = []
-    for K in (1, 2, 3, 4, 5, 8, 12, 16, 20, 32, 64, 128, 512):
+    ks = [int(k) for k in os.environ.get("PROBE_KS", "1,2,3,4,5,8,12,16,20,32,64,128,512").split(",")]
+    for K in ks:
         est = 0.03 + 0.006 * K  # ms per launch, rough
         R = max(3, int(40.0 / est))
         for _ in range(3):
@@ -61,9 +63,10 @@ def main():
     ev[1].record()
     torch.cuda.synchronize()
     print("zs_step back-to-back: %.2f us/launch" % (ev[0].elapsed_time(ev[1]) / 2000 * 1e3))
-    (k0, m0, _), (k1, m1, _) = rows[8], rows[-1]
-    slope = (m1 - m0) / (k1 - k0)
-    print("slope %.2f us/step, intercept at K=20: %.2f us" % (slope * 1e3, (m0 - slope * k0) * 1e3))
+    if len(rows) >= 9:
+        (k0, m0, _), (k1, m1, _) = rows[8], rows[-1]
+        slope = (m1 - m0) / (k1 - k0)
+        print("slope %.2f us/step, intercept at K=20: %.2f us" % (slope * 1e3, (m0 - slope * k0) * 1e3))
     eng.close()
 
 
