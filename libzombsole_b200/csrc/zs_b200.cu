@@ -284,6 +284,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         // ---- same-step auto-reset
         const bool need_init = (done || trunc) && auto_reset;
         if (wany<G, CV>(e, need_init)) {
+            TRF(8);
             if (need_init && lane == 0) {
                 atomicAdd(p.stats + 0, 1ull);
                 if (done && won) atomicAdd(p.stats + 1, 1ull);
@@ -319,7 +320,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         }
         gsync<G, CV>(e);
         PH(11);
-        if (step < 20) TR(4 + step);
+        if (step < 16) TR(4 + step);
     }
 #ifdef ZS_PHASE_CLOCKS
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -356,6 +357,9 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
     e.ph_last = clock64();
 #endif
     if (MODE == MODE_STEP) { TR(0); TR(31); }
+    // (programmatic dependent launch, launch_sim: the next kernel of the stream may start scheduling its CTAs now; it
+    // waits for this grid's completion in its own griddepcontrol.wait)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;  // (a CTA has ZS_WPC warps, or fewer for small batches)
     unsigned long long* const tmpl_bar = reinterpret_cast<unsigned long long*>(zs_smem + p.tmpl_smem_off + (p.tmpl_pair ? 2 : 1) * p.tmpl_bytes);
     if (p.tmpl_smem_off >= 0) {
@@ -370,6 +374,8 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
         }
         __syncthreads();  // (the barrier exists before anybody waits on it)
     }
+    // everything below reads what earlier work of the stream wrote (state, images, actions, masks)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (env >= p.N) return;
     e.tmpl_saddr = 0;
     if (p.tmpl_smem_off >= 0) {
@@ -500,11 +506,16 @@ struct ZsHandle {
     int64_t launches;
     int64_t bound_bytes;
     int sm_count;
-    int envs_per_cta;
-    int lanes_per_env;
-    int warps_per_cta;
-    int occ;
-    int smem_bytes;
+    // How a launch is cut into lane groups, CTAs and shared memory.  shape[0] serves fused rollouts; shape[1] the short
+    // launches (single steps, resets, encodes).  They differ for small worlds in mid-sized batches: two envs per warp halve
+    // the instructions of a long rollout, one env per warp gives a short launch the shorter critical path (fewer slow
+    // paths per warp, no waiting for the partner env).  Both work on the same state and the same parked images.
+    struct Shape {
+        int lanes_per_env, warps_per_cta, envs_per_cta, smem_per_env, smem_bytes, occ;
+        int tmpl_smem_off, tmpl_planes, tmpl_pair, tmpl_bytes;
+    } shape[2];
+    int short_steps;       // launches of fewer steps than this take shape[1]
+    int use_pdl;           // launch with programmatic stream serialization (launch_sim)
     int compact_words;     // words per compact observation record, 0 = this configuration has no compact form
     std::vector<int32_t> tmpl_obs_host;  // the pristine observation planes [obs_C][cells] (zs_expand_compact)
     int tmpl_single_step;  // launches of fewer than four steps stage the observation template for the TMA as well
@@ -599,29 +610,42 @@ template <int MODE>
 static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     // staging the observation template for the TMA pays off when a launch runs several steps
     ZsParams pp = h->p;
-    int smem = h->smem_bytes;
+    const ZsHandle::Shape& sh = h->shape[(MODE == MODE_STEP && io.n_steps >= h->short_steps && io.env_mask == nullptr) ? 0 : 1];
+    pp.smem_per_env = sh.smem_per_env; pp.tmpl_smem_off = sh.tmpl_smem_off; pp.tmpl_planes = sh.tmpl_planes;
+    pp.tmpl_pair = sh.tmpl_pair; pp.tmpl_bytes = sh.tmpl_bytes;
+    int smem = sh.smem_bytes;
     // envs in flight chip-wide, roughly: the distance load_state prefetches ahead (a launch of many short-lived CTAs)
-    pp.prefetch_ahead = (MODE != MODE_STEP || io.n_steps < 4) && !getenv("ZS_NO_PREFETCH") ? h->sm_count * 7 * h->envs_per_cta : 0;
+    pp.prefetch_ahead = (MODE != MODE_STEP || io.n_steps < 4) && !getenv("ZS_NO_PREFETCH") ? h->sm_count * 7 * sh.envs_per_cta : 0;
     if (MODE != MODE_STEP || (io.n_steps < 4 && h->tmpl_single_step == 0)) {  // (and without the template a CTA more fits an SM)
         if (pp.tmpl_smem_off >= 0) smem = pp.tmpl_smem_off;
         pp.tmpl_smem_off = -1;
     }
     // start from the parked images when they are current; a launch that goes through every env leaves them current
     pp.img_load = pp.img != nullptr && h->img_valid;
-    const dim3 grid((pp.N + h->envs_per_cta - 1) / h->envs_per_cta), block(h->warps_per_cta * 32);
+    const dim3 grid((pp.N + sh.envs_per_cta - 1) / sh.envs_per_cta), block(sh.warps_per_cta * 32);
     // the standard rollout shape gets the kernel with that shape compiled in (step_loop_one)
     const bool fast = MODE == MODE_STEP && pp.mpc <= 32 && pp.A == 1 && !pp.obs_per_agent && pp.minimum_zombies == 0 &&
                       pp.obs_scope == ZS_OBS_WORLD && io.actions && io.fmt == ZS_ACTIONS_DISCRETE && io.obs && io.reward &&
                       io.terminated && io.truncated && !io.draws && !io.agent_mask;
-    const int occ = MODE == MODE_STEP ? h->occ : ZS_MIN_CTAS;
+    const int occ = MODE == MODE_STEP ? sh.occ : ZS_MIN_CTAS;
     const bool surr = pp.obs_scope == ZS_OBS_SURROUNDINGS;
     // SH_: 0 world scope, 1 the standard rollout shape (step launches only), 2 surroundings (zs_sim_kernel: SHAPE)
-#define ZS_LAUNCH(MPC_, G_, SH_, O_) zs_sim_kernel<MODE, MPC_, G_, ((SH_) == 1 && MODE != MODE_STEP) ? 0 : (SH_), MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS><<<grid, block, smem, st>>>(pp, io)
+    // Programmatic dependent launch: the kernel's CTAs may be scheduled while the previous kernel of the stream is still
+    // draining (they stage the observation template and then wait in griddepcontrol.wait for that kernel to have
+    // completed, all its writes visible) — the launch latency and the ramp hide under the predecessor's tail.
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = (size_t)smem; lc.stream = st;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    la[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = la; lc.numAttrs = h->use_pdl ? 1 : 0;
+#define ZS_LAUNCH(MPC_, G_, SH_, O_) cudaLaunchKernelEx(&lc, zs_sim_kernel<MODE, MPC_, G_, ((SH_) == 1 && MODE != MODE_STEP) ? 0 : (SH_), MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS>, pp, io)
 #define ZS_LAUNCH_F(MPC_, G_, O_) do { if (fast) ZS_LAUNCH(MPC_, G_, 1, O_); else if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
 #define ZS_LAUNCH_G(MPC_, G_, O_) do { if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
     switch (pp.mpc) {
         case 16:
-            if (h->lanes_per_env == 16) {
+            if (sh.lanes_per_env == 16) {
                 if (occ == ZS_MIN_CTAS_LOWOCC) ZS_LAUNCH_F(16, 16, ZS_MIN_CTAS_LOWOCC);
                 else if (occ == ZS_MIN_CTAS_G16) ZS_LAUNCH_F(16, 16, ZS_MIN_CTAS_G16);
                 else ZS_LAUNCH_F(16, 16, ZS_MIN_CTAS);
@@ -841,7 +865,11 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     for (int i = 0; i < p.P; ++i) if (p.bot_kinds[i] != ZS_KIND_TERMINATOR && p.bot_kinds[i] != ZS_KIND_SNIPER) p.fast_init = 0;
     for (int i = 0; i < p.A; ++i) if (p.agent_weapons[i] == ZS_WEAPON_RANDOM) p.fast_init = 0;
     if (getenv("ZS_NO_FAST_INIT")) p.fast_init = 0;
-    if (p.fast_init) cand = p.n_ps + p.n_zs;  // both index lists side by side
+    if (p.fast_init) {
+        cand = p.n_ps + p.n_zs;  // both index lists side by side
+        for (int i = 0; i < p.n_ps; ++i) p.spawn_cells[i] = ps[i];
+        for (int i = 0; i < p.n_zs; ++i) p.spawn_cells[p.n_ps + i] = zs[i];
+    }
     p.cand_cap = cand;
     // the candidate list is only touched while things are being placed: long ones (a map without spawn cells offers every
     // cell) live in device memory, so they do not cost resident CTAs
@@ -873,71 +901,91 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     // lanes per env: a half warp (two envs per warp, in lock-step) when an env has at most 16 slots, the env count is
     // even and the batch is large enough that the halved instruction count matters more than the few extra cycles a
     // two-env warp needs per step (measured cross-over: about 16 envs per SM)
-    h->lanes_per_env = (p.mpc == 16 && p.N % 2 == 0 && p.N > prop.multiProcessorCount * 16) ? 16 : 32;
+    int lanes0 = (p.mpc == 16 && p.N % 2 == 0 && p.N > prop.multiProcessorCount * 16) ? 16 : 32;
+    // ... for fused rollouts.  A short launch of such a batch runs one env per warp as long as all its warps are resident
+    // at once (measured at 4,096 bridge envs: a single step takes 16.6 us with one env per warp, 21.8 us with two; from
+    // about eight fused steps on two envs per warp win)
+    int lanes1 = lanes0;
+    if (lanes0 == 16 && p.N <= prop.multiProcessorCount * 28 && !getenv("ZS_ONE_SHAPE")) lanes1 = 32;
     if (const char* force = getenv("ZS_LANES_PER_ENV")) {
         const int v = atoi(force);
-        if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) h->lanes_per_env = v;
+        if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) lanes0 = lanes1 = v;
     }
-    // two envs per warp: the halves touch the same fields of neighbouring env blocks with the same instruction, so the
-    // blocks are placed half a bank row apart (an odd multiple of 64 bytes): 16 lanes x 4 bytes of one env and of the
-    // other then fall on different banks.  (Swept on the bridge map, ZS_SMEM_SKEW = 0 .. 112: no measurable difference
-    // either way — the step is bound by dependent latency, not by shared-memory wavefronts; it fixes the layout so that
-    // a change of sizeof(EnvS) cannot move the two halves onto the same banks.)
-    if (h->lanes_per_env == 16) {
-        int skew = 64;
-        if (const char* force = getenv("ZS_SMEM_SKEW")) skew = atoi(force) & 0x70;
-        while ((p.smem_per_env & 127) != skew) p.smem_per_env += 16;
-    }
-    // warps per CTA: ZS_WPC, or 2 when the batch is small enough that 4-warp CTAs would spread unevenly over the SMs
-    // (a small batch is latency-bound: the most loaded SM sets the pace)
-    h->warps_per_cta = ZS_WPC;
-    if ((p.N + ZS_WPC * (32 / h->lanes_per_env) - 1) / (ZS_WPC * (32 / h->lanes_per_env)) < prop.multiProcessorCount * 5) h->warps_per_cta = 2;
-    if (const char* force = getenv("ZS_WARPS_PER_CTA")) { const int v = atoi(force); if (v == 1 || v == 2 || v == 4) h->warps_per_cta = v; }
-    h->envs_per_cta = h->warps_per_cta * (32 / h->lanes_per_env);
-    h->smem_bytes = p.smem_per_env * h->envs_per_cta;
-    p.tmpl_smem_off = -1; p.tmpl_planes = 0;
-    if (p.obs_scope == ZS_OBS_WORLD && (p.cells & 3) == 0) {
-        const int planes = p.obs_enc == ZS_OBS_CHANNELS ? 3 : 1;
-        int bytes = planes * p.cells * 4;
-        // two envs per warp in a batch that fits the chip at 16 warps per SM: one bulk copy for both (obs_world_template)
-        const bool pair = h->lanes_per_env == 16 && p.N / 2 <= prop.multiProcessorCount * ZS_MIN_CTAS_LOWOCC * ZS_WPC &&
-                          (h->smem_bytes + 2 * bytes + 1024) * (16 / h->warps_per_cta) <= (int)prop.sharedMemPerMultiprocessor &&
-                          !getenv("ZS_NO_TMA_PAIR");
-        if (pair) bytes *= 2;
-        // keep at least 6 CTAs per SM resident (2-warp CTAs are only chosen for batches that need no more)
-        if ((h->smem_bytes + bytes + 1024) * 6 <= (int)prop.sharedMemPerMultiprocessor && !getenv("ZS_NO_TMA")) {
-            p.tmpl_smem_off = h->smem_bytes; p.tmpl_planes = planes; p.tmpl_pair = pair; p.tmpl_bytes = planes * p.cells * 4;
-            h->smem_bytes += bytes + 16;  // (+ the mbarrier of the staging copy)
-        }
-    }
+    h->short_steps = 8;
+    h->use_pdl = getenv("ZS_PDL") ? 1 : 0;  // (measured: -8 % on back-to-back single steps, but a launch on an idle stream starts later)
+    if (const char* force = getenv("ZS_SHORT_STEPS")) h->short_steps = atoi(force);
     h->tmpl_single_step = getenv("ZS_NO_TMA_SINGLE") ? 0 : 1;
     h->compact_words = (p.mpc <= 32 && p.obs_scope == ZS_OBS_WORLD && !p.obs_per_agent)
                            ? (p.obs_enc == ZS_OBS_SIMPLE ? 128 : 256) : 0;
-    if (h->smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
-    if (int rc2 = set_smem_attr(p.mpc, h->lanes_per_env, h->smem_bytes)) { zs_destroy(h); return rc2; }
-    // resident CTAs per SM the step kernel is compiled for (zs_sim_kernel: OCC): fewest rounds first, then most registers;
-    // batches of three rounds or more are issue-bound and take the occupancy
-    h->occ = ZS_MIN_CTAS;
-    if (p.mpc <= 32) {
-        const int epw = 32 / h->lanes_per_env;
-        const long long warps = ((long long)p.N + epw - 1) / epw;
-        const int cands16[3] = {ZS_MIN_CTAS_LOWOCC, ZS_MIN_CTAS_G16, ZS_MIN_CTAS}, cands32[2] = {ZS_MIN_CTAS_LOWOCC, ZS_MIN_CTAS};
-        const int* cands = h->lanes_per_env == 16 ? cands16 : cands32;
-        const int nc = h->lanes_per_env == 16 ? 3 : 2;
-        long long rounds[3], best = 0;
-        for (int i = 0; i < nc; ++i) {
-            long long cap = (long long)resident_warps(p.mpc, h->lanes_per_env, cands[i], h->warps_per_cta * 32, h->smem_bytes) * prop.multiProcessorCount;
-            if (cap < 1) cap = 1;
-            rounds[i] = (warps + cap - 1) / cap;
-            if (i == 0 || rounds[i] < best) best = rounds[i];
+    const int smem_per_env_base = p.smem_per_env;
+    for (int si = 0; si < 2; ++si) {
+        ZsHandle::Shape& sh = h->shape[si];
+        if (si == 1 && lanes1 == lanes0) { sh = h->shape[0]; break; }
+        sh.lanes_per_env = si == 0 ? lanes0 : lanes1;
+        sh.smem_per_env = smem_per_env_base;
+        // two envs per warp: the halves touch the same fields of neighbouring env blocks with the same instruction, so the
+        // blocks are placed half a bank row apart (an odd multiple of 64 bytes): 16 lanes x 4 bytes of one env and of the
+        // other then fall on different banks.  (Swept on the bridge map, ZS_SMEM_SKEW = 0 .. 112: no measurable difference
+        // either way — the step is bound by dependent latency, not by shared-memory wavefronts; it fixes the layout so that
+        // a change of sizeof(EnvS) cannot move the two halves onto the same banks.)
+        if (sh.lanes_per_env == 16) {
+            int skew = 64;
+            if (const char* force = getenv("ZS_SMEM_SKEW")) skew = atoi(force) & 0x70;
+            while ((sh.smem_per_env & 127) != skew) sh.smem_per_env += 16;
         }
-        if (best >= 3) h->occ = h->lanes_per_env == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS;
-        else for (int i = 0; i < nc; ++i) if (rounds[i] == best) { h->occ = cands[i]; break; }
-        if (const char* force = getenv("ZS_OCC")) {
-            const int v = atoi(force);
-            if (v == ZS_MIN_CTAS_LOWOCC || v == ZS_MIN_CTAS || (v == ZS_MIN_CTAS_G16 && h->lanes_per_env == 16)) h->occ = v;
+        // warps per CTA: ZS_WPC, or 2 when the batch is small enough that 4-warp CTAs would spread unevenly over the SMs
+        // (a small batch is latency-bound: the most loaded SM sets the pace)
+        const int epw = 32 / sh.lanes_per_env;
+        sh.warps_per_cta = ZS_WPC;
+        if ((p.N + ZS_WPC * epw - 1) / (ZS_WPC * epw) < prop.multiProcessorCount * 5) sh.warps_per_cta = 2;
+        if (const char* force = getenv("ZS_WARPS_PER_CTA")) { const int v = atoi(force); if (v == 1 || v == 2 || v == 4) sh.warps_per_cta = v; }
+        sh.envs_per_cta = sh.warps_per_cta * epw;
+        sh.smem_bytes = sh.smem_per_env * sh.envs_per_cta;
+        sh.tmpl_smem_off = -1; sh.tmpl_planes = 0; sh.tmpl_pair = 0; sh.tmpl_bytes = 0;
+        if (p.obs_scope == ZS_OBS_WORLD && (p.cells & 3) == 0) {
+            const int planes = p.obs_enc == ZS_OBS_CHANNELS ? 3 : 1;
+            int bytes = planes * p.cells * 4;
+            // two envs per warp: ONE bulk copy can serve both envs of a warp (their rows are neighbours) from planes staged
+            // twice back to back.  Off by default since the staging itself became an asynchronous bulk copy: measured
+            // slightly behind one copy per env (ZS_TMA_PAIR=1 turns it on)
+            const bool pair = sh.lanes_per_env == 16 && getenv("ZS_TMA_PAIR") && !getenv("ZS_NO_TMA_PAIR") &&
+                              p.N / 2 <= prop.multiProcessorCount * ZS_MIN_CTAS_LOWOCC * ZS_WPC &&
+                              (sh.smem_bytes + 2 * bytes + 1024) * (16 / sh.warps_per_cta) <= (int)prop.sharedMemPerMultiprocessor;
+            if (pair) bytes *= 2;
+            // keep at least 6 CTAs per SM resident (2-warp CTAs are only chosen for batches that need no more)
+            if ((sh.smem_bytes + bytes + 1024) * 6 <= (int)prop.sharedMemPerMultiprocessor && !getenv("ZS_NO_TMA")) {
+                sh.tmpl_smem_off = sh.smem_bytes; sh.tmpl_planes = planes; sh.tmpl_pair = pair; sh.tmpl_bytes = planes * p.cells * 4;
+                sh.smem_bytes += bytes + 16;  // (+ the mbarrier of the staging copy)
+            }
+        }
+        if (sh.smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
+        // (the attribute belongs to the kernel, not to the handle: every handle asks for all a CTA can have, so that handles
+        // of different maps can live side by side)
+        if (int rc2 = set_smem_attr(p.mpc, sh.lanes_per_env, (int)prop.sharedMemPerBlockOptin)) { zs_destroy(h); return rc2; }
+        // resident CTAs per SM the step kernel is compiled for (zs_sim_kernel: OCC): fewest rounds first, then most
+        // registers; batches of three rounds or more are issue-bound and take the occupancy
+        sh.occ = ZS_MIN_CTAS;
+        if (p.mpc <= 32) {
+            const long long warps = ((long long)p.N + epw - 1) / epw;
+            const int cands16[3] = {ZS_MIN_CTAS_LOWOCC, ZS_MIN_CTAS_G16, ZS_MIN_CTAS}, cands32[2] = {ZS_MIN_CTAS_LOWOCC, ZS_MIN_CTAS};
+            const int* cands = sh.lanes_per_env == 16 ? cands16 : cands32;
+            const int nc = sh.lanes_per_env == 16 ? 3 : 2;
+            long long rounds[3], best = 0;
+            for (int i = 0; i < nc; ++i) {
+                long long cap = (long long)resident_warps(p.mpc, sh.lanes_per_env, cands[i], sh.warps_per_cta * 32, sh.smem_bytes) * prop.multiProcessorCount;
+                if (cap < 1) cap = 1;
+                rounds[i] = (warps + cap - 1) / cap;
+                if (i == 0 || rounds[i] < best) best = rounds[i];
+            }
+            if (best >= 3) sh.occ = sh.lanes_per_env == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS;
+            else for (int i = 0; i < nc; ++i) if (rounds[i] == best) { sh.occ = cands[i]; break; }
+            if (const char* force = getenv("ZS_OCC")) {
+                const int v = atoi(force);
+                if (v == ZS_MIN_CTAS_LOWOCC || v == ZS_MIN_CTAS || (v == ZS_MIN_CTAS_G16 && sh.lanes_per_env == 16)) sh.occ = v;
+            }
         }
     }
+    p.smem_per_env = h->shape[0].smem_per_env;
 
     *out = h;
     return 0;
@@ -1026,9 +1074,9 @@ extern "C" __attribute__((visibility("default"))) int zs_step_masked(ZsHandle* h
     DeviceGuard guard(h);
     if (!actions_dev) return fail("zs_step_masked needs an action tensor");
     if (action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
-    if (env_mask_dev && h->lanes_per_env != 32)
-        return fail("masked steps need one warp per env: this handle packs two envs per warp (batches of more than 16 envs per SM "
-                    "of at most 16 things; set ZS_LANES_PER_ENV=32 before zs_create)");
+    if (env_mask_dev && h->shape[1].lanes_per_env != 32)
+        return fail("masked steps need one warp per env: this handle packs two envs per warp in every launch (very large batches "
+                    "of at most 16 things per env, or ZS_LANES_PER_ENV=16)");
     ZsIO io;
     memset(&io, 0, sizeof(io));
     io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1; io.reward = reward_dev;
@@ -1178,4 +1226,4 @@ extern "C" __attribute__((visibility("default"))) int zs_debug_trace(unsigned lo
 #endif
 
 extern "C" __attribute__((visibility("default"))) int64_t zs_launch_count(const ZsHandle* h) { return h ? h->launches : 0; }
-extern "C" __attribute__((visibility("default"))) int32_t zs_lanes_per_env(const ZsHandle* h) { return h ? h->lanes_per_env : 0; }
+extern "C" __attribute__((visibility("default"))) int32_t zs_lanes_per_env(const ZsHandle* h) { return h ? h->shape[0].lanes_per_env : 0; }

@@ -63,6 +63,8 @@ struct ZsParams {
     uint8_t agent_weapons[ZS_MAX_AGENTS];
     uint8_t bot_kinds[ZS_MAX_BOTS];
     int32_t agent_obs_ids[ZS_MAX_AGENTS];
+    uint16_t spawn_cells[256];     // fast_init: the player spawn cells, then the zombie spawn cells (n_ps + n_zs <= 256), in
+                                   // the kernel parameters so that a world init reads them through the constant cache
     // ---- map tables (device, read-only)
     const int16_t* cell_static;    // [cells] static index or -1
     const uint16_t* static_cell;   // [Sp] cell of static i
@@ -330,8 +332,15 @@ __device__ __forceinline__ unsigned zs_smid() { unsigned r; asm volatile("mov.u3
         if ((threadIdx.x & 31) == 0 && _w < ZS_TRACE_WARPS && (i) < ZS_TRACE_SLOTS)                   \
             zs_trace_buf[_w * ZS_TRACE_SLOTS + (i)] = (i) == 31 ? (unsigned long long)zs_smid() : zs_globaltimer(); \
     } while (0)
+// which of the less common paths a warp took during the launch (slot 28, one bit each)
+#define TRF(bit)                                                                                      \
+    do {                                                                                              \
+        const int _w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);                           \
+        if ((threadIdx.x & 31) == 0 && _w < ZS_TRACE_WARPS) zs_trace_buf[_w * ZS_TRACE_SLOTS + 28] |= (1ull << (bit)); \
+    } while (0)
 #else
 #define TR(i) do { } while (0)
+#define TRF(bit) do { } while (0)
 #endif
 
 // ---------------------------------------------------------------- lane-group primitives

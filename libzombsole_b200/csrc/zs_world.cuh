@@ -200,14 +200,20 @@ ZS_TPL __device__ __forceinline__ void spl_update_one(const ZsParams& p, const E
 }
 
 // A new world: every box/wall is back in World.things, also the ones with life <= 0 (game.py:154-155).
-ZS_TPL __device__ __forceinline__ void spl_refresh_present(const ZsParams& p, const Env& e) {
+// (An entry with a payload already shows its box/wall as present with its current life: only the entries of boxes/walls
+// that were gone — payload 0 — change, so the map tables are only read for those.)  restore_grid: the grid is not
+// rebuilt from the template by the caller; the returning boxes/walls are put back on it here.
+ZS_TPL __device__ __forceinline__ void spl_refresh_present(const ZsParams& p, const Env& e, bool restore_grid = false) {
     ZS_VIEWS;
     const int n = SPN;
 #pragma unroll 1
     for (int i = e.gl; i < n; i += G) {
-        const int cell = SPL(i) & 0xffffu;
+        const uint32_t w = SPL(i);
+        if ((w >> 16) != 0u) continue;
+        const int cell = w & 0xffffu;
         const int si = __ldg(p.cell_static + cell);
         SPL(i) = (uint32_t)cell | ((uint32_t)static_payload(p, __ldg(p.static_max + si), SL(si), true) << 16);
+        if (restore_grid) GRID(cell) = G_STATIC;
     }
 }
 
@@ -1315,6 +1321,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             if (type == D_WANDER || type == D_RANDOM) unpack_decision(BK(s), type, a, b);
         }
     } else if (wany<G, CV>(e, type == D_WANDER)) {
+        TRF(0);
         const unsigned wm = gor_bits<G, CV>(e, type == D_WANDER ? (1u << rk) : 0u);
         if (type == D_WANDER) {
             int pick = below(draw_at(p, e, t_word, __popc(wm & ((1u << rk) - 1u))), __popc(freemask));
@@ -1328,6 +1335,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     // the idle things before it.  Everything that cannot change before the actor acts is resolved here.
     int pos = (int)rk;
     if (wany<G, CV>(e, live && type == D_IDLE)) {
+        TRF(1);
         const unsigned im = gor_bits<G, CV>(e, (live && type == D_IDLE) ? (1u << rk) : 0u);
         pos -= __popc(im & ((1u << (rk & 31u)) - 1u));
     }
@@ -1427,6 +1435,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             inrange = dist2(xy_x(hi32), xy_y(hi32), xy_x(txy), xy_y(txy)) <= (int)((lo32 >> 11) & 127);
         }
         if (wany<G, CV>(e, inrange)) {
+            TRF(2);
             const unsigned hit_m = gballot<G, CV>(e, inrange);
             const int si = hi32 & 0xffffu;
             const bool heal = kind == X_HEAL_M || kind == X_HEAL_S;
@@ -1454,6 +1463,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             }
             const bool slead = lead && on_static;
             if (wany<G, CV>(e, slead)) {
+                TRF(3);
                 // a box/wall changed: clean_dead_things (core.py:121-138) for the ones destroyed now (on the first step of
                 // a world the clean phase covers them), and their entries in the static patch list
                 bool is_new = false, gone = false;
@@ -1483,6 +1493,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             }
         }
         gsync<G, CV>(e);
+        if (wany<G, CV>(e, seq)) TRF(4);
         if (seq) {  // rare, and possibly only one env of the warp: the divergent flavour from here
             if (s == 0) { SCALW(0) = k; SCALW(1) = e.flags; SCALW(2) = e.deaths; }
             gsync<G, false>(e);
@@ -1496,6 +1507,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     int nd_all = 0;
     const bool fresh_scan = (e.flags & FL_FRESH) && (e.flags & FL_DMG);
     if (e.flags & FL_FRESH) {  // first step of this world: every box/wall with life <= 0 leaves now
+        TRF(7);
         if (e.flags & FL_DMG) nd_all = spl_clean_fresh<MPC, G, CV>(p, e);
         e.flags &= ~FL_FRESH;
     }
@@ -1514,6 +1526,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     }
     const unsigned dead_m = gballot<G, CV>(e, dead);
     if (wany<G, CV>(e, dead)) {  // remember the cells for the observation patches (the bitmap stays the state)
+        TRF(5);
         const int n0 = DBL(0), idx = n0 + __popc(dead_m & below_s), tot = n0 + __popc(dead_m);
         gsync<G, CV>(e);  // (everybody has read the count before lane 0 rewrites it)
         if (dead && idx < ZS_DEAD_CAP) DBL(1 + idx) = (uint16_t)(xy_y(nxy) * p.W + xy_x(nxy));
@@ -1526,6 +1539,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     if (wany<G, CV>(e, fresh_scan)) e.deaths += gadd<G, CV>(e, nd_all);  // (nd_all is 0 for an env that did not scan)
     e.zd += __popc(dead_m >> NP);
     if (wany<G, CV>(e, succ_m || dead_m)) {  // (an env without changes gets its old ranks back)
+        TRF(6);
         const bool alive = live && !dead;
         const unsigned stay_m = gor_bits<G, CV>(e, (alive && !moved) ? (1u << rk) : 0u);
         const unsigned move_m = gor_bits<G, CV>(e, (alive && moved) ? (1u << mvp) : 0u);
@@ -1699,6 +1713,7 @@ ZS_TPL __device__ __forceinline__ int initialize_world_fast(const ZsParams& p, E
     // candidates consumes n - 1 draws whatever is placed
     const int n1 = p.n_ps, n2 = p.n_ps - P, n3 = p.n_zs;
     const int K1 = n1 > 1 ? n1 - 1 : 0, K2 = K1 + (n2 > 1 ? n2 - 1 : 0), K3 = K2 + Z0, K4 = K3 + (n3 > 1 ? n3 - 1 : 0);
+    TR(20);
     const bool in_cap = G == MPC || s < MPC;
     const bool is_bot = s < P, is_agent = !is_bot && s < NP, placed = s < NP + Z0;
     const int base = is_bot ? 0 : is_agent ? P : NP;
@@ -1728,19 +1743,34 @@ ZS_TPL __device__ __forceinline__ int initialize_world_fast(const ZsParams& p, E
         }
         if (is_agent) q = x;
     }
-    const int c = placed ? (int)(s < NP ? __ldg(p.ps_cells + q) : __ldg(p.zs_cells + q)) : 0;
+    const int c = placed ? (int)p.spawn_cells[s < NP ? q : n1 + q] : 0;  // (kernel parameters: constant cache, no trip to memory)
     const int flags_in = e.flags;
+    TR(21);
+    // The grid of a new world is the pristine template: every box/wall is back, nothing else is on it.  It is reached from
+    // the old world's grid by taking off what the lists name — the things in the world, the dead bodies — and putting
+    // back the boxes/walls that were gone; all of it in shared memory (the template copy was a trip to the L2).
+    const bool by_lists = !(flags_in & FL_DEAD_OVER);
     if (need) {
-        // decorations and the grid of a new world (= the pristine template: every box/wall is back)
+        if (by_lists) {
+            if (in_cap && (TM(s) & 0x80)) { const uint32_t oxy = TXY(s); GRID(xy_y(oxy) * p.W + xy_x(oxy)) = G_EMPTY; }
+            const int nb = DBL(0);
 #pragma unroll 1
-        for (int w = s; w < p.dead_words; w += G) DEADW(w) = 0;
-        if (s == 0) DBL(0) = 0;
-        const uint4* tg = (const uint4*)p.tmpl_grid;
+            for (int i = s; i < nb; i += G) { const int dc = DBL(1 + i); GRID(dc) = G_EMPTY; DEADW(dc >> 5) = 0u; }
+        } else {  // the dead-body list is not complete: the template, and the whole bitmap
+            const uint4* tg = (const uint4*)p.tmpl_grid;
 #pragma unroll 6
-        for (int i = s; i < (p.cells_pad >> 4); i += G) reinterpret_cast<uint4*>(GRIDP)[i] = __ldg(tg + i);
-        if (flags_in & FL_DMG) spl_refresh_present<MPC, G, CV>(p, e);
+            for (int i = s; i < (p.cells_pad >> 4); i += G) reinterpret_cast<uint4*>(GRIDP)[i] = __ldg(tg + i);
+#pragma unroll 1
+            for (int w = s; w < p.dead_words; w += G) DEADW(w) = 0;
+        }
     }
     gsync<G, CV>(e);
+    if (need) {
+        if (s == 0) DBL(0) = 0;
+        if (flags_in & FL_DMG) spl_refresh_present<MPC, G, CV>(p, e, by_lists);
+    }
+    gsync<G, CV>(e);
+    TR(22);
     if (need && in_cap) {
         int w = ZS_WEAPON_CLAWS;
         if (is_bot) w = p.bot_kinds[s] == ZS_KIND_SNIPER ? ZS_WEAPON_RIFLE : ZS_WEAPON_SHOTGUN;  // sniper.py:23-24, terminator.py:41-42
@@ -1762,6 +1792,7 @@ ZS_TPL __device__ __forceinline__ int initialize_world_fast(const ZsParams& p, E
         e.flags = (flags_in & (FL_DMG | FL_SL_DIRTY)) | FL_FRESH | ((flags_in & FL_DEAD_LAUNCH) ? (FL_DEAD_OVER | FL_DEAD_LAUNCH) : 0);
     }
     gsync<G, CV>(e);
+    TR(23);
     return K4;
 }
 

@@ -53,20 +53,26 @@ def main():
         print("  build_grid                ", q(t[:, 3] - t[:, 2]))
         print("  wait for the obs template  ", q(t[:, 29] - t[:, 3]))
         prev = t[:, 29]
-        for s in range(min(K, 20)):
+        for s in range(min(K, 16)):
             cur = t[:, 4 + s]
             print("  step %2d                   " % s, q(cur - prev))
             prev = cur
         print("  last traced step -> exit  ", q(t[:, 30] - prev))
-        last0 = t[:, 4 + K - 2] if 2 <= K <= 20 else t[:, 29]
-        if K <= 20:
+        last0 = t[:, 4 + K - 2] if 2 <= K <= 16 else t[:, 29]
+        if K <= 16:
             print("  LAST step: template issue  ", q(t[:, 24] - last0))
             print("  LAST step: world_step      ", q(t[:, 25] - t[:, 24]))
             print("  LAST step: reward/rules/out", q(t[:, 26] - t[:, 25]))
             print("  LAST step: world init      ", q(t[:, 27] - t[:, 26]), " (%d warps > 1 us)" % int(((t[:, 27] - t[:, 26]) > 1000).sum()))
             print("  LAST step: obs patches     ", q(t[:, 4 + K - 1] - t[:, 27]))
+        did = t[:, 23] > t[:, 20]
+        did &= t[:, 20] > t0
+        if did.any():
+            print("  world init (last one of %d warps): draws+shuffle %s" % (int(did.sum()), q((t[:, 21] - t[:, 20])[did])))
+            print("                                     grid/lists    %s" % q((t[:, 22] - t[:, 21])[did]))
+            print("                                     placement     %s" % q((t[:, 23] - t[:, 22])[did]))
         print("  exit after first entry    ", q(t[:, 30] - t0), "  (kernel span %.2f us)" % ((t[:, 30].max() - t0) / 1e3))
-        if K <= 20:  # is the slow tail of the first step made of each SM's FIRST warps (cold instruction / data caches)?
+        if K <= 16:  # is the slow tail of the first step made of each SM's FIRST warps (cold instruction / data caches)?
             ws = t[:, 25] - t[:, 24]
             smv = t[:, 31]
             by_rank = {}
@@ -79,6 +85,13 @@ def main():
                   {r: round(float(np.mean(v)) / 1e3, 2) for r, v in sorted(by_rank.items())})
             slow = ws > 2 * np.median(ws)
             print("  slow warps (> 2 x median): %d of %d; on %d SMs" % (int(slow.sum()), len(ws), len(set(smv[slow].tolist()))))
+            names = ["wander", "idle", "hits", "static hit", "sequential execute", "deaths", "re-rank", "fresh world", "world init"]
+            fl = t[:, 28]
+            for b, nm in enumerate(names):
+                took = (fl >> b) & 1 == 1
+                if took.any():
+                    print("    path %-20s taken by %4d warps: world_step mean %.2f us (others %.2f); %d of the slow warps" % (
+                        nm, int(took.sum()), ws[took].mean() / 1e3, ws[~took].mean() / 1e3 if (~took).any() else 0, int((took & slow).sum())))
         # per SM: warps, span
         sm = t[:, 31]
         per = [(int(i), int((sm == i).sum()), (t[sm == i, 30].max() - t0) / 1e3) for i in sorted(set(sm.tolist()))]
