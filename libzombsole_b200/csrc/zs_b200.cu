@@ -116,7 +116,7 @@ __device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO&
 #pragma unroll 1
             for (int s0 = NP; s0 < p.M; s0 += G) zc += __popc(gballot<G, CV>(e, s0 + lane < p.M && (TM(s0 + lane) & 0x80)));
             if (zc < p.minimum_zombies) {
-                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive, false);
+                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive, false, false);
                 e.nlive = SCALW(ZS_S_STAMP_COUNTER);
             }
         }
@@ -250,7 +250,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         if (!FAST && p.minimum_zombies > 0) {
             const int zc = __popc(gballot<G, CV>(e, lane >= NP && lane < p.M && (TM(lane < p.M ? lane : 0) & 0x80)));
             if (zc < p.minimum_zombies) {  // rare, and possibly only one env of the warp: the divergent flavour
-                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive, false);
+                k = spawn_zombies<MPC, G, false>(p, id_of(e), e.episode, (uint32_t)(e.t + 1), k, p.minimum_zombies - zc, e.nlive, false, false);
                 e.nlive = SCALW(ZS_S_STAMP_COUNTER);
             }
         }
@@ -827,6 +827,16 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     rc |= upload(h, tmpl_grid, &p.tmpl_grid); rc |= upload(h, tmpl_obs, &p.tmpl_obs);
     h->tmpl_obs_host = tmpl_obs;
     rc |= upload(h, objective_bits, &p.objective_bits); rc |= upload(h, ps, &p.ps_cells); rc |= upload(h, zs, &p.zs_cells);
+    if (p.n_ps == 0 || p.n_zs == 0) {  // some group may stand anywhere: the cells without a box/wall, x-major (core.py:44-46)
+        std::vector<uint16_t> free_xm, free_index(cells, 0xffff);
+        for (int x = 0; x < p.W; ++x)
+            for (int y = 0; y < p.H; ++y) {
+                const int cc = y * p.W + x;
+                if (cell_static[cc] < 0) { free_index[cc] = (uint16_t)free_xm.size(); free_xm.push_back((uint16_t)cc); }
+            }
+        p.n_free0 = (int)free_xm.size();
+        if (!getenv("ZS_NO_FREE_TABLE")) { rc |= upload(h, free_xm, &p.free_xm); rc |= upload(h, free_index, &p.free_index); }
+    }
     std::vector<unsigned long long> zero(4, 0ull);
     const unsigned long long* st = nullptr;
     rc |= upload(h, zero, &st);

@@ -79,6 +79,9 @@ struct ZsParams {
     int32_t win_ints, win_pitch;   // agent standing on the cell, laid out like the output; rows start on 128-byte
                                    // boundaries (L2-resident; NULL when it would be too large)
     const uint32_t* objective_bits;// [dead_words]
+    const uint16_t* free_xm;       // [n_free0] the cells without a box/wall in x-major order: World.spawn_in_random's candidates
+    const uint16_t* free_index;    // [cells] position of a cell in free_xm (maps where some group has no spawn cells; else NULL)
+    int32_t n_free0;
     const uint16_t* ps_cells;      // [n_ps] player spawn cells, file order
     const uint16_t* zs_cells;      // [n_zs]
     // ---- state (device, caller-owned buffer; see ZsLayout)

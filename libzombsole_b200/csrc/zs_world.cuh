@@ -1567,7 +1567,8 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
 // carry boxes/walls, and player and zombie spawn cells are different cells), so the list is taken as it is.
 // Returns the new draw index; the new number of things in the world is left in SCALW(ZS_S_STAMP_COUNTER).
 ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, int episode,
-                                                   uint32_t t_word, int k, int count, int which, int rank0, bool all_free) {
+                                                   uint32_t t_word, int k, int count, int which, int rank0, bool all_free,
+                                                   bool new_world) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
@@ -1577,10 +1578,19 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
     const int n_spawn = which ? p.n_zs : p.n_ps;
     const int n_src = n_spawn > 0 ? n_spawn : p.cells;
     int n = 0;
+    // A group without spawn cells of its own may stand on any cell that holds no thing, taken in x-major order
+    // (core.py:44-52).  In a NEW world those are the cells without a box/wall — a constant of the map, tabulated once
+    // (free_xm) — minus the cells of the things placed so far, which all stand on such cells: the candidate list is not
+    // materialised at all.  Candidate i is entry x of the table, x the smallest index with x - #{taken <= x} == i; the
+    // taken entries (TAKEN, at most the players) are noted as the groups are placed.
+    uint16_t* const TAKEN = reinterpret_cast<uint16_t*>(S.bk);
+    const bool virt = new_world && n_spawn == 0 && p.free_xm != nullptr && rank0 <= ZS_NP_MAX && rank0 <= 2 * MPC;
     if (all_free && n_spawn > 0) {
 #pragma unroll 4
         for (int i = lane; i < n_spawn; i += G) CAND(i) = __ldg(spawn + i);
         n = n_spawn;
+    } else if (virt) {
+        n = p.n_free0 - rank0;
     } else {
 #pragma unroll 1
         for (int b0 = 0; b0 < n_src; b0 += G) {
@@ -1611,11 +1621,24 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
     int16_t* const Pi = reinterpret_cast<int16_t*>(S.draws);  // [MPC] last earlier iteration that wrote position i, or -1
     int16_t* const Pj = Pi + MPC;                             // [MPC] ... position j
     uint16_t* const Ch = reinterpret_cast<uint16_t*>(Pj + MPC);  // [MPC] the cell the it-th thing gets
+    auto cand_at = [&](int i) -> uint16_t {
+        if (!virt) return CAND(i);
+        int x = i;
+#pragma unroll 1
+        for (;;) {
+            int c = 0;
+#pragma unroll 1
+            for (int t = 0; t < rank0; ++t) c += (int)TAKEN[t] <= x;
+            if (i + c == x) break;
+            x = i + c;
+        }
+        return __ldg(p.free_xm + x);
+    };
 #pragma unroll 1
     for (int it = e.gl; it < placed; it += G) {
         const int i = n - 1 - it;
         const int j = i >= 1 ? below(draw_at(p, e, t_word, k + it), i + 1) : i;
-        Jp[it] = (uint16_t)j; Bi[it] = CAND(i); Bj[it] = CAND(j);
+        Jp[it] = (uint16_t)j; Bi[it] = cand_at(i); Bj[it] = cand_at(j);
     }
     gsync<G, CV>(e);
 #pragma unroll 1
@@ -1650,6 +1673,9 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
         SOR(rank0 + it) = (uint8_t)s;
         MVQ(s) = RK_NONE;
         GRID(c) = (uint8_t)(s + 1);
+        // (a later group of this world init may take its candidates from the table: see TAKEN above)
+        if (new_world && p.free_index != nullptr && which == 0 && rank0 + it < ZS_NP_MAX && rank0 + it < 2 * MPC)
+            TAKEN[rank0 + it] = __ldg(p.free_index + c);
     }
     gsync<G, CV>(e);
     return k + (n > 1 ? n - 1 : 0);
@@ -1658,7 +1684,7 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
 // Game.spawn_zombies (game.py:189-194): `count` Zombie() constructions (life draws, things.py:62)
 // followed by spawn_in_random on the zombie spawn cells; free zombie slots are taken in ascending order.
 ZS_TPL __device__ __noinline__ int spawn_zombies(const ZsParams& p, GrpId id, int episode,
-                                                 uint32_t t_word, int k, int count, int rank0, bool all_free) {
+                                                 uint32_t t_word, int k, int count, int rank0, bool all_free, bool new_world) {
     ZS_CONSTS;
     Env e = env_of(p, id);
     ZS_VIEWS;
@@ -1684,7 +1710,7 @@ ZS_TPL __device__ __noinline__ int spawn_zombies(const ZsParams& p, GrpId id, in
         TM(s) = ZS_WEAPON_CLAWS;
     }
     gsync<G, CV>(e);
-    return spawn_in_random<MPC, G, false>(p, id, episode, t_word, k + count, made, 1, rank0, all_free);
+    return spawn_in_random<MPC, G, false>(p, id, episode, t_word, k + count, made, 1, rank0, all_free, new_world);
 }
 
 // Game.__initialize_world__ for the common shape (p.fast_init, decided in zs_create): one lane per slot, a map with
@@ -1867,14 +1893,14 @@ ZS_TPL __device__ __noinline__ int initialize_world(const ZsParams& p, GrpId id,
     for (int s = e.gl; s < p.P; s += G) LIST(s) = (uint16_t)s;
     if (lane == 0) SCALW(ZS_S_STAMP_COUNTER) = 0;
     gsync<G, CV>(e);
-    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.P, 0, 0, true);
+    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.P, 0, 0, true, true);
     PH(15);
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) LIST(a) = (uint16_t)(p.P + a);
     gsync<G, CV>(e);
-    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.A, 0, SCALW(ZS_S_STAMP_COUNTER), p.P == 0);
+    k = spawn_in_random<MPC, G, false>(p, id, episode, 0u, k, p.A, 0, SCALW(ZS_S_STAMP_COUNTER), p.P == 0, true);
     PH(16);
-    k = spawn_zombies<MPC, G, false>(p, id, episode, 0u, k, p.initial_zombies, SCALW(ZS_S_STAMP_COUNTER), true);
+    k = spawn_zombies<MPC, G, false>(p, id, episode, 0u, k, p.initial_zombies, SCALW(ZS_S_STAMP_COUNTER), true, true);
     PH(17);
 #pragma unroll 1
     for (int a = e.gl; a < p.A; a += G) PREVL(a) = TL(p.P + a);

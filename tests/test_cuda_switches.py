@@ -27,6 +27,15 @@ CASES = [
     ("ZS_IMAGE_MB", "0", "c1_bridge_ext", 2048, 48),
     ("ZS_IMAGE_MB", "0", "c3_city_evac", 256, 40),
     ("ZS_IMAGE_MB", "0", "c4_maze_safehouse", 128, 24),
+    # groups without spawn cells: candidates by compaction of all cells instead of from the map's free-cell table
+    ("ZS_NO_FREE_TABLE", "1", "c4_maze_safehouse", 128, 24),
+    ("ZS_NO_FREE_TABLE", "1", "c3_city_evac", 256, 40),
+    ("ZS_NO_FREE_TABLE", "1", "minz_allcells", 256, 40),
+    # one launch shape for everything / single steps with two envs per warp
+    ("ZS_ONE_SHAPE", "1", "c1_bridge_ext", 4000, 48),
+    ("ZS_SHORT_STEPS", "1000", "c1_bridge_ext", 4000, 48),
+    ("ZS_PDL", "1", "c1_bridge_ext", 2048, 48),
+    ("ZS_TMA_PAIR", "1", "c1_bridge_ext", 4000, 48),
 ]
 
 
