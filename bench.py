@@ -274,12 +274,13 @@ def run_other_config(name, spec, torch, dist, abi, dev, rank, world, K, min_ms, 
     tape = torch.empty((K, per_gpu, eng.A), dtype=torch.int32, device=dev)
     for s in range(K):
         eng.fill_synthetic_actions(s, tape[s])
+    reward, term, trunc = eng.new_outputs(K)  # every output of the step is written, as in the headline run
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for _ in range(2):
-        eng.rollout(K, 0, tape, abi.ACTIONS_DISCRETE, obs, None, None, None)
+        eng.rollout(K, 0, tape, abi.ACTIONS_DISCRETE, obs, reward, term, trunc)
     barrier()
     ev[0].record()
-    eng.rollout(K, 0, tape, abi.ACTIONS_DISCRETE, obs, None, None, None)
+    eng.rollout(K, 0, tape, abi.ACTIONS_DISCRETE, obs, reward, term, trunc)
     ev[1].record()
     barrier()
     est = max_over_ranks(ev[0].elapsed_time(ev[1]))
@@ -287,12 +288,12 @@ def run_other_config(name, spec, torch, dist, abi, dev, rank, world, K, min_ms, 
     barrier()
     ev[0].record()
     for _ in range(reps):
-        eng.rollout(K, 0, tape, abi.ACTIONS_DISCRETE, obs, None, None, None)
+        eng.rollout(K, 0, tape, abi.ACTIONS_DISCRETE, obs, reward, term, trunc)
     ev[1].record()
     barrier()
     ms = max_over_ranks(ev[0].elapsed_time(ev[1]))
     env.close()
-    del obs, tape
+    del obs, tape, reward, term, trunc
     torch.cuda.empty_cache()
     total = per_gpu * world
     value = total * K * reps / (ms * 1e-3)

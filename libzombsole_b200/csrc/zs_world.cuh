@@ -1558,6 +1558,21 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     return k;
 }
 
+// Draws k0 .. k0 + count - 1 of the env's stream, staged in shared memory (the per-step draw array): consecutive draw
+// indices share Philox blocks of four, so ONE evaluation per lane yields up to 4 * G draws.  Returns how many of the
+// `count` it staged (what the staging area holds); draw k is then at STAGE[k - 4 * (k0 >> 2)].
+ZS_TPL __device__ __forceinline__ int stage_draws(const ZsParams& p, const Env& e, uint32_t t_word, int k0, int count) {
+    ZS_VIEWS;
+    constexpr int NB = (3 * MPC + 4) / 4 < G ? (3 * MPC + 4) / 4 : G;  // blocks the array holds / lanes there are
+    const int off = k0 & 3;
+    const int chunk = min(count, 4 * NB - off);
+    gsync<G, CV>(e);  // (whatever used the array before has been read)
+    if (e.gl < NB && e.gl * 4 < off + chunk)
+        reinterpret_cast<uint4*>(S.draws)[e.gl] = philox4x32_10(e.env_global, (uint32_t)e.episode, t_word, (uint32_t)((k0 >> 2) + e.gl), p.key0, p.key1);
+    gsync<G, CV>(e);
+    return chunk;
+}
+
 // ---------------------------------------------------------------- World.spawn_in_random (core.py:40-66)
 // Places the `count` slots listed in LIST[0..count) on shuffled free cells of the player (which = 0) or
 // zombie (which = 1) spawn cells, or of the whole map, x-major, when the map has no such spawn cells.  Only
@@ -1610,17 +1625,23 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
     gsync<G, CV>(e);
     const int placed = count < n ? count : n;
     // random.shuffle + spawns.pop() (core.py:54-61): only the first `placed` Fisher-Yates iterations decide anything, and
-    // they touch at most 2 * placed positions of the list.  Iteration `it` swaps positions i = n - 1 - it and j = draw;
-    // the value at a position is what the LAST earlier iteration with that j left there, else the list's own entry.
-    // So: read the entries at all i and j up front (in parallel — the list may be in device memory), find every
-    // iteration's predecessors in parallel, and leave only a chain of shared-memory reads to one lane.
+    // they touch at most 2 * placed positions of the list.  Iteration `it` swaps positions i = n - 1 - it and j = draw:
+    // it takes what is at j and leaves there what was at i.  What an iteration finds at a position is what the LAST
+    // earlier iteration with that j left there, else the list's own entry.  All of it is resolved in parallel:
+    //   * the draws: consecutive draw indices share Philox blocks of four, so one evaluation per lane yields the draws of
+    //     128 iterations (staged through shared memory);
+    //   * PI[it], the last earlier iteration that wrote position i_it: only an iteration q with j_q >= n - placed can
+    //     have hit one of the i's, and it names the iteration it hits (n - 1 - j_q) itself — an atomic max, no search;
+    //   * PJ[it], the last earlier iteration with the same j: equal draws are rare, so a hashed bitmap of the j's says
+    //     which iterations have a partner at all and only those search (short groups: one match.any);
+    //   * what iteration q left at j_q is the list entry at the root of q's PI chain, so every lane follows its own.
     uint16_t* const Bi = reinterpret_cast<uint16_t*>(S.act);  // [MPC] list entry at i
     uint16_t* const Bj = Bi + MPC;                            // [MPC] list entry at j
     uint16_t* const Jp = Bj + MPC;                            // [MPC] j
-    uint16_t* const Vw = Jp + MPC;                            // [MPC] value the iteration writes to position j
-    int16_t* const Pi = reinterpret_cast<int16_t*>(S.draws);  // [MPC] last earlier iteration that wrote position i, or -1
-    int16_t* const Pj = Pi + MPC;                             // [MPC] ... position j
-    uint16_t* const Ch = reinterpret_cast<uint16_t*>(Pj + MPC);  // [MPC] the cell the it-th thing gets
+    uint16_t* const Ch = Jp + MPC;                            // [MPC] the cell the it-th thing gets
+    int32_t* const PI = reinterpret_cast<int32_t*>(S.draws);  // [MPC] see above, or -1
+    int16_t* const PJ = reinterpret_cast<int16_t*>(PI + MPC); // [MPC] see above, or -1
+    uint32_t* const STAGE = reinterpret_cast<uint32_t*>(S.draws);  // [4 * G] draws of one chunk (before PI / PJ are written)
     auto cand_at = [&](int i) -> uint16_t {
         if (!virt) return CAND(i);
         int x = i;
@@ -1635,32 +1656,73 @@ ZS_TPL __device__ __noinline__ int spawn_in_random(const ZsParams& p, GrpId id, 
         return __ldg(p.free_xm + x);
     };
 #pragma unroll 1
-    for (int it = e.gl; it < placed; it += G) {
-        const int i = n - 1 - it;
-        const int j = i >= 1 ? below(draw_at(p, e, t_word, k + it), i + 1) : i;
-        Jp[it] = (uint16_t)j; Bi[it] = cand_at(i); Bj[it] = cand_at(j);
-    }
-    gsync<G, CV>(e);
+    for (int it0 = 0; it0 < placed;) {  // a chunk of draws k + it0 ..: as many blocks of four as the staging area holds
+        const int chunk = stage_draws<MPC, G, CV>(p, e, t_word, k + it0, placed - it0);
+        const int kb = (k + it0) >> 2;
 #pragma unroll 1
-    for (int it = e.gl; it < placed; it += G) {
-        const int i = n - 1 - it, j = Jp[it];
-        int pi = -1, pj = -1;
-#pragma unroll 1
-        for (int q = 0; q < it; ++q) { const int jq = Jp[q]; if (jq == i) pi = q; if (jq == j) pj = q; }
-        Pi[it] = (int16_t)pi; Pj[it] = (int16_t)pj;
-    }
-    gsync<G, CV>(e);
-    if (lane == 0) {
-#pragma unroll 1
-        for (int it = 0; it < placed; ++it) {
-            const int pi = Pi[it], pj = Pj[it];
-            const int vi = pi >= 0 ? (int)Vw[pi] : (int)Bi[it];
-            const int vj = (int)Jp[it] == n - 1 - it ? vi : (pj >= 0 ? (int)Vw[pj] : (int)Bj[it]);
-            Vw[it] = (uint16_t)vi;   // position j now holds what was at i
-            Ch[it] = (uint16_t)vj;   // position i (never read again) holds what was at j: the it-th thing's cell
+        for (int it = it0 + lane; it < it0 + chunk; it += G) {
+            const int i = n - 1 - it;
+            const int j = i >= 1 ? below(STAGE[(k + it) - 4 * kb], i + 1) : i;
+            Jp[it] = (uint16_t)j; Bi[it] = cand_at(i); Bj[it] = cand_at(j);
         }
-        SCALW(ZS_S_STAMP_COUNTER) = rank0 + placed;
+        gsync<G, CV>(e);
+        it0 += chunk;
     }
+#pragma unroll 1
+    for (int it = lane; it < placed; it += G) { PI[it] = -1; PJ[it] = -1; }
+    gsync<G, CV>(e);
+#pragma unroll 1
+    for (int q = lane; q < placed; q += G) {  // the iterations whose partner position is one of the i's
+        const int hit = n - 1 - (int)Jp[q];
+        if (hit > q && hit < placed) atomicMax(&PI[hit], q);
+    }
+    if (placed <= G) {  // one round: equal draws by match.any, the partner is the nearest lower lane
+        const bool on = lane < placed;
+        const unsigned grp = gmatch<G, CV>(e, on ? (uint32_t)Jp[on ? lane : 0] : 0x80000u + (uint32_t)lane) & ((1u << lane) - 1u);
+        if (on && grp) PJ[lane] = (int16_t)(31 - __clz(grp));
+    } else if constexpr (MPC > 32) {
+        // hashed bitmaps over the j's, in the decide phase's per-slot arrays DA and DB (free here): 16 bits per slot each
+        uint32_t* const SEEN = reinterpret_cast<uint32_t*>(S.da);  // [HB / 32]
+        constexpr int HB = 16 * EnvS<MPC>::GEN;
+        static_assert((HB & (HB - 1)) == 0 && offsetof(EnvS<MPC>, db) == offsetof(EnvS<MPC>, da) + sizeof(int16_t) * EnvS<MPC>::GEN, "DA and DB are adjacent");
+        uint32_t* const DUP = SEEN + HB / 32;
+#pragma unroll 1
+        for (int w = lane; w < 2 * (HB / 32); w += G) SEEN[w] = 0u;
+        gsync<G, CV>(e);
+#pragma unroll 1
+        for (int it = lane; it < placed; it += G) {
+            const uint32_t hsh = ((uint32_t)Jp[it] * 0x9E3779B1u) >> 16 & (uint32_t)(HB - 1);
+            const uint32_t old = atomicOr(&SEEN[hsh >> 5], 1u << (hsh & 31));
+            if ((old >> (hsh & 31)) & 1u) atomicOr(&DUP[hsh >> 5], 1u << (hsh & 31));
+        }
+        gsync<G, CV>(e);
+#pragma unroll 1
+        for (int it = lane; it < placed; it += G) {
+            const int j = Jp[it];
+            const uint32_t hsh = ((uint32_t)j * 0x9E3779B1u) >> 16 & (uint32_t)(HB - 1);
+            if (!((DUP[hsh >> 5] >> (hsh & 31)) & 1u)) continue;
+            int pj = -1;
+#pragma unroll 1
+            for (int q = 0; q < it; ++q) if ((int)Jp[q] == j) pj = q;
+            PJ[it] = (int16_t)pj;
+        }
+    }
+    gsync<G, CV>(e);
+    auto left_by = [&](int q) -> int {  // what iteration q left at its position j: the list entry at the root of its PI chain
+        int r = q;
+#pragma unroll 1
+        while (PI[r] >= 0) r = PI[r];
+        return (int)Bi[r];
+    };
+#pragma unroll 1
+    for (int it = lane; it < placed; it += G) {
+        const int pj = PJ[it];
+        int vj;
+        if ((int)Jp[it] == n - 1 - it) vj = left_by(it);   // (a swap with itself: what is at i)
+        else vj = pj >= 0 ? left_by(pj) : (int)Bj[it];
+        Ch[it] = (uint16_t)vj;  // position i (never read again) holds what was at j: the it-th thing's cell
+    }
+    if (lane == 0) SCALW(ZS_S_STAMP_COUNTER) = rank0 + placed;
     gsync<G, CV>(e);
 #pragma unroll 1
     for (int it = e.gl; it < placed; it += G) {  // spawns.pop() for the it-th thing: place it, append it to the dict order
@@ -1704,10 +1766,16 @@ ZS_TPL __device__ __noinline__ int spawn_zombies(const ZsParams& p, GrpId id, in
     const int made = count < n ? count : n;
     gsync<G, CV>(e);
 #pragma unroll 1
-    for (int i = e.gl; i < made; i += G) {
-        const int s = LIST(i);
-        TL(s) = (int16_t)(50 + below(draw_at(p, e, t_word, k + i), 51));
-        TM(s) = ZS_WEAPON_CLAWS;
+    for (int i0 = 0; i0 < made;) {  // Zombie.__init__: life = randint(50, 100) (things.py:62), one draw each
+        const int chunk = stage_draws<MPC, G, CV>(p, e, t_word, k + i0, made - i0);
+        const int kb = (k + i0) >> 2;
+#pragma unroll 1
+        for (int i = i0 + e.gl; i < i0 + chunk; i += G) {
+            const int s = LIST(i);
+            TL(s) = (int16_t)(50 + below(S.draws[(k + i) - 4 * kb], 51));
+            TM(s) = ZS_WEAPON_CLAWS;
+        }
+        i0 += chunk;
     }
     gsync<G, CV>(e);
     return spawn_in_random<MPC, G, false>(p, id, episode, t_word, k + count, made, 1, rank0, all_free, new_world);
