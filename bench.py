@@ -272,8 +272,7 @@ def run_other_config(name, spec, torch, dist, abi, dev, rank, world, K, min_ms, 
     ring = max(1, min(-(-2 * L2_BYTES // obs_bytes), K))
     obs = eng.new_obs(ring)
     tape = torch.empty((K, per_gpu, eng.A), dtype=torch.int32, device=dev)
-    for s in range(K):
-        eng.fill_synthetic_actions(s, tape[s])
+    eng.fill_synthetic_tape(0, tape)
     reward, term, trunc = eng.new_outputs(K)  # every output of the step is written, as in the headline run
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for _ in range(2):
@@ -324,8 +323,7 @@ def run_ours(args, rank, world, local_rank):
     reward, term, trunc = eng.new_outputs(K)
     TAPE = max(W + K, min(4096, W + 64 * K))  # action tape resident in HBM; repeats walk through it and wrap around
     tape = torch.empty((TAPE, N, 1), dtype=torch.int32, device=dev)
-    for s in range(TAPE):
-        eng.fill_synthetic_actions(s, tape[s])
+    eng.fill_synthetic_tape(0, tape)
     torch.cuda.synchronize(dev)
 
     def barrier():

@@ -254,6 +254,8 @@ int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t*
 
 /* actions_dev int32 [N, A]: uniform discrete ids for step `step_index` (Philox action stream). */
 int zs_fill_synthetic_actions(ZsHandle* h, int64_t step_index, int32_t* actions_dev, void* stream);
+/* the same for n_steps consecutive steps in one launch: actions_dev int32 [n_steps, N, A] (an action tape for zs_rollout) */
+int zs_fill_synthetic_tape(ZsHandle* h, int64_t first_step_index, int32_t n_steps, int32_t* actions_dev, void* stream);
 
 /* Episode statistics accumulated on the device since the last call with reset=1:
  * out_dev int64 [4] = episodes finished, episodes won, sum of episode lengths, sum of zombie deaths. */

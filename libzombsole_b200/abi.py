@@ -87,6 +87,7 @@ PROTOTYPES = {
     "zs_rollout": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_fill_synthetic_actions": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "zs_fill_synthetic_tape": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "zs_episode_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "zs_launch_count": (C.c_int64, [C.c_void_p]),
     "zs_lanes_per_env": (C.c_int32, [C.c_void_p]),

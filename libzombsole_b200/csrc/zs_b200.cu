@@ -466,11 +466,14 @@ __global__ void zs_build_window_table_kernel(const __grid_constant__ ZsParams p,
     }
 }
 
-__global__ void zs_fill_actions_kernel(const __grid_constant__ ZsParams p, uint32_t step_index, int32_t* actions) {
-    const int n = p.N * p.A;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int env = i / p.A, a = i - env * p.A;
-        actions[i] = synthetic_action(p, p.env_base + (uint32_t)env, step_index, a);
+// actions [n_steps, N, A] of the synthetic action stream, steps step_index .. step_index + n_steps - 1
+__global__ void zs_fill_actions_kernel(const __grid_constant__ ZsParams p, uint32_t step_index, int32_t n_steps, int32_t* actions) {
+    const long long per = (long long)p.N * p.A, n = per * n_steps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int step = (int)(i / per);
+        const int r = (int)(i - step * per);
+        const int env = r / p.A, a = r - env * p.A;
+        actions[i] = synthetic_action(p, p.env_base + (uint32_t)env, step_index + (uint32_t)step, a);
     }
 }
 
@@ -1213,7 +1216,19 @@ extern "C" __attribute__((visibility("default"))) int zs_fill_synthetic_actions(
     const int n = h->p.N * h->p.A;
     int blocks = (n + 255) / 256;
     if (blocks > h->sm_count * 8) blocks = h->sm_count * 8;
-    zs_fill_actions_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->p, (uint32_t)step_index, actions_dev);
+    zs_fill_actions_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h->p, (uint32_t)step_index, 1, actions_dev);
+    return launched(h);
+}
+
+extern "C" __attribute__((visibility("default"))) int zs_fill_synthetic_tape(ZsHandle* h, int64_t first_step_index, int32_t n_steps, int32_t* actions_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (!actions_dev) return fail("null actions");
+    if (n_steps < 1) return fail("n_steps must be >= 1");
+    DeviceGuard guard(h);
+    const long long n = (long long)h->p.N * h->p.A * n_steps;
+    long long blocks = (n + 255) / 256;
+    if (blocks > h->sm_count * 16) blocks = h->sm_count * 16;
+    zs_fill_actions_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(h->p, (uint32_t)first_step_index, n_steps, actions_dev);
     return launched(h);
 }
 

@@ -211,6 +211,13 @@ class ZsEngine(object):
                                                self._arg(actions, torch.int32, self.N * self.A, "actions"), self._stream()))
         return actions
 
+    def fill_synthetic_tape(self, first_step_index, actions):
+        """actions int32 [n_steps, N, A]: the synthetic action stream of n_steps consecutive steps, one launch."""
+        n_steps = int(actions.shape[0])
+        check(self.L.zs_fill_synthetic_tape(self.h, int(first_step_index), n_steps,
+                                            self._arg(actions, torch.int32, n_steps * self.N * self.A, "actions"), self._stream()))
+        return actions
+
     def episode_stats(self, reset=False):
         out = torch.zeros(4, dtype=torch.int64, device=self.device)
         check(self.L.zs_episode_stats(self.h, _ptr(out), 1 if reset else 0, self._stream()))

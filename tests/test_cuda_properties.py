@@ -252,3 +252,16 @@ def test_host_output_mode_matches_device_outputs():
         assert torch.equal(te.cpu(), hte) and torch.equal(tr.cpu(), htr)
     dev_env.close()
     host_env.close()
+
+
+def test_tape_fill_equals_per_step_fill():
+    """zs_fill_synthetic_tape (one launch) writes the same ids as zs_fill_synthetic_actions step by step."""
+    eng, cfg, _ = engine("c3_city_evac", 300, seed=9, base=17)
+    K = 11
+    tape = torch.zeros((K, eng.N, eng.A), dtype=torch.int32, device=eng.device)
+    eng.fill_synthetic_tape(40, tape)
+    one = torch.zeros((eng.N, eng.A), dtype=torch.int32, device=eng.device)
+    for s in range(K):
+        eng.fill_synthetic_actions(40 + s, one)
+        assert torch.equal(tape[s], one), s
+    eng.close()
