@@ -239,18 +239,23 @@ int zs_rollout(ZsHandle* h, int32_t n_steps, int64_t first_step_index, const int
  * records in `prev_host` and only rewrites the cells that changed.  (Reference: observation.py:83-89, 122-142 builds
  * the same tensor cell by cell; gym_env.py:99-145 returns it with reward and flags.) */
 #define ZS_COMPACT_HEADER 4
-/* words per record for this handle (0 if the configuration has no compact form: surroundings scope, per-agent
- * observations, more than 32 slots) */
+/* zs_compact_words: a good record size for this handle in words (0 if the configuration has no compact form:
+ * surroundings scope, per-agent observations, more than 32 slots); zs_compact_max_words: the size no env overflows
+ * by count.  The caller picks compact_words (the same value for zs_step_compact and zs_expand_compact of a step) and may
+ * grow it when overflows become frequent: box/wall damage persists across episodes (game.py:154-155), so the number of
+ * differing cells of a long-running env creeps up. */
 int32_t zs_compact_words(const ZsHandle* h);
+int32_t zs_compact_max_words(const ZsHandle* h);
 int zs_step_compact(ZsHandle* h, const int32_t* actions_dev, int32_t action_format, uint32_t* compact_dev,
-                    int32_t* obs_dev, void* stream);
-/* compact_host, prev_host: uint32 [N, zs_compact_words]; obs_host int32 [N, obs_elems_per_env]; reward_host float64 [N];
+                    int32_t compact_words, int32_t* obs_dev, void* stream);
+/* compact_host, prev_host: uint32 [N, compact_words]; obs_host int32 [N, obs_elems_per_env]; reward_host float64 [N];
  * terminated_host / truncated_host uint8 [N]; overflow_envs_host int32 [N] receives the indices of the envs whose rows
  * the caller must copy from obs_dev, *n_overflow their number.  first_call != 0: prev_host / obs_host hold nothing yet.
  * n_threads <= 0: all the host threads of the process. */
 int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t* prev_host, int32_t* obs_host,
                       double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
-                      int32_t* overflow_envs_host, int32_t* n_overflow, int32_t first_call, int32_t n_threads);
+                      int32_t* overflow_envs_host, int32_t* n_overflow, int32_t compact_words, int32_t first_call,
+                      int32_t n_threads);
 
 /* actions_dev int32 [N, A]: uniform discrete ids for step `step_index` (Philox action stream). */
 int zs_fill_synthetic_actions(ZsHandle* h, int64_t step_index, int32_t* actions_dev, void* stream);

@@ -76,9 +76,10 @@ PROTOTYPES = {
     "zs_step_masked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_compact_words": (C.c_int32, [C.c_void_p]),
-    "zs_step_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "zs_compact_max_words": (C.c_int32, [C.c_void_p]),
+    "zs_step_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "zs_expand_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+                                    C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "zs_init_static_life": (C.c_int, [C.c_void_p, C.c_void_p]),
     "zs_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "zs_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1100,18 +1100,27 @@ extern "C" __attribute__((visibility("default"))) int zs_step_masked(ZsHandle* h
 }
 
 extern "C" __attribute__((visibility("default"))) int32_t zs_compact_words(const ZsHandle* h) { return h ? h->compact_words : 0; }
+// the record size that no env can overflow by count: every thing, every box/wall, every listed dead body
+extern "C" __attribute__((visibility("default"))) int32_t zs_compact_max_words(const ZsHandle* h) {
+    if (!h || !h->compact_words) return 0;
+    const int wpe = h->p.obs_enc == ZS_OBS_SIMPLE ? 1 : 2;
+    const int entries = h->p.M + h->p.S + h->p.cells;  // (dead bodies: at most every cell; far more than ever occurs)
+    const int cap = h->p.M + h->p.S + 64;
+    return round_up(ZS_COMPACT_HEADER + wpe * (cap < entries ? cap : entries), 32);
+}
 
 extern "C" __attribute__((visibility("default"))) int zs_step_compact(ZsHandle* h, const int32_t* actions_dev, int32_t action_format, uint32_t* compact_dev,
-                                                                       int32_t* obs_dev, void* stream) {
+                                                                       int32_t compact_words, int32_t* obs_dev, void* stream) {
     if (int rc = check_bound(h)) return rc;
     DeviceGuard guard(h);
     if (!h->compact_words) return fail("this configuration has no compact observation form (world scope, one reward per env, at most 32 slots)");
     if (!actions_dev || !compact_dev) return fail("zs_step_compact needs an action tensor and a record buffer");
+    if (compact_words < ZS_COMPACT_HEADER + 8 || compact_words > 65535) return fail("compact_words out of range");
     if (action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
     ZsIO io;
     memset(&io, 0, sizeof(io));
     io.actions = actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1;
-    io.compact = compact_dev; io.compact_words = h->compact_words;
+    io.compact = compact_dev; io.compact_words = compact_words;
     io.n_steps = 1;
     launch_sim<MODE_STEP>(h, io, (cudaStream_t)stream);
     return launched(h);
@@ -1122,11 +1131,13 @@ extern "C" __attribute__((visibility("default"))) int zs_step_compact(ZsHandle* 
 // rewritten on the first call and after an overflow.
 extern "C" __attribute__((visibility("default"))) int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t* prev_host, int32_t* obs_host,
                                                                          double* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
-                                                                         int32_t* overflow_envs_host, int32_t* n_overflow, int32_t first_call, int32_t n_threads) {
+                                                                         int32_t* overflow_envs_host, int32_t* n_overflow, int32_t compact_words,
+                                                                         int32_t first_call, int32_t n_threads) {
     if (!h) return fail("null handle");
     if (!h->compact_words) return fail("this configuration has no compact observation form");
     if (!compact_host || !prev_host || !obs_host || !overflow_envs_host || !n_overflow) return fail("null argument");
-    const int N = h->p.N, words = h->compact_words, cells = h->p.cells, C = h->p.obs_C;
+    if (compact_words < ZS_COMPACT_HEADER + 8) return fail("compact_words out of range");
+    const int N = h->p.N, words = compact_words, cells = h->p.cells, C = h->p.obs_C;
     const bool simple = h->p.obs_enc == ZS_OBS_SIMPLE;
     const int wpe = simple ? 1 : 2;
     const int32_t* T = h->tmpl_obs_host.data();

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/zs_b200.h"
 
@@ -230,32 +231,44 @@ struct Env {
     uint8_t* const SIDXP = (MPC > 32 && p.spl_global) ? reinterpret_cast<uint8_t*>(SPLP + p.Sp)          \
                                                       : GRIDP + p.off_sidx;                              \
     (void)S; (void)GRIDP; (void)DEADP; (void)SLP; (void)CANDP; (void)SPLP; (void)SIDXP
-#define GRID(i) GRIDP[i]
-#define DEADW(i) DEADP[i]
-#define SL(i) SLP[i]
-#define CAND(i) CANDP[i]
-#define TXY(i) S.txy[i]
-#define TL(i) S.tl[i]
-#define TM(i) S.tm[i]
-#define RK(i) S.rk[i]
-#define SOR(i) S.sor[i]
-#define MVQ(i) S.mvq[i]
-#define DTYPE(i) S.dtype[i]
+// -DZS_CHECKS (development builds, tools/checked_build.sh): every access through these views is bounds-checked on the
+// device and a violation traps the kernel (the launch then fails with an error instead of corrupting a neighbour env).
+// compute-sanitizer is closed on the GPU pool this was developed on; this is the in-house substitute.
+#ifdef ZS_CHECKS
+template <typename T> __device__ __forceinline__ T& zs_chk(T* base, long long i, long long n, int what) {
+    if (i < 0 || i >= n) { printf("ZS_CHECKS: view %d index %lld outside [0, %lld) (block %d thread %d)\n", what, i, n, blockIdx.x, threadIdx.x); __trap(); }
+    return base[i];
+}
+#define ZS_AT(base, i, n, what) zs_chk(base, (long long)(i), (long long)(n), what)
+#else
+#define ZS_AT(base, i, n, what) (base)[i]
+#endif
+#define GRID(i) ZS_AT(GRIDP, i, p.cells_pad, 1)
+#define DEADW(i) ZS_AT(DEADP, i, p.dead_words, 2)
+#define SL(i) ZS_AT(SLP, i, p.Sp, 3)
+#define CAND(i) ZS_AT(CANDP, i, p.cand_cap, 4)
+#define TXY(i) ZS_AT(S.txy, i, MPC, 5)
+#define TL(i) ZS_AT(S.tl, i, MPC, 6)
+#define TM(i) ZS_AT(S.tm, i, MPC, 7)
+#define RK(i) ZS_AT(S.rk, i, MPC, 8)
+#define SOR(i) ZS_AT(S.sor, i, MPC, 9)
+#define MVQ(i) ZS_AT(S.mvq, i, MPC, 10)
+#define DTYPE(i) ZS_AT(S.dtype, i, MPC, 11)
 #define DA(i) S.da[i]
 #define DB(i) S.db[i]
-#define ACT(i) S.act[i]
-#define DRAWS(i) S.draws[i]
-#define LIST(i) S.list[i]
+#define ACT(i) ZS_AT(S.act, i, MPC, 12)
+#define DRAWS(i) ZS_AT(S.draws, i, 3 * MPC + 4, 13)
+#define LIST(i) ZS_AT(S.list, i, MPC, 14)
 #define PREVL(i) S.prev[i]
 #define ACTS(i) S.acts[i]
-#define BK(i) S.bk[i]
+#define BK(i) ZS_AT(S.bk, i, MPC, 15)
 #define ZB(i) S.zb[i]
 #define SCALW(i) S.scal[i]
 #define MASKW(i) S.masks[i]
 #define SPN S.spn[0]
-#define SPL(i) SPLP[i]
-#define SIDX(i) SIDXP[i]
-#define DBL(i) S.dbl[i]
+#define SPL(i) ZS_AT(SPLP, i, p.Sp, 16)
+#define SIDX(i) ZS_AT(SIDXP, i, p.Sp, 17)
+#define DBL(i) ZS_AT(S.dbl, i, ZS_DEAD_CAP + 2, 18)
 
 // ---------------------------------------------------------------- TMA bulk copies (shared -> global)
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {

@@ -175,11 +175,15 @@ class ZsEngine(object):
         """Words per compact observation record, 0 if this configuration has no compact form."""
         return int(self.L.zs_compact_words(self.h))
 
+    def compact_max_words(self):
+        return int(self.L.zs_compact_max_words(self.h))
+
     def step_compact(self, actions, fmt, records, obs=None):
         """One transition whose observation / reward / flags come out as one small record per env (device tensor
-        ``records`` int32 [N, compact_words]); ``obs`` receives the full row of the rare env a record cannot hold."""
+        ``records`` int32 [N, words]); ``obs`` receives the full row of the rare env a record cannot hold."""
+        words = int(records.shape[-1])
         check(self.L.zs_step_compact(self.h, self._action_arg(actions, fmt, 1), fmt,
-                                     self._arg(records, torch.int32, self.N * self.compact_words(), "records"),
+                                     self._arg(records, torch.int32, self.N * words, "records"), words,
                                      self._arg(obs, torch.int32, self.N * self.obs_elems, "obs"), self._stream()))
 
     def expand_compact(self, records_host, prev_host, obs_host, reward_host, term_host, trunc_host, overflow_host,
@@ -189,7 +193,8 @@ class ZsEngine(object):
         n_over = C.c_int32(0)
         check(self.L.zs_expand_compact(self.h, records_host.data_ptr(), prev_host.data_ptr(), obs_host.data_ptr(),
                                        reward_host.data_ptr(), term_host.data_ptr(), trunc_host.data_ptr(),
-                                       overflow_host.data_ptr(), C.addressof(n_over), 1 if first_call else 0, int(n_threads)))
+                                       overflow_host.data_ptr(), C.addressof(n_over), int(records_host.shape[-1]),
+                                       1 if first_call else 0, int(n_threads)))
         return overflow_host[:n_over.value]
 
     def encode_obs(self, obs):

@@ -65,7 +65,7 @@ class ZombsoleVectorEnv(object):
     def __init__(self, rules_name, player_names, map_name, agent_id, initial_zombies=0, minimum_zombies=0,
                  render_mode=None, observation_scope="world", observation_position_encoding="simple",
                  agent_weapon="rifle", debug=False, *, num_envs=1, device="cuda", seed=0, env_index_base=0,
-                 max_episode_steps=None, auto_reset=True, host_outputs=False, host_threads=0):
+                 max_episode_steps=None, auto_reset=True, host_outputs=False, host_threads=0, compact_words=0):
         if render_mode is not None:
             if render_mode not in self.metadata["render.modes"]:
                 raise ValueError("render_mode={} is not supported".format(render_mode))
@@ -100,12 +100,9 @@ class ZombsoleVectorEnv(object):
                 raise ValueError("host_outputs='compact' needs a world-scope observation and at most 32 things per env")
             self.obs, self.reward, self._term, self._trunc = self.engine.new_host_outputs()
             self._dev_obs = self.engine.new_obs()  # full rows of the rare envs a record cannot hold
-            self._records = torch.zeros((num_envs, words), dtype=torch.int32, device=self.device)
-            self._records_host = torch.zeros((num_envs, words), dtype=torch.int32).pin_memory()
-            self._records_prev = torch.zeros((num_envs, words), dtype=torch.int32)
             self._overflow = torch.zeros(num_envs, dtype=torch.int32)
-            self._compact_first = True
             self.compact_overflows = 0
+            self._size_records(int(compact_words) if compact_words else words)
         elif self.host_outputs:
             self.obs, self.reward, self._term, self._trunc = self.engine.new_host_outputs()
         else:
@@ -168,6 +165,15 @@ class ZombsoleVectorEnv(object):
             torch.cuda.current_stream(self.device).synchronize()  # the host owns the results when step() returns
         return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}  # (0/1 bytes: a view, no kernel)
 
+    def _size_records(self, words):
+        """(Re)allocate the record buffers: ``words`` 32-bit words per env (header + entries)."""
+        words = min(int(words), self.engine.compact_max_words())
+        self.compact_words = words
+        self._records = torch.zeros((self.num_envs, words), dtype=torch.int32, device=self.device)
+        self._records_host = torch.zeros((self.num_envs, words), dtype=torch.int32).pin_memory()
+        self._records_prev = torch.zeros((self.num_envs, words), dtype=torch.int32)
+        self._compact_first = True
+
     def _step_compact(self, a, fmt):
         eng = self.engine
         eng.step_compact(a, fmt, self._records, self._dev_obs)
@@ -180,9 +186,17 @@ class ZombsoleVectorEnv(object):
         self._compact_first = False
         if len(over):  # rare: more differing cells than a record holds — fetch those rows as they are
             self.compact_overflows += len(over)
-            for e in over.tolist():
-                self.obs[e].copy_(self._dev_obs[e], non_blocking=True)
-            stream.synchronize()
+            if len(over) > 16:  # many: one gather on the device, one copy
+                idx = over.to(self.device, dtype=torch.long)
+                self.obs[over.long()] = self._dev_obs[idx].cpu()
+            else:
+                for e in over.tolist():
+                    self.obs[e].copy_(self._dev_obs[e], non_blocking=True)
+                stream.synchronize()
+            # box/wall damage persists across episodes, so the differing cells of long-running envs creep up: when more
+            # than one env in 64 no longer fits, the records double (up to the size nothing can overflow)
+            if len(over) * 64 > self.num_envs and self.compact_words < eng.compact_max_words():
+                self._size_records(2 * self.compact_words)
         return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}
 
     def reset(self, seed=None, options=None, mask=None):
