@@ -59,6 +59,8 @@ __device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO&
     int oslot = 0;
 #pragma unroll 1
     for (int step = 0; step < io.n_steps; ++step) {
+        // (experiment, ZS_STEP_SYNC: the warps of a CTA start every step together, for instruction-cache locality)
+        if (p.step_sync) __syncthreads();
         const size_t sn = (size_t)step * p.N + env;
         int32_t* obs_out = nullptr;
         if (io.obs) {
@@ -73,7 +75,11 @@ __device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO&
 #pragma unroll
         for (int r = 0; r < AR; ++r) {
             const int a = lane + r * G;
-            if (a < A) { ACTS(3 * a) = at[r]; ACTS(3 * a + 1) = adx[r]; ACTS(3 * a + 2) = ady[r]; }
+            // (narrowed to 16 bits: an unknown action type stays unknown, an offset beyond +-4097 is off any map either way)
+            if (a < A) {
+                ACTS(3 * a) = (int16_t)max(-1, min(127, at[r]));
+                ACTS(3 * a + 1) = (int16_t)max(-4097, min(4097, adx[r])); ACTS(3 * a + 2) = (int16_t)max(-4097, min(4097, ady[r]));
+            }
             alive_before |= gballot<G, CV>(e, a < A && TL(p.P + (a < A ? a : 0)) > 0) << (r * G);
             life_before[r] = a < A ? PREVL(a) : 0;
         }
@@ -925,6 +931,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) lanes0 = lanes1 = v;
     }
     h->short_steps = 8;
+    p.step_sync = getenv("ZS_STEP_SYNC") ? 1 : 0;
     h->use_pdl = getenv("ZS_PDL") ? 1 : 0;  // (measured: -8 % on back-to-back single steps, but a launch on an idle stream starts later)
     if (const char* force = getenv("ZS_SHORT_STEPS")) h->short_steps = atoi(force);
     h->tmpl_single_step = getenv("ZS_NO_TMA_SINGLE") ? 0 : 1;
@@ -971,6 +978,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
                 sh.smem_bytes += bytes + 16;  // (+ the mbarrier of the staging copy)
             }
         }
+        if (const char* pad = getenv("ZS_EXTRA_SMEM")) sh.smem_bytes += atoi(pad) & ~15;  // (experiment: fewer resident CTAs)
         if (sh.smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
         // (the attribute belongs to the kernel, not to the handle: every handle asks for all a CTA can have, so that handles
         // of different maps can live side by side)

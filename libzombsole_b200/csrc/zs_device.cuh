@@ -107,6 +107,7 @@ struct ZsParams {
     int32_t tmpl_pair;             // the planes are staged twice back to back: one bulk copy serves both envs of a warp
     int32_t tmpl_bytes;            // bytes of one staged copy of the planes (tmpl_planes * cells * 4)
     int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
+    int32_t step_sync;             // (experiment) general step loop: __syncthreads at the top of every step
 };
 
 struct ZsIO {
@@ -167,10 +168,14 @@ struct alignas(16) EnvS {
     // ---- scratch: lives for a step (or a launch)
     unsigned long long act[MPC];            // the step's action list (packed, see pack_action): actor order, then shuffled in place
     uint32_t bk[MPC];                       // per step: closest-player key of a zombie / heal_closest agent
-    alignas(16) uint32_t draws[3 * MPC + 4];  // per step: the draws, 4 per Philox block (stored as uint4)
+    // per step: the draws, 4 per Philox block (stored as uint4).  One-lane kernels: up to 3 per slot (a randoman's decision)
+    // plus shuffle and hit; general kernels: a slot draws for wandering or for a hit, never both, so 2 per slot plus the
+    // randomans' (bots only: at most ZS_MAX_BOTS of them)
+    static constexpr int NDRAWS = MPC > 32 ? 2 * MPC + 3 * ZS_MAX_BOTS + 4 : 3 * MPC + 4;
+    alignas(16) uint32_t draws[NDRAWS];
     uint32_t zb[GEN < ZS_NP_MAX ? GEN : ZS_NP_MAX];  // per step: closest-zombie key of a player slot
     int32_t scal[8];                        // scalar hand-off around out-of-line functions
-    int32_t acts[3 * (GEN < ZS_MAX_AGENTS ? GEN : ZS_MAX_AGENTS) + 1];  // agent actions of the step (type, dx, dy)
+    int16_t acts[3 * (GEN < ZS_MAX_AGENTS ? GEN : ZS_MAX_AGENTS) + 1];  // agent actions of the step (type, dx, dy), narrowed
     uint32_t masks[2 * ((MPC + 31) / 32) + 2];  // rank bit-masks: stayers, then movers
     alignas(8) unsigned long long mbar;     // mbarrier of the image load (one phase per launch)
     int16_t da[GEN];
@@ -179,7 +184,7 @@ struct alignas(16) EnvS {
     uint8_t dtype[MPC];
     uint8_t mvp[GEN];                       // general kernels: list position of the slot's successful move, RK_NONE if none
     uint8_t mpos[GEN];                      // general kernels: list position of the slot's (valid) move action, RK_NONE if none
-    alignas(16) uint8_t fyj[MPC];           // per step: Fisher-Yates partner of every list position (one-lane-per-slot kernels)
+    alignas(16) uint8_t fyj[MPC > 32 ? 16 : MPC];  // per step: Fisher-Yates partner of every list position (one-lane-per-slot kernels)
     // ---- the IMAGE: everything from here to the end of the struct, and the run-time tail behind it up to the spawn
     // candidate list, is what an env needs on chip between two steps.  A launch leaves it in device memory as one
     // contiguous block next to the canonical state (ZsParams::img) and the next launch brings it back with ONE bulk copy
@@ -257,7 +262,7 @@ template <typename T> __device__ __forceinline__ T& zs_chk(T* base, long long i,
 #define DA(i) S.da[i]
 #define DB(i) S.db[i]
 #define ACT(i) ZS_AT(S.act, i, MPC, 12)
-#define DRAWS(i) ZS_AT(S.draws, i, 3 * MPC + 4, 13)
+#define DRAWS(i) ZS_AT(S.draws, i, EnvS<MPC>::NDRAWS, 13)
 #define LIST(i) ZS_AT(S.list, i, MPC, 14)
 #define PREVL(i) S.prev[i]
 #define ACTS(i) S.acts[i]

@@ -1563,7 +1563,7 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
 // `count` it staged (what the staging area holds); draw k is then at STAGE[k - 4 * (k0 >> 2)].
 ZS_TPL __device__ __forceinline__ int stage_draws(const ZsParams& p, const Env& e, uint32_t t_word, int k0, int count) {
     ZS_VIEWS;
-    constexpr int NB = (3 * MPC + 4) / 4 < G ? (3 * MPC + 4) / 4 : G;  // blocks the array holds / lanes there are
+    constexpr int NB = EnvS<MPC>::NDRAWS / 4 < G ? EnvS<MPC>::NDRAWS / 4 : G;  // blocks the array holds / lanes there are
     const int off = k0 & 3;
     const int chunk = min(count, 4 * NB - off);
     gsync<G, CV>(e);  // (whatever used the array before has been read)
