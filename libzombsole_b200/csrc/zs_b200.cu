@@ -665,8 +665,8 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
         case 32:
             if (occ == ZS_MIN_CTAS_LOWOCC) ZS_LAUNCH_F(32, 32, ZS_MIN_CTAS_LOWOCC); else ZS_LAUNCH_F(32, 32, ZS_MIN_CTAS);
             break;
-        case 128: ZS_LAUNCH_G(128, 32, ZS_MIN_CTAS); break;
-        default: ZS_LAUNCH_G(256, 32, ZS_MIN_CTAS); break;
+        case 128: ZS_LAUNCH_G(128, 32, ZS_OCC_GENERAL); break;
+        default: ZS_LAUNCH_G(256, 32, ZS_OCC_GENERAL); break;
     }
 #undef ZS_LAUNCH_G
 #undef ZS_LAUNCH_F
@@ -687,6 +687,7 @@ static cudaError_t set_smem_attr_for(int bytes) {
     cudaError_t e = set_smem_attr_step<MPC, G, ZS_MIN_CTAS>(bytes);
     if (e == cudaSuccess && MPC <= 32) e = set_smem_attr_step<MPC, G, (MPC <= 32 ? ZS_MIN_CTAS_LOWOCC : ZS_MIN_CTAS)>(bytes);
     if (e == cudaSuccess && G == 16) e = set_smem_attr_step<MPC, G, (G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS)>(bytes);
+    if (e == cudaSuccess && MPC > 32) e = set_smem_attr_step<MPC, G, (MPC > 32 ? ZS_OCC_GENERAL : ZS_MIN_CTAS)>(bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, 0, ZS_MIN_CTAS>, attr, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, 0, ZS_MIN_CTAS>, attr, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, 2, ZS_MIN_CTAS>, attr, bytes);
@@ -936,7 +937,7 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     if (const char* force = getenv("ZS_SHORT_STEPS")) h->short_steps = atoi(force);
     h->tmpl_single_step = getenv("ZS_NO_TMA_SINGLE") ? 0 : 1;
     h->compact_words = (p.mpc <= 32 && p.obs_scope == ZS_OBS_WORLD && !p.obs_per_agent)
-                           ? (p.obs_enc == ZS_OBS_SIMPLE ? 128 : 256) : 0;
+                           ? (p.obs_enc == ZS_OBS_SIMPLE ? 96 : 192) : 0;  // header + 92 entries; the caller grows them
     const int smem_per_env_base = p.smem_per_env;
     for (int si = 0; si < 2; ++si) {
         ZsHandle::Shape& sh = h->shape[si];

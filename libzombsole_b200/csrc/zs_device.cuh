@@ -25,6 +25,9 @@
 #define ZS_WPC 4              // warps per CTA
 #define ZS_MIN_CTAS 7         // 7 CTAs x 4 warps resident per SM: 4,096 full-warp envs fit the 148 SMs in one wave
 #define ZS_MIN_CTAS_LOWOCC 4  // small (latency-bound) batches: 4 CTAs x 4 warps per SM, 128 registers
+#ifndef ZS_OCC_GENERAL
+#define ZS_OCC_GENERAL 6      // step kernels with more slots than lanes: shared memory allows six CTAs at best (80 registers)
+#endif
 #ifndef ZS_MIN_CTAS_G16
 #define ZS_MIN_CTAS_G16 6     // two envs per warp: 6 CTAs (80 registers) measured slightly ahead of 7 (72) and of 5 (96)
 #endif

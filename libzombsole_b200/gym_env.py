@@ -109,6 +109,7 @@ class ZombsoleVectorEnv(object):
             self.obs = self.engine.new_obs()
             self.reward, self._term, self._trunc = self.engine.new_outputs()
         self._actions = torch.zeros((num_envs, 1, 3), dtype=torch.int32, device=self.device)
+        self._act_dev = torch.zeros((num_envs, 1), dtype=torch.int32, device=self.device)
         self._h2d_done, self._h2d_pending = None, False
 
     # -- the reference's object protocol for one world of the batch
@@ -135,6 +136,11 @@ class ZombsoleVectorEnv(object):
             self._actions.copy_(torch.from_numpy(rows), non_blocking=True)
             return self._actions, abi.ACTIONS_FULL
         t = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+        if self.compact and t.dtype == torch.int32 and t.device.type == "cpu" and t.numel() == self.num_envs:
+            # the host loop's hot path: one copy into the env's own device buffer; step() synchronises the stream before it
+            # returns, so the caller's buffer is free again by then
+            self._act_dev.copy_(t.view(self.num_envs, 1), non_blocking=True)
+            return self._act_dev, abi.ACTIONS_DISCRETE
         if self.host_outputs and not self.compact and t.dtype == torch.int32 and t.device.type == "cpu" and t.is_pinned():
             pass  # the kernel reads a pinned host action tensor in place
         elif t.dtype != torch.int32 or t.device != self.device:
@@ -173,6 +179,7 @@ class ZombsoleVectorEnv(object):
         self._records_host = torch.zeros((self.num_envs, words), dtype=torch.int32).pin_memory()
         self._records_prev = torch.zeros((self.num_envs, words), dtype=torch.int32)
         self._compact_first = True
+        self._overflows_since_resize = 0
 
     def _step_compact(self, a, fmt):
         eng = self.engine
@@ -194,8 +201,11 @@ class ZombsoleVectorEnv(object):
                     self.obs[e].copy_(self._dev_obs[e], non_blocking=True)
                 stream.synchronize()
             # box/wall damage persists across episodes, so the differing cells of long-running envs creep up: when more
-            # than one env in 64 no longer fits, the records double (up to the size nothing can overflow)
-            if len(over) * 64 > self.num_envs and self.compact_words < eng.compact_max_words():
+            # than one env in 64 no longer fits, or full rows keep being fetched, the records double (up to the size nothing
+            # can overflow)
+            self._overflows_since_resize += len(over)
+            if ((len(over) * 64 > self.num_envs or self._overflows_since_resize > 64)
+                    and self.compact_words < eng.compact_max_words()):
                 self._size_records(2 * self.compact_words)
         return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}
 
