@@ -182,10 +182,13 @@ __device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO&
 // FAST = the standard rollout shape, fixed at compile time: one agent, one reward per env, world-scope observation,
 // no minimum-zombie respawn, a discrete action tape in, observation / reward / terminated / truncated out and no
 // diagnostics outputs (zs_launch picks it when a launch has that shape).
-template <int MPC, int G, bool CV, bool FAST, bool SURR>
+// PROD: the observation of every step is handed to the CTA's producer warp (zs_obs.cuh: obs_producer) instead of being
+// written by the game warp: no bulk-copy issue, no wait for it, no global stores on the game warps' dependent chain.
+template <int MPC, int G, bool CV, bool FAST, bool SURR, bool PROD = false>
 __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io, Env& e) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl, env = e.env;
+    ObsMail* const mail = PROD ? reinterpret_cast<ObsMail*>(zs_smem + p.prod_off + (int)(e.b / (uint32_t)p.smem_per_env) * ((int)sizeof(ObsMail) + 8 * p.prod_cap)) : nullptr;
     const int A = FAST ? 1 : p.A, P = p.P, NP = P + A;
     const int aidx = lane - P;
     const bool is_agent = aidx >= 0 && aidx < A;
@@ -217,7 +220,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         if (FAST || obs_out) {
             if (++oslot >= io.obs_slots) { oslot = 0; obs_cur = obs_first; } else obs_cur += obs_stride;
             // pass 1 of the world observation does not depend on the transition: issue its stores now
-            if constexpr (world_obs) { if (FAST || io.compact == nullptr) obs_world_template<MPC, G, CV>(p, e, obs_out); }
+            if constexpr (world_obs && !PROD) { if (FAST || io.compact == nullptr) obs_world_template<MPC, G, CV>(p, e, obs_out); }
         }
         PH(18);
         if (step == io.n_steps - 1) TR(24);
@@ -320,7 +323,17 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
                 }
             }
         }
-        if (!compacted && (FAST || obs_out)) {
+        if constexpr (PROD) {
+            // hand the observation over: the mailbox is free again once the producer is done with the previous step's
+            // record (long ago, normally), the record is filled, the group's lane 0 tells the producer
+            if (step > 0) mbar_wait(&mail->empty, (uint32_t)((step - 1) & 1));
+            const int cnt = obs_world_record<MPC, G, CV>(p, e, reinterpret_cast<uint32_t*>(mail + 1), p.prod_cap);
+            if (lane == 0) { mail->count = cnt; mail->flags = e.flags; }
+            gsync<G, CV>(e);
+            if (lane == 0) mbar_arrive(&mail->full);
+            // (the record could not describe the env: the producer reads the env's block itself, which must not change meanwhile)
+            if (cnt < 0) mbar_wait(&mail->empty, (uint32_t)(step & 1));
+        } else if (!compacted && (FAST || obs_out)) {
             if constexpr (world_obs) obs_world_patch<MPC, G, CV>(p, e, obs_out);
             else encode_surroundings<MPC, G, CV>(p, e, obs_out);
         }
@@ -346,10 +359,14 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
 // SHAPE: what is compiled in — 0 = world-scope observation, 1 = the standard rollout shape (FAST, world scope),
 // 2 = surroundings observation.  (With both observation encoders in one kernel the step loop of the kernels that
 // never run the window code spilled more registers: 5-8 % on large world-scope batches.)
+// SHAPE 3 = the standard rollout shape with a producer warp: CTAs of four game warps (eight envs) plus one warp that writes
+// the observations (160 threads; compiled for 4 CTAs per SM: 20 warps, five per scheduler = 96 registers, and 4,096 envs
+// are one wave.  Three-warp CTAs at seven per SM would put six warps on one scheduler: 80 registers and spills).
 template <int MODE, int MPC, int G, int SHAPE, int OCC>
-__global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
+__global__ void __launch_bounds__(SHAPE == 3 ? 160 : ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_constant__ ZsParams p, const __grid_constant__ ZsIO io) {
     ZS_CONSTS;
-    constexpr bool FAST = SHAPE == 1, SURR = SHAPE == 2;
+    constexpr bool PROD = SHAPE == 3;
+    constexpr bool FAST = SHAPE == 1 || PROD, SURR = SHAPE == 2;
     // the step kernel keeps both envs of a warp converged (zs_device.cuh); masked resets and encodes may not
     constexpr bool CV = MODE == MODE_STEP;
     constexpr int EPW = 32 / G;  // envs per warp
@@ -366,7 +383,8 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
     // (programmatic dependent launch, launch_sim: the next kernel of the stream may start scheduling its CTAs now; it
     // waits for this grid's completion in its own griddepcontrol.wait)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int env = blockIdx.x * ((blockDim.x >> 5) * EPW) + slot;  // (a CTA has ZS_WPC warps, or fewer for small batches)
+    const int game_warps = (int)(blockDim.x >> 5) - (PROD ? 1 : 0);
+    const int env = blockIdx.x * (game_warps * EPW) + slot;  // (a CTA has ZS_WPC warps, or fewer for small batches)
     unsigned long long* const tmpl_bar = reinterpret_cast<unsigned long long*>(zs_smem + p.tmpl_smem_off + (p.tmpl_pair ? 2 : 1) * p.tmpl_bytes);
     if (p.tmpl_smem_off >= 0) {
         // stage the pristine observation planes once per CTA, the source of the per-step TMA bulk copies: one thread
@@ -377,11 +395,26 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
             mbar_expect_tx(tmpl_bar, (uint32_t)((p.tmpl_pair ? 2 : 1) * p.tmpl_bytes));
             bulk_load(zs_smem + p.tmpl_smem_off, p.tmpl_obs, (uint32_t)p.tmpl_bytes, tmpl_bar);
             if (p.tmpl_pair) bulk_load(zs_smem + p.tmpl_smem_off + p.tmpl_bytes, p.tmpl_obs, (uint32_t)p.tmpl_bytes, tmpl_bar);
+            if (PROD) {
+                for (int i = 0; i < game_warps * EPW; ++i) {
+                    ObsMail* m = reinterpret_cast<ObsMail*>(zs_smem + p.prod_off + i * ((int)sizeof(ObsMail) + 8 * p.prod_cap));
+                    mbar_init(&m->full, 1); mbar_init(&m->empty, 1);
+                }
+            }
         }
-        __syncthreads();  // (the barrier exists before anybody waits on it)
+        __syncthreads();  // (the barriers exist before anybody waits on them)
     }
     // everything below reads what earlier work of the stream wrote (state, images, actions, masks)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if constexpr (PROD) {
+        if (wid == game_warps) {  // the producer warp
+            uint32_t sa = (uint32_t)__cvta_generic_to_shared(zs_smem + p.tmpl_smem_off);
+            if (wlane == 0) mbar_wait(tmpl_bar, 0u);
+            __syncwarp();
+            obs_producer<MPC>(p, io, game_warps * EPW, sa);
+            return;
+        }
+    }
     if (env >= p.N) return;
     e.tmpl_saddr = 0;
     if (p.tmpl_smem_off >= 0) {
@@ -439,7 +472,7 @@ __global__ void __launch_bounds__(ZS_WPC * 32, OCC) zs_sim_kernel(const __grid_c
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
 #endif
-    if constexpr (ONE) step_loop_one<MPC, G, CV, FAST, SURR>(p, io, e);
+    if constexpr (ONE) step_loop_one<MPC, G, CV, FAST, SURR, PROD>(p, io, e);
     else step_loop_general<MPC, G, CV, SURR>(p, io, e);
 #ifdef ZS_PHASE_CLOCKS
     e.ph_last = clock64();
@@ -522,6 +555,7 @@ struct ZsHandle {
     struct Shape {
         int lanes_per_env, warps_per_cta, envs_per_cta, smem_per_env, smem_bytes, occ;
         int tmpl_smem_off, tmpl_planes, tmpl_pair, tmpl_bytes;
+        int prod_off, prod_cap, prod_smem_bytes;  // the producer-warp variant of the standard rollout shape (0 bytes = not available)
     } shape[2];
     int short_steps;       // launches of fewer steps than this take shape[1]
     int use_pdl;           // launch with programmatic stream serialization (launch_sim)
@@ -621,7 +655,7 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     ZsParams pp = h->p;
     const ZsHandle::Shape& sh = h->shape[(MODE == MODE_STEP && io.n_steps >= h->short_steps && io.env_mask == nullptr) ? 0 : 1];
     pp.smem_per_env = sh.smem_per_env; pp.tmpl_smem_off = sh.tmpl_smem_off; pp.tmpl_planes = sh.tmpl_planes;
-    pp.tmpl_pair = sh.tmpl_pair; pp.tmpl_bytes = sh.tmpl_bytes;
+    pp.tmpl_pair = sh.tmpl_pair; pp.tmpl_bytes = sh.tmpl_bytes; pp.prod_off = -1; pp.prod_cap = 0;
     int smem = sh.smem_bytes;
     // envs in flight chip-wide, roughly: the distance load_state prefetches ahead (a launch of many short-lived CTAs)
     pp.prefetch_ahead = (MODE != MODE_STEP || io.n_steps < 4) && !getenv("ZS_NO_PREFETCH") ? h->sm_count * 7 * sh.envs_per_cta : 0;
@@ -638,6 +672,8 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
                       io.terminated && io.truncated && !io.draws && !io.agent_mask;
     const int occ = MODE == MODE_STEP ? sh.occ : ZS_MIN_CTAS;
     const bool surr = pp.obs_scope == ZS_OBS_SURROUNDINGS;
+    // the standard rollout shape of a batch that one wave of producer-warp CTAs holds: observations through a third warp
+    const bool prod = fast && MODE == MODE_STEP && sh.prod_smem_bytes > 0 && pp.tmpl_smem_off >= 0 && io.env_mask == nullptr;
     // SH_: 0 world scope, 1 the standard rollout shape (step launches only), 2 surroundings (zs_sim_kernel: SHAPE)
     // Programmatic dependent launch: the kernel's CTAs may be scheduled while the previous kernel of the stream is still
     // draining (they stage the observation template and then wait in griddepcontrol.wait for that kernel to have
@@ -652,6 +688,14 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
 #define ZS_LAUNCH(MPC_, G_, SH_, O_) cudaLaunchKernelEx(&lc, zs_sim_kernel<MODE, MPC_, G_, ((SH_) == 1 && MODE != MODE_STEP) ? 0 : (SH_), MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS>, pp, io)
 #define ZS_LAUNCH_F(MPC_, G_, O_) do { if (fast) ZS_LAUNCH(MPC_, G_, 1, O_); else if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
 #define ZS_LAUNCH_G(MPC_, G_, O_) do { if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
+    if (prod) {
+        pp.prod_off = sh.prod_off; pp.prod_cap = sh.prod_cap; pp.tmpl_smem_off = ZS_PROD_ENVS * sh.smem_per_env;
+        lc.gridDim = dim3((pp.N + ZS_PROD_ENVS - 1) / ZS_PROD_ENVS); lc.blockDim = dim3(32 * (ZS_PROD_ENVS / 2 + 1));
+        lc.dynamicSmemBytes = (size_t)sh.prod_smem_bytes;
+        if constexpr (MODE == MODE_STEP) cudaLaunchKernelEx(&lc, zs_sim_kernel<MODE_STEP, 16, 16, 3, ZS_MIN_CTAS_LOWOCC>, pp, io);
+        if (pp.img != nullptr) const_cast<ZsHandle*>(h)->img_valid = true;
+        return;
+    }
     switch (pp.mpc) {
         case 16:
             if (sh.lanes_per_env == 16) {
@@ -687,6 +731,7 @@ static cudaError_t set_smem_attr_for(int bytes) {
     cudaError_t e = set_smem_attr_step<MPC, G, ZS_MIN_CTAS>(bytes);
     if (e == cudaSuccess && MPC <= 32) e = set_smem_attr_step<MPC, G, (MPC <= 32 ? ZS_MIN_CTAS_LOWOCC : ZS_MIN_CTAS)>(bytes);
     if (e == cudaSuccess && G == 16) e = set_smem_attr_step<MPC, G, (G == 16 ? ZS_MIN_CTAS_G16 : ZS_MIN_CTAS)>(bytes);
+    if (e == cudaSuccess && G == 16 && MPC == 16) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_STEP, 16, 16, 3, ZS_MIN_CTAS_LOWOCC>, attr, bytes);
     if (e == cudaSuccess && MPC > 32) e = set_smem_attr_step<MPC, G, (MPC > 32 ? ZS_OCC_GENERAL : ZS_MIN_CTAS)>(bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_RESET, MPC, G, 0, ZS_MIN_CTAS>, attr, bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(zs_sim_kernel<MODE_ENCODE, MPC, G, 0, ZS_MIN_CTAS>, attr, bytes);
@@ -978,6 +1023,22 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
                 sh.tmpl_smem_off = sh.smem_bytes; sh.tmpl_planes = planes; sh.tmpl_pair = pair; sh.tmpl_bytes = planes * p.cells * 4;
                 sh.smem_bytes += bytes + 16;  // (+ the mbarrier of the staging copy)
             }
+        }
+        // the producer-warp variant (four game warps + one producer per CTA, 4 CTAs per SM): for two-env warps whose whole
+        // batch is one wave of such CTAs, with the TMA template; one record of every thing, every box/wall and every listed
+        // dead body per env
+        sh.prod_off = -1; sh.prod_cap = 0; sh.prod_smem_bytes = 0;
+        // OFF by default (ZS_PRODUCER=1): measured at 4,096 bridge envs it is SLOWER — 7.8 us per fused step with a producer
+        // that issues the rows as bulk copies, 8.1 us with 128-bit stores, 9.2 us with a producer that polls its envs one by
+        // one, against 5.6 us with the game warps writing their own observations (and 4.9 us with no observation at all).
+        // More resident warps slow every warp on the SM down (the same shows with 4-warp CTAs): the step is bound by how
+        // its dependent chain interleaves with the other warps' chains, not by the observation's own instructions.
+        if (sh.lanes_per_env == 16 && p.mpc == 16 && sh.tmpl_smem_off >= 0 && !sh.tmpl_pair && getenv("ZS_PRODUCER") &&
+            (p.N + ZS_PROD_ENVS - 1) / ZS_PROD_ENVS <= 4 * prop.multiProcessorCount) {
+            const int cap = round_up(p.M + p.S + ZS_DEAD_CAP, 8);
+            const int off = round_up(ZS_PROD_ENVS * sh.smem_per_env + sh.tmpl_bytes + 16, 16);
+            const int total = off + ZS_PROD_ENVS * ((int)sizeof(ObsMail) + 8 * cap);
+            if ((total + 1024) * 4 <= (int)prop.sharedMemPerMultiprocessor) { sh.prod_off = off; sh.prod_cap = cap; sh.prod_smem_bytes = total; }
         }
         if (const char* pad = getenv("ZS_EXTRA_SMEM")) sh.smem_bytes += atoi(pad) & ~15;  // (experiment: fewer resident CTAs)
         if (sh.smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }

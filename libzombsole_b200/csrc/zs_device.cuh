@@ -25,6 +25,7 @@
 #define ZS_WPC 4              // warps per CTA
 #define ZS_MIN_CTAS 7         // 7 CTAs x 4 warps resident per SM: 4,096 full-warp envs fit the 148 SMs in one wave
 #define ZS_MIN_CTAS_LOWOCC 4  // small (latency-bound) batches: 4 CTAs x 4 warps per SM, 128 registers
+#define ZS_PROD_ENVS 8        // envs of a producer-warp CTA (four two-env game warps + the producer warp)
 #ifndef ZS_OCC_GENERAL
 #define ZS_OCC_GENERAL 6      // step kernels with more slots than lanes: shared memory allows six CTAs at best (80 registers)
 #endif
@@ -109,6 +110,8 @@ struct ZsParams {
     int32_t tmpl_planes;           // planes staged there: 1 (simple) or 3 (channels: label, life, zeros)
     int32_t tmpl_pair;             // the planes are staged twice back to back: one bulk copy serves both envs of a warp
     int32_t tmpl_bytes;            // bytes of one staged copy of the planes (tmpl_planes * cells * 4)
+    int32_t prod_off;              // producer-warp launches: CTA-shared mailboxes (ObsMail + record) of the CTA's envs, -1 if unused
+    int32_t prod_cap;              // entries one record holds
     int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
     int32_t step_sync;             // (experiment) general step loop: __syncthreads at the top of every step
 };
@@ -204,6 +207,22 @@ struct alignas(16) EnvS {
     uint8_t mvq[MPC];                       // order of this step's successful moves, RK_NONE if none
 };
 template <int MPC> __host__ __device__ constexpr int img_off() { return (int)offsetof(EnvS<MPC>, txy); }
+
+// Producer-warp launches (zs_sim_kernel SHAPE 3): the game warps hand the observation of every step to a third warp of
+// the CTA through one mailbox per env — the cells that differ from the pristine planes as (cell, value) entries — and go on
+// with the next transition; the producer warp sends the pristine planes (bulk copy), waits for them, stores the entries.
+struct alignas(16) ObsMail {
+    unsigned long long full;    // mbarrier: the game warp has filled the record of a step
+    unsigned long long empty;   // mbarrier: the producer warp is done with it
+    int32_t count;              // entries, or -1: the producer encodes from the env's own shared-memory block (the game warp waits)
+    int32_t flags;              // Env::flags of the env at that moment (for the -1 case)
+    int32_t pad[2];
+    // uint32_t rec[2 * prod_cap] follows
+};
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
 
 // The env a lane group is working on (warp-uniform within the group).
 struct Env {

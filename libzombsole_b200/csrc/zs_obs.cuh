@@ -251,6 +251,144 @@ ZS_TPL __device__ __forceinline__ bool obs_world_compact(const ZsParams& p, Env&
     return over;
 }
 
+// World scope as a record for the producer warp (zs_device.cuh: ObsMail): the cells pass 2 would patch as two-word entries
+// in shared memory — simple encoding: cell, value; channels: cell | thing << 16, (life & 0xffff) | weapon << 16.  Returns
+// the number of entries, or -1 when the record cannot describe the env (the dead-body list is not complete, more entries
+// than it holds, a channel value outside 16 bits): the producer then encodes from the env's block itself.
+ZS_TPL __device__ __forceinline__ int obs_world_record(const ZsParams& p, Env& e, uint32_t* __restrict__ rec, int cap) {
+    ZS_CONSTS; ZS_VIEWS;
+    const int lane = e.gl;
+    const unsigned below_l = (1u << lane) - 1u;
+    const bool simple = p.obs_enc == ZS_OBS_SIMPLE;
+    int n = 0;
+    bool bad = (e.flags & FL_DEAD_OVER) != 0;
+    auto emit = [&](bool on, int cell, int v0, int v1, int v2) {
+        const unsigned m = gballot<G, CV>(e, on);
+        const int pos = n + __popc(m & below_l);
+        if (on && pos < cap) {
+            if (simple) { rec[2 * pos] = (uint32_t)cell; rec[2 * pos + 1] = (uint32_t)v0; }
+            else {
+                bad |= (unsigned)v0 > 0xffffu || (unsigned)v2 > 0xffffu || v1 < -32768 || v1 > 32767;
+                rec[2 * pos] = (uint32_t)cell | ((uint32_t)v0 << 16);
+                rec[2 * pos + 1] = ((uint32_t)v1 & 0xffffu) | ((uint32_t)v2 << 16);
+            }
+        }
+        n += __popc(m);
+    };
+    const int n_spl = (e.flags & FL_DMG) ? (int)SPN : 0;
+    const int r_spl = wmax<G, CV>(e, n_spl);
+#pragma unroll 1
+    for (int i0 = 0; i0 < r_spl; i0 += G) {
+        const int i = i0 + lane;
+        const uint32_t w = i < n_spl ? SPL(i < n_spl ? i : 0) : 0xffff0000u;
+        const int cell = w & 0xffffu, pay = w >> 16;
+        // gone from World.things (payload 0): whatever took the cell shows itself; else the cell reads as empty
+        const bool on = i < n_spl && (pay != 0 || GRID(cell) == G_EMPTY);
+        if (simple) emit(on, cell, pay, 0, 0);
+        else emit(on, cell, pay >> 12, (int)((uint32_t)pay << 20) >> 20, 0);
+    }
+    const int body0 = simple ? 256 * ZS_LABEL_DEAD_BODY : ZS_LABEL_DEAD_BODY;
+    const int n_dead = (e.flags & FL_DEAD_OVER) ? 0 : (int)DBL(0);
+    const int r_dead = wmax<G, CV>(e, n_dead);
+#pragma unroll 1
+    for (int i0 = 0; i0 < r_dead; i0 += G) {
+        const int i = i0 + lane;
+        const int c = i < n_dead ? (int)DBL(1 + i) : 0;
+        emit(i < n_dead && GRID(c) == G_DEAD, c, body0, 0, 0);
+    }
+    {
+        const bool in_cap = G == MPC || lane < MPC;
+        const int m = in_cap ? (int)TM(in_cap ? lane : 0) : 0;
+        const bool on = (m & 0x80) != 0;
+        const uint32_t xy = in_cap ? TXY(in_cap ? lane : 0) : 0u;
+        const CellInfo ci = thing_info(p, lane, in_cap ? (int)TL(in_cap ? lane : 0) : 0, m);
+        if (simple) emit(on, xy_y(xy) * p.W + xy_x(xy), encode_simple(ci), 0, 0);
+        else emit(on, xy_y(xy) * p.W + xy_x(xy), channel_label(p, ci), ci.life, ci.weapon);
+    }
+    return (gany<G, CV>(e, bad) || n > cap) ? -1 : n;
+}
+
+// The producer warp of a CTA (zs_sim_kernel SHAPE 3): for every step, the pristine planes go to the rows of the CTA's envs,
+// then the entries the game warps left in the mailboxes are stored.  One warp, 32 lanes, no env of its own.
+template <int MPC>
+__device__ __forceinline__ void obs_producer(const ZsParams& p, const ZsIO& io, int envs_per_cta, uint32_t tmpl_saddr) {
+    const int lane = threadIdx.x & 31;
+    const int env0 = blockIdx.x * envs_per_cta;
+    const int mail_stride = (int)sizeof(ObsMail) + 8 * p.prod_cap;
+    const int n4 = (p.tmpl_planes * p.cells) >> 2;  // 128-bit words per row
+    const uint4* const t4 = reinterpret_cast<const uint4*>(zs_smem + p.tmpl_smem_off);
+    const bool simple = p.obs_enc == ZS_OBS_SIMPLE;
+    int n_act = p.N - env0;
+    if (n_act > envs_per_cta) n_act = envs_per_cta;
+    const size_t obs_stride = (size_t)p.N * p.obs_elems;
+    // pass 1 for one row: the pristine planes straight from the staged copy with 128-bit stores (a bulk copy per row,
+    // issued by one thread, cost more than the whole step it was meant to relieve: measured)
+    auto pristine = [&](int32_t* row) {
+        uint4* const o4 = reinterpret_cast<uint4*>(row);
+#pragma unroll 4
+        for (int c = lane; c < n4; c += 32) __stcs(o4 + c, t4[c]);
+    };
+    // The envs are served as their records arrive, each at its own pace (lane i keeps env i's step and ring slot): a
+    // producer that waited for all its envs every step would tie the four game warps of the CTA to the slowest of them.
+    int my_step = 0, my_slot = 0;
+#pragma unroll 1
+    for (int i = 0; i < n_act; ++i) pristine(io.obs + (size_t)(env0 + i) * p.obs_elems);  // step 0's rows
+    __syncwarp();
+    int left = n_act * io.n_steps;
+#pragma unroll 1
+    while (left > 0) {
+        // which envs have a record waiting (one test per lane, no blocking)
+        bool ready = false;
+        if (lane < n_act && my_step < io.n_steps) {
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(&reinterpret_cast<ObsMail*>(zs_smem + p.prod_off + lane * mail_stride)->full);
+            uint32_t ok;
+            asm volatile("{\n.reg .pred q;\nmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}\n"
+                         : "=r"(ok) : "r"(a), "r"((uint32_t)(my_step & 1)) : "memory");
+            ready = ok != 0u;
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, ready);
+        if (todo == 0u) { __nanosleep(64); continue; }
+#pragma unroll 1
+        for (; todo; todo &= todo - 1u) {
+            const int i = __ffs(todo) - 1;
+            const int slot_i = __shfl_sync(0xffffffffu, my_slot, i), step_i = __shfl_sync(0xffffffffu, my_step, i);
+            ObsMail* const mail = reinterpret_cast<ObsMail*>(zs_smem + p.prod_off + i * mail_stride);
+            const uint32_t* rec = reinterpret_cast<const uint32_t*>(mail + 1);
+            int32_t* const obs = io.obs + (size_t)slot_i * obs_stride + (size_t)(env0 + i) * p.obs_elems;
+            const int cnt = mail->count;
+            if (cnt >= 0) {  // pass 2: the entries
+#pragma unroll 1
+                for (int k = lane; k < cnt; k += 32) {
+                    const uint32_t w0 = rec[2 * k], w1 = rec[2 * k + 1];
+                    if (simple) obs[w0] = (int32_t)w1;
+                    else {
+                        const int cell = (int)(w0 & 0xffffu);
+                        obs[cell] = (int32_t)(w0 >> 16);
+                        obs[p.cells + cell] = (int32_t)(int16_t)(w1 & 0xffffu);
+                        obs[2 * p.cells + cell] = (int32_t)(w1 >> 16);
+                    }
+                }
+            } else {  // rare: straight from the env's block (its game warp waits for `empty`)
+                Env e2;
+                e2.b = (uint32_t)(i * p.smem_per_env); e2.env = env0 + i; e2.env_global = p.env_base + (uint32_t)(env0 + i);
+                e2.gl = lane; e2.gm = 0xffffffffu; e2.gshift = 0; e2.flags = mail->flags; e2.tmpl_saddr = tmpl_saddr;
+                e2.t = e2.episode = e2.deaths = e2.zd = e2.nlive = e2.prev_zd = e2.ep_steps = 0;
+                obs_world_patch<MPC, 32, false>(p, e2, obs);
+            }
+            __syncwarp();  // (the record has been read; these stores come before this warp's next stores into the same row)
+            if (lane == 0) mbar_arrive(&mail->empty);
+            // the next step's row of this env gets its pristine planes right away, long before its record arrives
+            if (step_i + 1 < io.n_steps) {
+                const int ns = slot_i + 1 >= io.obs_slots ? 0 : slot_i + 1;
+                pristine(io.obs + (size_t)ns * obs_stride + (size_t)(env0 + i) * p.obs_elems);
+                __syncwarp();
+            }
+            if (lane == i) { my_step += 1; my_slot = my_slot + 1 >= io.obs_slots ? 0 : my_slot + 1; }
+            left -= 1;
+        }
+    }
+}
+
 // surroundings window (observation.py:99-119): rows = y, columns = x, centred on the agent's (possibly stale, if
 // dead) position; out-of-bounds cells are a fresh Wall (observation.py:43-44,64-65).  Like the world scope it is
 // written in two passes: the pristine layer of every window from the (L1-resident) padded template planes, then
