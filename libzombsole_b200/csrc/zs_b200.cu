@@ -23,12 +23,15 @@ __device__ __forceinline__ int synthetic_action(const ZsParams& p, uint32_t env_
 
 // discrete id -> (type, dx, dy): ZombsoleGymEnvDiscreteAction.game_actions (gym_env.py:328-351),
 // MultiagentZombsoleEnvDiscreteAction.game_actions (multiagent_env.py:259-285)
+// (a table: type | (dx + 1) << 8 | (dy + 1) << 16 per id — one constant-bank load instead of a chain of selects)
+__constant__ uint32_t c_discrete[8] = {
+    ZS_ACT_MOVE | (1u << 8) | (2u << 16), ZS_ACT_MOVE | (0u << 8) | (1u << 16), ZS_ACT_MOVE | (1u << 8) | (0u << 16),
+    ZS_ACT_MOVE | (2u << 8) | (1u << 16), ZS_ACT_ATTACK_CLOSEST | (1u << 8) | (1u << 16), ZS_ACT_HEAL | (1u << 8) | (1u << 16),
+    ZS_ACT_HEAL_CLOSEST | (1u << 8) | (1u << 16), ZS_ACT_NONE | (1u << 8) | (1u << 16)};
 __device__ __forceinline__ void discrete_to_action(const ZsParams& p, int id, int& type, int& dx, int& dy) {
-    type = ZS_ACT_NONE; dx = 0; dy = 0;
-    if (id < 0) { if (p.obs_per_agent) type = ZS_ACT_ABSENT; return; }
-    if (id >= p.n_discrete) return;
-    if (id < 4) { type = ZS_ACT_MOVE; dx = id == 1 ? -1 : id == 3 ? 1 : 0; dy = id == 0 ? 1 : id == 2 ? -1 : 0; }
-    else type = id == 4 ? ZS_ACT_ATTACK_CLOSEST : id == 5 ? ZS_ACT_HEAL : ZS_ACT_HEAL_CLOSEST;
+    uint32_t w = c_discrete[(unsigned)id < (unsigned)p.n_discrete ? id : 7];
+    if (id < 0 && p.obs_per_agent) w = ZS_ACT_ABSENT | (1u << 8) | (1u << 16);
+    type = (int)(w & 0xffu); dx = (int)((w >> 8) & 0xffu) - 1; dy = (int)(w >> 16) - 1;
 }
 
 // ---------------------------------------------------------------- the K-step loop, more slots than lanes

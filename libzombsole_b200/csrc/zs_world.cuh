@@ -1208,8 +1208,16 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     // (utils.py:47-52)
     unsigned gs[4];
     unsigned freemask = 0;
-#pragma unroll
-    for (int d = 0; d < 4; ++d) gs[d] = (live && !agent) ? (unsigned)grid_at(p, GRIDP, x + adj_dx(d), y + adj_dy(d)) : (unsigned)G_STATIC;
+    {
+        // (0,+1), (0,-1), (+1,0), (-1,0) from ONE cell index: a thing in the world stands inside the map, so a neighbour is
+        // outside exactly at the map's edges — four compares instead of a bounds check per neighbour
+        const bool look = live && !agent;
+        const int c0 = y * p.W + x;
+        gs[0] = !look ? (unsigned)G_STATIC : (y + 1 < p.H ? (unsigned)GRIDP[c0 + p.W] : (unsigned)G_EMPTY);
+        gs[1] = !look ? (unsigned)G_STATIC : (y > 0 ? (unsigned)GRIDP[c0 - p.W] : (unsigned)G_EMPTY);
+        gs[2] = !look ? (unsigned)G_STATIC : (x + 1 < p.W ? (unsigned)GRIDP[c0 + 1] : (unsigned)G_EMPTY);
+        gs[3] = !look ? (unsigned)G_STATIC : (x > 0 ? (unsigned)GRIDP[c0 - 1] : (unsigned)G_EMPTY);
+    }
     const int my_tm = in_cap ? (int)TM(s) : 0;
     const bool has_humans = gany<G, CV>(e, live && !zombie);
 
