@@ -221,7 +221,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
     for (int step = 0; step < io.n_steps; ++step, sn += p.N) {
         int32_t* const obs_out = obs_cur;
         if (FAST || obs_out) {
-            if (++oslot >= io.obs_slots) { oslot = 0; obs_cur = obs_first; } else obs_cur += obs_stride;
+            { const bool wrap = ++oslot >= io.obs_slots; oslot = wrap ? 0 : oslot; obs_cur = wrap ? obs_first : obs_cur + obs_stride; }
             // pass 1 of the world observation does not depend on the transition: issue its stores now
             if constexpr (world_obs && !PROD) { if (FAST || io.compact == nullptr) obs_world_template<MPC, G, CV>(p, e, obs_out); }
         }

@@ -1395,11 +1395,23 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             const uint4 v = reinterpret_cast<const uint4*>(S.fyj)[q];
             jw[4 * q] = v.x; jw[4 * q + 1] = v.y; jw[4 * q + 2] = v.z; jw[4 * q + 3] = v.w;
         }
-#pragma unroll
-        for (int i = MPC - 1; i >= 1; --i) {
-            const int j = (int)((jw[i >> 2] >> (8 * (i & 3))) & 0xffu);  // j == i beyond the list: both branches keep my_pos
-            my_pos = my_pos == i ? j : (my_pos == j ? i : my_pos);
+        // iterations at or beyond the list's length swap nothing: enter the unrolled sequence at the longest list of the
+        // warp (one indexed branch; the cases fall through down to iteration 1)
+#define ZS_FY(i)                                                                        \
+    case (i) + 1:                                                                       \
+        if constexpr ((i) < MPC) {                                                      \
+            const int j = (int)((jw[(i) >> 2] >> (8 * ((i) & 3))) & 0xffu);             \
+            my_pos = my_pos == (i) ? j : (my_pos == j ? (i) : my_pos);                  \
         }
+        const int Lw = wmax<G, CV>(e, L);
+        switch (Lw < MPC ? Lw : MPC) {
+            ZS_FY(31) ZS_FY(30) ZS_FY(29) ZS_FY(28) ZS_FY(27) ZS_FY(26) ZS_FY(25) ZS_FY(24)
+            ZS_FY(23) ZS_FY(22) ZS_FY(21) ZS_FY(20) ZS_FY(19) ZS_FY(18) ZS_FY(17) ZS_FY(16)
+            ZS_FY(15) ZS_FY(14) ZS_FY(13) ZS_FY(12) ZS_FY(11) ZS_FY(10) ZS_FY(9) ZS_FY(8)
+            ZS_FY(7) ZS_FY(6) ZS_FY(5) ZS_FY(4) ZS_FY(3) ZS_FY(2) ZS_FY(1)
+            default: break;
+        }
+#undef ZS_FY
     }
     if (my_pos >= 0) ACT(my_pos) = my_word;
     if (in_cap) { MPOS(s) = (uint8_t)(((uint32_t)my_word & 7u) == X_MOVE ? my_pos : RK_NONE); MVP(s) = RK_NONE; }
