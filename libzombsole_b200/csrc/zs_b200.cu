@@ -62,8 +62,6 @@ __device__ __forceinline__ void step_loop_general(const ZsParams& p, const ZsIO&
     int oslot = 0;
 #pragma unroll 1
     for (int step = 0; step < io.n_steps; ++step) {
-        // (experiment, ZS_STEP_SYNC: the warps of a CTA start every step together, for instruction-cache locality)
-        if (p.step_sync) __syncthreads();
         const size_t sn = (size_t)step * p.N + env;
         int32_t* obs_out = nullptr;
         if (io.obs) {
@@ -980,7 +978,6 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) lanes0 = lanes1 = v;
     }
     h->short_steps = 8;
-    p.step_sync = getenv("ZS_STEP_SYNC") ? 1 : 0;
     h->use_pdl = getenv("ZS_PDL") ? 1 : 0;  // (measured: -8 % on back-to-back single steps, but a launch on an idle stream starts later)
     if (const char* force = getenv("ZS_SHORT_STEPS")) h->short_steps = atoi(force);
     h->tmpl_single_step = getenv("ZS_NO_TMA_SINGLE") ? 0 : 1;
@@ -1043,7 +1040,6 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
             const int total = off + ZS_PROD_ENVS * ((int)sizeof(ObsMail) + 8 * cap);
             if ((total + 1024) * 4 <= (int)prop.sharedMemPerMultiprocessor) { sh.prod_off = off; sh.prod_cap = cap; sh.prod_smem_bytes = total; }
         }
-        if (const char* pad = getenv("ZS_EXTRA_SMEM")) sh.smem_bytes += atoi(pad) & ~15;  // (experiment: fewer resident CTAs)
         if (sh.smem_bytes > (int)prop.sharedMemPerBlockOptin) { zs_destroy(h); return fail("map/thing count needs more shared memory than one CTA has"); }
         // (the attribute belongs to the kernel, not to the handle: every handle asks for all a CTA can have, so that handles
         // of different maps can live side by side)

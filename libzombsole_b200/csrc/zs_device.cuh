@@ -113,7 +113,6 @@ struct ZsParams {
     int32_t prod_off;              // producer-warp launches: CTA-shared mailboxes (ObsMail + record) of the CTA's envs, -1 if unused
     int32_t prod_cap;              // entries one record holds
     int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
-    int32_t step_sync;             // (experiment) general step loop: __syncthreads at the top of every step
 };
 
 struct ZsIO {
