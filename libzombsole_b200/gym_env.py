@@ -245,6 +245,11 @@ class ZombsoleVectorEnv(object):
         """Text frame of world ``env`` laid out like the reference's terminal renderer (renderer.py:45-88); debugging aid."""
         return self.game(env).draw_text(use_basic_icons)
 
+    def render_image(self, env=0, with_text=True):
+        """RGB frame (uint8 [height, width, 3]) of world ``env`` with the geometry and shapes of the reference's OpenCV
+        renderer (renderer.py:97-277); debugging aid."""
+        return self.game(env).draw_image(with_text)
+
     def close(self):
         self.engine.close()
 

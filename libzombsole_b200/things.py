@@ -204,6 +204,12 @@ class Game(object):
         from .renderer import TerminalRenderer
         return TerminalRenderer(use_basic_icons).draw_text(self)
 
+    def draw_image(self, with_text=True):
+        """The frame the reference's OpenCV renderer would show (renderer.py:241-277), as an RGB uint8 array."""
+        from .renderer import ImageRenderer
+        w, h = self.map.size
+        return ImageRenderer(w, h + 2 + len(self.players) + len(self.agents)).draw_image(self, with_text)
+
     def draw(self):
         print(self.draw_text())
 
