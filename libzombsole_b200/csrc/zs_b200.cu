@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(SHAPE == 3 ? 160 : ZS_WPC * 32, OCC) zs_sim_ke
         if (io.env_mask && !io.env_mask[env]) return;
         // slots keep their last position/life until re-placed; bring them in so the store is complete
         if (p.img_load) { load_image_issue<MPC, G, CV>(p, e); load_image_wait<MPC, G, CV>(p, e); }
-        else load_state<MPC, G, CV>(p, e, false);
+        else load_state<MPC, G, CV>(p, e, false, true);
         if (!p.img) e.flags |= FL_DEAD_LAUNCH;
         const int k = initialize_world<MPC, G, false>(p, id_of(e), e.episode + 1, e.flags);
         scalars_from_smem<MPC, G, CV>(p, e);

@@ -264,7 +264,10 @@ ZS_TPL __device__ __noinline__ int scan_dead_bodies(const ZsParams& p, GrpId id)
 }
 
 // with_lists: also build the dead-body list (worth it when the launch runs several steps; a single step walks the bitmap)
-ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, bool with_lists) {
+// for_reset: the world is about to be re-initialised — the dead-body bitmap, the tracker lives and the dict order are all
+// set anew by the world init, so they are neither loaded nor derived (the slots are: one that is not placed again keeps
+// what it holds, and the store writes every slot).
+ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, bool with_lists, bool for_reset = false) {
     ZS_CONSTS; ZS_VIEWS;
     const size_t row = (size_t)e.env * p.Mp;
     // A launch starts with a handful of dependent round trips to memory unless the loads are issued together: the first
@@ -278,8 +281,8 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, boo
     constexpr int DR = 96 / G;  // rounds of the dead-body bitmap issued up front (96 words = 3,072 cells)
     uint32_t dw[DR];
 #pragma unroll
-    for (int r = 0; r < DR; ++r) dw[r] = e.gl + r * G < p.dead_words ? dead[e.gl + r * G] : 0u;
-    const int pv = e.gl < p.Ap ? (int)p.PREV[(size_t)e.env * p.Ap + e.gl] : 0;
+    for (int r = 0; r < DR; ++r) dw[r] = (!for_reset && e.gl + r * G < p.dead_words) ? dead[e.gl + r * G] : 0u;
+    const int pv = (!for_reset && e.gl < p.Ap) ? (int)p.PREV[(size_t)e.env * p.Ap + e.gl] : 0;
     const bool sl_here = !(MPC > 32 && p.sl_global);
     const uint4* sl4 = (const uint4*)(p.SLIFE + (size_t)e.env * p.Sp);
     constexpr int SR = 32 / G;  // rounds of box/wall lives issued up front (32 words = 256 boxes/walls)
@@ -310,10 +313,10 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, boo
 #pragma unroll
     for (int r = 0; r < DR; ++r) if (e.gl + r * G < p.dead_words) DEADW(e.gl + r * G) = dw[r];
 #pragma unroll 1
-    for (int w = e.gl + DR * G; w < p.dead_words; w += G) DEADW(w) = dead[w];
+    for (int w = e.gl + DR * G; w < p.dead_words; w += G) DEADW(w) = for_reset ? 0u : dead[w];
     if (e.gl < p.Ap) PREVL(e.gl) = (int16_t)pv;
 #pragma unroll 1
-    for (int a = e.gl + G; a < p.Ap; a += G) PREVL(a) = p.PREV[(size_t)e.env * p.Ap + a];
+    for (int a = e.gl + G; a < p.Ap; a += G) PREVL(a) = for_reset ? (int16_t)0 : p.PREV[(size_t)e.env * p.Ap + a];
     if (sl_here) {
 #pragma unroll
         for (int r = 0; r < SR; ++r) if (e.gl + r * G < (p.Sp >> 3)) reinterpret_cast<uint4*>(SLP)[e.gl + r * G] = sv[r];
@@ -322,7 +325,8 @@ ZS_TPL __device__ __forceinline__ void load_state(const ZsParams& p, Env& e, boo
     }
     scalars_from_lane<G, CV>(e, sc);
     gsync<G, CV>(e);
-    e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e), st0);
+    if (for_reset) e.nlive = 0;
+    else e.nlive = ranks_from_stamps<MPC, G, false>(p, id_of(e), st0);
     e.flags = (e.flags & FL_FRESH) | scan_damaged_statics<MPC, G, false>(p, id_of(e), e.flags & FL_FRESH);
     if (ONE && with_lists) e.flags |= scan_dead_bodies<MPC, G, false>(p, id_of(e));
     else e.flags |= FL_DEAD_OVER;
