@@ -1256,53 +1256,47 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
         const uint32_t gxy = tg >= 0 ? TXY(tg) : 0u;
         const int gx = xy_x(gxy), gy = xy_y(gxy);
         if (!agent) {
-            // the four adjacent cells: how far they are from the target
+            // The scripted actors decide with as little divergence as possible: the lanes of a warp are zombies, terminators
+            // and others side by side, and every branch one kind takes is issued for the whole warp.
+            // the four adjacent cells: how far they are from the target, which are free, which hold a box/wall
             int dd[4];
+            unsigned staticmask = 0;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 dd[d] = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
                 if (!g_is_thing(gs[d])) freemask |= 1u << d;
+                if (g_is_static(gs[d])) staticmask |= 1u << d;
             }
-            if (zombie) {  // Zombie.next_step (things.py:70-105)
-                if (!has_humans) {
-                    if (freemask) type = D_WANDER;
-                } else if (d2 <= 2) { type = D_ATTACK; a = tg; }  // distance < 1.5 (things.py:83)
-                else {
-                    // free cells: closest(target, positions), first minimum in adjacency order; boxed in: the first
-                    // Box/Wall among the adjacent cells stably sorted by distance to the target (things.py:88-99)
-                    int bdir = -1, bdist = 0x7fffffff;
+            const bool term = bkind == ZS_KIND_TERMINATOR;
+            // Zombie.next_step (things.py:70-105): a human out of reach (distance >= 1.5) is chased — to the free adjacent
+            // cell closest to it (first minimum in adjacency order), or, boxed in, the first Box/Wall among the adjacent
+            // cells stably sorted by distance to the target is attacked (things.py:88-99).
+            // Terminator.next_step (players/terminator.py:9-37): a zombie out of range is approached through the adjacent
+            // cell closest to it, out-of-bounds cells included; what stands there is healed (a player) or attacked.
+            const bool z_chase = zombie && has_humans && d2 > 2;
+            const bool t_chase = term && tg >= 0 && d2 > c_range2[my_tm & 15];
+            const unsigned cand = t_chase ? 0xfu : (freemask ? freemask : staticmask);
+            int bdir = -1, bdist = 0x7fffffff;
 #pragma unroll
-                    for (int d = 0; d < 4; ++d) {
-                        const bool cand = freemask ? ((freemask >> d) & 1u) : g_is_static(gs[d]);
-                        if (cand && dd[d] < bdist) { bdir = d; bdist = dd[d]; }
-                    }
-                    if (bdir >= 0) {
-                        const int cx = x + adj_dx(bdir), cy = y + adj_dy(bdir);
-                        if (freemask) { type = D_MOVE; a = cx; b = cy; }
-                        else { type = D_ATTACK; a = p.M + (int)__ldg(p.cell_static + cy * p.W + cx); }
-                    }
-                }
-            } else if (bkind == ZS_KIND_TERMINATOR) {  // Terminator.next_step (players/terminator.py:9-37)
-                if (tg < 0) { type = D_HEAL; a = s; }
-                else if (d2 > c_range2[my_tm & 15]) {
-                    int bdir = 0, bdist = 0x7fffffff, g = 0;
-#pragma unroll
-                    for (int d = 0; d < 4; ++d)  // closest(target, adjacent_positions(self)): out-of-bounds cells included
-                        if (dd[d] < bdist) { bdir = d; bdist = dd[d]; g = (int)gs[d]; }
-                    const int bx = x + adj_dx(bdir), by = y + adj_dy(bdir);
-                    if (g_is_thing(g)) {
-                        type = (g <= G_MAX_SLOT && (g - 1) < NP) ? D_HEAL : D_ATTACK;
-                        a = target_of_cell(p, g, by * p.W + bx);
-                    } else { type = D_MOVE; a = bx; b = by; }
-                } else { type = D_ATTACK; a = tg; }
-            } else if (bkind == ZS_KIND_SNIPER) {  // Sniper.next_step (players/sniper.py:9-19)
-                if (tg >= 0) { type = D_ATTACK; a = tg; }
-            } else if (bkind == ZS_KIND_TROLL) {   // Troll.next_step (players/troll.py:10-12)
-                type = D_HEAL; a = s;
-            } else if (bkind == ZS_KIND_HAMSTER) { // Hamster.next_step (players/hamster.py:10-14)
-                if (freemask) type = D_WANDER;
-            } else {                               // RandoMan.next_step: resolved in decide_draws_seq
-                type = D_RANDOM;
+            for (int d = 0; d < 4; ++d)
+                if (((cand >> d) & 1u) && dd[d] < bdist) { bdir = d; bdist = dd[d]; }
+            if ((z_chase || t_chase) && bdir >= 0) {
+                const int cx = x + adj_dx(bdir), cy = y + adj_dy(bdir);
+                const int g = (int)(bdir == 0 ? gs[0] : bdir == 1 ? gs[1] : bdir == 2 ? gs[2] : gs[3]);
+                if (g_is_thing(g)) {
+                    type = (g <= G_MAX_SLOT && (g - 1) < NP) ? D_HEAL : D_ATTACK;
+                    a = target_of_cell(p, g, cy * p.W + cx);
+                } else { type = D_MOVE; a = cx; b = cy; }
+            } else {
+                // zombie next to its human: attack it (distance < 1.5, things.py:83); no humans: wander (things.py:101-103);
+                // terminator: in range attack, no zombies heal self; Sniper (players/sniper.py:9-19): attack the closest
+                // zombie; Troll (troll.py:10-12): heal self; Hamster (hamster.py:10-14): wander; RandoMan: decide_draws_seq
+                const bool attack_tg = (zombie && has_humans && d2 <= 2) || (term && tg >= 0 && !t_chase) ||
+                                       (bkind == ZS_KIND_SNIPER && tg >= 0);
+                const bool heal_self = (term && tg < 0) || bkind == ZS_KIND_TROLL;
+                const bool wander = freemask != 0u && ((zombie && !has_humans) || bkind == ZS_KIND_HAMSTER);
+                type = attack_tg ? D_ATTACK : heal_self ? D_HEAL : wander ? D_WANDER : bkind == ZS_KIND_RANDOMAN ? D_RANDOM : D_IDLE;
+                a = attack_tg ? tg : heal_self ? s : 0;
             }
         } else {  // Agent.next_step (players/agent.py:28-96)
             // (a step of two cells or more fails whatever its length, core.py:149-153: clamped, so nothing can overflow)
