@@ -257,6 +257,26 @@ int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t*
                       int32_t* overflow_envs_host, int32_t* n_overflow, int32_t compact_words, int32_t first_call,
                       int32_t n_threads);
 
+/* zs_step_host: zs_step_compact + zs_expand_compact in one call for a caller whose buffers live in HOST memory.
+ * `actions_host` (int32 [N, A(,3)], any host memory; pinned avoids a staging copy) goes to the device with the copy engine
+ * ahead of the launch.  The kernel writes `compact_pinned` (uint32 [N, compact_words]) in place — it must be page-locked
+ * host memory the device can address (cudaHostAlloc / cudaHostRegister / torch pin_memory) — as coalesced rows, and the
+ * warp that completes the batch raises a flag in pinned memory behind one system-scope fence; n_threads host threads,
+ * already spinning on that flag inside their parallel region, expand the records into obs_host / reward_host / terminated_host / truncated_host (ordinary
+ * host memory, as for zs_expand_compact) the moment it shows.  No device-to-host copy, no stream synchronisation and no
+ * thread wake-up are on the way of a step; when the call returns every env has been expanded, the action buffer is the
+ * caller's again, and obs_dev holds the rows of the envs listed in overflow_envs_host (as for zs_expand_compact; the
+ * call synchronises the stream when there are any).  prev_host / first_call as for zs_expand_compact (one prev_host per record buffer).  Fails
+ * after ten seconds if the flag does not show.  (Reference: the same transition as gym_env.py:99-145 returns to a caller
+ * on the host.) */
+int zs_step_host(ZsHandle* h, const int32_t* actions_host, int32_t action_format, uint32_t* compact_pinned,
+                 uint32_t* prev_host, int32_t compact_words, int32_t* obs_dev, int32_t* obs_host, double* reward_host,
+                 uint8_t* terminated_host, uint8_t* truncated_host, int32_t* overflow_envs_host, int32_t* n_overflow,
+                 int32_t first_call, int32_t n_threads, void* stream);
+/* diagnostics: out[4] = zs_step_host calls since the last read, and the mean microseconds from entry until the launches
+ * were issued / the flag showed (every record in host memory) / the call returned (every env expanded) */
+int zs_step_host_stats(ZsHandle* h, double* out);
+
 /* actions_dev int32 [N, A]: uniform discrete ids for step `step_index` (Philox action stream). */
 int zs_fill_synthetic_actions(ZsHandle* h, int64_t step_index, int32_t* actions_dev, void* stream);
 /* the same for n_steps consecutive steps in one launch: actions_dev int32 [n_steps, N, A] (an action tape for zs_rollout) */

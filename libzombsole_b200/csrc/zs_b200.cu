@@ -6,7 +6,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
+#include <omp.h>
 #include <vector>
 
 #include "zs_device.cuh"
@@ -316,11 +318,30 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
                 uint32_t* const rec = io.compact + (size_t)env * io.compact_words;
                 int n_ent = 0;
                 const bool over = obs_world_compact<MPC, G, CV>(p, e, rec, io.compact_words - ZS_COMPACT_HEADER, n_ent);
-                if (lane == 0) rec[0] = (uint32_t)n_ent | (done ? 1u << 16 : 0u) | (trunc ? 1u << 17 : 0u) | (over ? 1u << 18 : 0u);
-                if (lane_sum ? lane == 0 : aidx == 0) { rec[2] = (uint32_t)__double2loint(rew); rec[3] = (uint32_t)__double2hiint(rew); }
+                {
+                    uint32_t* const stage = reinterpret_cast<uint32_t*>(zs_smem + e.b);  // (EnvS::act: see obs_world_compact)
+                    if (lane == 0) { stage[0] = (uint32_t)n_ent | (done ? 1u << 16 : 0u) | (trunc ? 1u << 17 : 0u) | (over ? 1u << 18 : 0u); stage[1] = 0u; }
+                    if (lane_sum ? lane == 0 : aidx == 0) { stage[2] = (uint32_t)__double2loint(rew); stage[3] = (uint32_t)__double2hiint(rew); }
+                    compact_flush<MPC, G, CV>(e, rec, ZS_COMPACT_HEADER + n_ent * (p.obs_enc == ZS_OBS_SIMPLE ? 1 : 2));
+                }
                 if (wany<G, CV>(e, over) && obs_out) {  // rare: the full row, for the caller to fetch
                     obs_world_template<MPC, G, CV>(p, e, obs_out);
                     obs_world_patch<MPC, G, CV>(p, e, obs_out);
+                }
+                if (io.host_flags) {
+                    // ONE system-scope fence per group of envs, by whoever completes the group (a fence per warp takes 8-34 us
+                    // when 4,096 warps fence at once): the others order their record words before the counter at gpu scope
+                    __threadfence();
+                    gsync<G, CV>(e);
+                    if (lane == 0) {
+                        const int grp = env / io.group_envs;
+                        const int size = min(io.group_envs, p.N - grp * io.group_envs);
+                        if (atomicAdd(io.group_count + grp, 1) == size - 1) {
+                            io.group_count[grp] = 0;
+                            __threadfence_system();
+                            *reinterpret_cast<volatile uint32_t*>(io.host_flags + 16 * grp) = io.ticket;
+                        }
+                    }
                 }
             }
         }
@@ -525,6 +546,12 @@ __global__ void zs_stats_kernel(unsigned long long* stats, int64_t* out, int res
     }
 }
 
+// zs_step_host with ZS_HOST_GROUPS=0 (a diagnostic setting): runs behind the step kernel in the stream — that kernel's writes to
+// host memory are complete and visible when this one starts — and tells the waiting host threads so.  The default is a flag
+// raised by the step kernel itself (ZsIO::host_flags): 3-5 us earlier.
+#define ZS_HOST_GROUPS_MAX 256
+__global__ void zs_host_flag_kernel(volatile uint32_t* flag, uint32_t ticket) { *flag = ticket; }
+
 // ================================================================ host side
 static thread_local char g_err[512] = "";
 static int fail(const char* fmt, const char* a = "") {
@@ -561,6 +588,13 @@ struct ZsHandle {
     int short_steps;       // launches of fewer steps than this take shape[1]
     int use_pdl;           // launch with programmatic stream serialization (launch_sim)
     int compact_words;     // words per compact observation record, 0 = this configuration has no compact form
+    int32_t* host_actions_dev = nullptr;  // zs_step_host: this step's actions on the device
+    uint32_t host_ticket = 0;  // zs_step_host: the value that marks the current step's records as arrived
+    volatile uint32_t* host_flag = nullptr;  // pinned, one cache line each: [0] zs_host_flag_kernel's, [1 + g] group g's (the step kernel's)
+    int32_t* host_group_count = nullptr;     // device: envs of each group done in this step
+    int host_groups = 0;
+    const void* host_records_checked = nullptr;
+    double host_stats[4] = {0, 0, 0, 0};  // zs_step_host: calls, and summed us from entry to: launched / flag seen / return
     std::vector<int32_t> tmpl_obs_host;  // the pristine observation planes [obs_C][cells] (zs_expand_compact)
     int tmpl_single_step;  // launches of fewer than four steps stage the observation template for the TMA as well
     bool img_valid;  // the parked images (ZsParams::img) match the canonical state of every env
@@ -1078,6 +1112,7 @@ extern "C" __attribute__((visibility("default"))) int zs_destroy(ZsHandle* h) {
     DeviceGuard guard(h);
     cudaDeviceSynchronize();
     for (void* d : h->dev_allocs) cudaFree(d);
+    if (h->host_flag) cudaFreeHost((void*)h->host_flag);
     delete h;
     return 0;
 }
@@ -1195,6 +1230,57 @@ extern "C" __attribute__((visibility("default"))) int zs_step_compact(ZsHandle* 
     return launched(h);
 }
 
+static int host_threads(int n_threads, int N) {
+    if (n_threads <= 0) {
+        cpu_set_t set;
+        n_threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
+    }
+    return n_threads > N ? N : n_threads;
+}
+
+// HOST code: one env's record -> its row of the observation tensor, reward and flags.  Returns true when the record could not
+// hold the env (overflow bit): the caller copies that row from the device.
+struct ExpandCtx {
+    const int32_t* T;  // the pristine observation planes [C][cells]
+    int cells, C, wpe, words;
+    bool first_call;
+    int32_t* obs; double* reward; uint8_t* terminated; uint8_t* truncated;
+};
+static inline bool expand_one(const ExpandCtx& cx, int e, const uint32_t* r, uint32_t* pv) {
+    const int cells = cx.cells, C = cx.C, wpe = cx.wpe;
+    const int32_t* T = cx.T;
+    const size_t row = (size_t)C * cells;
+    int32_t* o = cx.obs + (size_t)e * row;
+    const uint32_t h0 = r[0];
+    const int n = (int)(h0 & 0xffffu);
+    if (cx.terminated) cx.terminated[e] = (uint8_t)((h0 >> 16) & 1u);
+    if (cx.truncated) cx.truncated[e] = (uint8_t)((h0 >> 17) & 1u);
+    if (cx.reward) memcpy(cx.reward + e, r + 2, sizeof(double));
+    const bool prev_unknown = cx.first_call || ((pv[0] >> 18) & 1u);
+    if ((h0 >> 18) & 1u) { pv[0] = h0; return true; }
+    if (prev_unknown) memcpy(o, T, row * sizeof(int32_t));
+    else {
+        const int pn = (int)(pv[0] & 0xffffu);
+        for (int i = 0; i < pn; ++i) {
+            const int cell = (int)(pv[ZS_COMPACT_HEADER + i * wpe] & 0xffffu);
+            for (int c = 0; c < C; ++c) o[(size_t)c * cells + cell] = T[(size_t)c * cells + cell];
+        }
+    }
+    if (wpe == 1) {
+        for (int i = 0; i < n; ++i) { const uint32_t w = r[ZS_COMPACT_HEADER + i]; o[w & 0xffffu] = (int32_t)(w >> 16); }
+    } else {
+        for (int i = 0; i < n; ++i) {
+            const uint32_t w0 = r[ZS_COMPACT_HEADER + 2 * i], w1 = r[ZS_COMPACT_HEADER + 2 * i + 1];
+            const int cell = (int)(w0 & 0xffffu);
+            o[cell] = (int32_t)(w0 >> 16);
+            o[(size_t)cells + cell] = (int32_t)(int16_t)(w1 & 0xffffu);
+            o[2 * (size_t)cells + cell] = (int32_t)(w1 >> 16);
+        }
+    }
+    memcpy(pv, r, (size_t)(ZS_COMPACT_HEADER + n * wpe) * sizeof(uint32_t));
+    return false;
+}
+
 // HOST code: records -> the reference's observation tensor (include/zs_b200.h).  Incremental: the cells the previous
 // record of an env patched go back to the pristine value, the new record's cells are written; a full row is only
 // rewritten on the first call and after an overflow.
@@ -1208,56 +1294,157 @@ extern "C" __attribute__((visibility("default"))) int zs_expand_compact(const Zs
     if (compact_words < ZS_COMPACT_HEADER + 8) return fail("compact_words out of range");
     const int N = h->p.N, words = compact_words, cells = h->p.cells, C = h->p.obs_C;
     const bool simple = h->p.obs_enc == ZS_OBS_SIMPLE;
-    const int wpe = simple ? 1 : 2;
-    const int32_t* T = h->tmpl_obs_host.data();
-    const size_t row = (size_t)C * cells;
-    if (n_threads <= 0) {
-        cpu_set_t set;
-        n_threads = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : 1;
-    }
-    if (n_threads > N) n_threads = N;
+    n_threads = host_threads(n_threads, N);
     int n_over = 0;
+    const ExpandCtx cx{h->tmpl_obs_host.data(), cells, C, simple ? 1 : 2, words, first_call != 0, obs_host, reward_host, terminated_host,
+                       truncated_host};
 #pragma omp parallel for num_threads(n_threads) schedule(static)
     for (int e = 0; e < N; ++e) {
-        const uint32_t* r = compact_host + (size_t)e * words;
-        uint32_t* pv = prev_host + (size_t)e * words;
-        int32_t* o = obs_host + (size_t)e * row;
-        const uint32_t h0 = r[0];
-        const int n = (int)(h0 & 0xffffu);
-        if (terminated_host) terminated_host[e] = (uint8_t)((h0 >> 16) & 1u);
-        if (truncated_host) truncated_host[e] = (uint8_t)((h0 >> 17) & 1u);
-        if (reward_host) memcpy(reward_host + e, r + 2, sizeof(double));
-        const bool prev_unknown = first_call || ((pv[0] >> 18) & 1u);
-        if ((h0 >> 18) & 1u) {  // the record could not hold this env: the caller copies its row from the device
+        if (expand_one(cx, e, compact_host + (size_t)e * words, prev_host + (size_t)e * words)) {
             int at;
 #pragma omp atomic capture
             at = n_over++;
             overflow_envs_host[at] = e;
-            pv[0] = h0;
-            continue;
         }
-        if (prev_unknown) memcpy(o, T, row * sizeof(int32_t));
-        else {
-            const int pn = (int)(pv[0] & 0xffffu);
-            for (int i = 0; i < pn; ++i) {
-                const int cell = (int)(pv[ZS_COMPACT_HEADER + i * wpe] & 0xffffu);
-                for (int c = 0; c < C; ++c) o[(size_t)c * cells + cell] = T[(size_t)c * cells + cell];
-            }
-        }
-        if (simple) {
-            for (int i = 0; i < n; ++i) { const uint32_t w = r[ZS_COMPACT_HEADER + i]; o[w & 0xffffu] = (int32_t)(w >> 16); }
-        } else {
-            for (int i = 0; i < n; ++i) {
-                const uint32_t w0 = r[ZS_COMPACT_HEADER + 2 * i], w1 = r[ZS_COMPACT_HEADER + 2 * i + 1];
-                const int cell = (int)(w0 & 0xffffu);
-                o[cell] = (int32_t)(w0 >> 16);
-                o[(size_t)cells + cell] = (int32_t)(int16_t)(w1 & 0xffffu);
-                o[2 * (size_t)cells + cell] = (int32_t)(w1 >> 16);
-            }
-        }
-        memcpy(pv, r, (size_t)(ZS_COMPACT_HEADER + n * wpe) * sizeof(uint32_t));
     }
     *n_overflow = n_over;
+    return 0;
+}
+
+// One transition with HOST buffers (include/zs_b200.h): the actions go over with the copy engine, the kernel writes the
+// pinned record buffer itself (coalesced rows staged in shared memory) and whoever completes the batch raises a flag in
+// pinned memory behind ONE system-scope fence; the host threads are already spinning on that flag inside their parallel
+// region and expand the records the moment it shows.  No device-to-host copy, no stream synchronisation, no thread
+// wake-up on the way.  What was measured on the way here (profiles/r02_e2e_host_step.txt): a fence + ticket per warp, so
+// that envs could be expanded as they arrive, costs 8-34 us per warp with 4,096 warps fencing at once; a flag per group
+// of envs does not arrive earlier than the last one either (a system-scope fence waits for the whole burst to drain), so
+// one group is the default (ZS_HOST_GROUPS).
+extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, const int32_t* actions_host, int32_t action_format,
+                                                                    uint32_t* compact_pinned, uint32_t* prev_host, int32_t compact_words,
+                                                                    int32_t* obs_dev, int32_t* obs_host, double* reward_host,
+                                                                    uint8_t* terminated_host, uint8_t* truncated_host,
+                                                                    int32_t* overflow_envs_host, int32_t* n_overflow, int32_t first_call,
+                                                                    int32_t n_threads, void* stream) {
+    if (int rc = check_bound(h)) return rc;
+    DeviceGuard guard(h);
+    if (!h->compact_words) return fail("this configuration has no compact observation form (world scope, one reward per env, at most 32 slots)");
+    if (!actions_host || !compact_pinned || !prev_host || !obs_host || !overflow_envs_host || !n_overflow) return fail("null argument");
+    if (compact_words < ZS_COMPACT_HEADER + 8 || compact_words > 65535) return fail("compact_words out of range");
+    if (action_format != ZS_ACTIONS_FULL && action_format != ZS_ACTIONS_DISCRETE) return fail("bad action format");
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto us_since = [&ts0]() {
+        struct timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        return (double)(t.tv_sec - ts0.tv_sec) * 1e6 + (double)(t.tv_nsec - ts0.tv_nsec) * 1e-3;
+    };
+    if (compact_pinned != h->host_records_checked) {  // the device must reach the record buffer in place (checked once per buffer)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, compact_pinned) != cudaSuccess || (at.type != cudaMemoryTypeHost && at.type != cudaMemoryTypeManaged)) {
+            cudaGetLastError();
+            return fail("zs_step_host needs the records in pinned (page-locked) host memory");
+        }
+        h->host_records_checked = compact_pinned;
+    }
+    const cudaStream_t st = (cudaStream_t)stream;
+    // the actions go over with the copy engine: 4,096 warps each reading its own word of host memory in place is 4,096 PCIe
+    // read round trips
+    const size_t act_bytes = (size_t)h->p.N * h->p.A * (action_format == ZS_ACTIONS_FULL ? 3 : 1) * sizeof(int32_t);
+    if (!h->host_actions_dev) {
+        void* d = nullptr;
+        if (cudaMalloc(&d, (size_t)h->p.N * h->p.A * 3 * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory (action buffer)"); }
+        h->dev_allocs.push_back(d);
+        h->host_actions_dev = (int32_t*)d;
+        CU(cudaHostAlloc((void**)&h->host_flag, 64 * (ZS_HOST_GROUPS_MAX + 1), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset((void*)h->host_flag, 0, 64 * (ZS_HOST_GROUPS_MAX + 1));
+        if (cudaMalloc(&d, ZS_HOST_GROUPS_MAX * sizeof(int32_t)) != cudaSuccess) { cudaGetLastError(); return fail("out of device memory (group counters)"); }
+        h->dev_allocs.push_back(d);
+        h->host_group_count = (int32_t*)d;
+        CU(cudaMemsetAsync(d, 0, ZS_HOST_GROUPS_MAX * sizeof(int32_t), st));
+        const char* force = getenv("ZS_HOST_GROUPS");
+        h->host_groups = force ? atoi(force) : 1;
+        if (h->host_groups > ZS_HOST_GROUPS_MAX) h->host_groups = ZS_HOST_GROUPS_MAX;
+        if (h->host_groups > h->p.N) h->host_groups = h->p.N;
+    }
+    CU(cudaMemcpyAsync(h->host_actions_dev, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
+    const int N = h->p.N, words = compact_words;
+    uint32_t ticket = ++h->host_ticket;
+    if (ticket == 0) ticket = ++h->host_ticket;
+    ZsIO io;
+    memset(&io, 0, sizeof(io));
+    io.actions = h->host_actions_dev; io.fmt = action_format; io.obs = obs_dev; io.obs_slots = 1;
+    io.compact = compact_pinned; io.compact_words = compact_words;
+    io.n_steps = 1;
+    const int groups = h->host_groups;  // 0: one flag for everything, raised by a kernel behind the step kernel
+    const int group_envs = groups > 0 ? (N + groups - 1) / groups : N;
+    if (groups > 0) { io.host_flags = (uint32_t*)h->host_flag + 16; io.group_count = h->host_group_count; io.group_envs = group_envs; io.ticket = ticket; }
+    launch_sim<MODE_STEP>(h, io, st);
+    if (groups <= 0) { zs_host_flag_kernel<<<1, 1, 0, st>>>(h->host_flag, ticket); h->launches++; }
+    if (int rc = launched(h)) return rc;
+    const double us_launched = us_since();
+    double us_flag = 0;
+    n_threads = host_threads(n_threads, N);
+    const ExpandCtx cx{h->tmpl_obs_host.data(), h->p.cells, h->p.obs_C, h->p.obs_enc == ZS_OBS_SIMPLE ? 1 : 2, words, first_call != 0,
+                       obs_host, reward_host, terminated_host, truncated_host};
+    int n_over = 0, gave_up = 0;
+    const volatile uint32_t* const flags = h->host_flag;
+    const int n_flags = groups > 0 ? (N + group_envs - 1) / group_envs : 1;
+#pragma omp parallel num_threads(n_threads)
+    {
+        // every thread waits for the flags itself (nobody has to be woken when one shows) and expands its share of each
+        // group as the group arrives, while the records of later groups are still on their way
+        // (shares cut by hand: a thread that gave up must not leave the others stuck in a work-sharing construct)
+        const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
+        struct timespec t0;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int g = 0; g < n_flags; ++g) {
+            const volatile uint32_t* const flag = flags + (groups > 0 ? 16 * (g + 1) : 0);
+            for (unsigned spins = 1; *flag != ticket; ++spins) {
+                __builtin_ia32_pause();
+                if ((spins & 0xfffffu) == 0) {  // a launch that died never delivers: give up after ten seconds
+                    struct timespec t1;
+                    clock_gettime(CLOCK_MONOTONIC, &t1);
+                    if (t1.tv_sec - t0.tv_sec > 10) break;
+                }
+            }
+            __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            if (*flag != ticket) {
+#pragma omp atomic write
+                gave_up = 1;
+                break;
+            }
+            if (tid == 0 && g == 0) us_flag = us_since();
+            const int g0 = g * group_envs, gn = (g0 + group_envs < N ? g0 + group_envs : N) - g0;
+            const int e0 = g0 + (int)((long long)gn * tid / nt), e1 = g0 + (int)((long long)gn * (tid + 1) / nt);
+            for (int e = e0; e < e1; ++e) {
+                if (expand_one(cx, e, compact_pinned + (size_t)e * words, prev_host + (size_t)e * words)) {
+                    int at;
+#pragma omp atomic capture
+                    at = n_over++;
+                    overflow_envs_host[at] = e;
+                }
+            }
+        }
+    }
+    *n_overflow = n_over;
+    if (gave_up) {
+        const cudaError_t err = cudaStreamSynchronize(st);
+        return err != cudaSuccess ? fail("zs_step_host: %s", cudaGetErrorString(err)) : fail("zs_step_host: the records did not arrive");
+    }
+    // rows of overflowing envs: obs_dev is complete when the launch is (the caller reads them next)
+    if (n_over > 0) CU(cudaStreamSynchronize(st));
+    h->host_stats[0] += 1; h->host_stats[1] += us_launched; h->host_stats[2] += us_flag; h->host_stats[3] += us_since();
+    return 0;
+}
+
+// diagnostics: out[4] = zs_step_host calls since the last read, and the mean microseconds from entry until the launches were
+// issued / the flag showed (all records in host memory) / the call returned (all envs expanded)
+extern "C" __attribute__((visibility("default"))) int zs_step_host_stats(ZsHandle* h, double* out) {
+    if (!h || !out) return fail("null argument");
+    const double n = h->host_stats[0] > 0 ? h->host_stats[0] : 1;
+    out[0] = h->host_stats[0];
+    for (int i = 1; i < 4; ++i) out[i] = h->host_stats[i] / n;
+    for (double& v : h->host_stats) v = 0;
     return 0;
 }
 

@@ -127,6 +127,12 @@ struct ZsIO {
     int32_t* draws;           // [n_steps, N] or NULL
     uint32_t* compact;        // [N, compact_words] compact observation records (zs_obs.cuh: obs_world_compact) or NULL
     int32_t compact_words;    // words per record: ZS_COMPACT_HEADER + entry words
+    // zs_step_host, records streamed to pinned HOST memory in groups of group_envs consecutive envs: the warp that completes a
+    // group raises that group's flag (host_flags + 16 * group, one cache line each) to `ticket` behind a system-scope fence
+    uint32_t* host_flags;     // or NULL
+    int32_t* group_count;     // device counters, zero between steps
+    int32_t group_envs;
+    uint32_t ticket;
     const uint8_t* env_mask;  // reset only
     int32_t n_steps;
     int64_t first_step;

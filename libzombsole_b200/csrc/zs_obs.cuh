@@ -172,6 +172,16 @@ ZS_TPL __device__ __forceinline__ void obs_world_patch(const ZsParams& p, Env& e
 // need no order; their positions come from ballot prefix sums (all rounds run on warp-level bounds: the primitives are
 // full-mask when two envs share a warp).  Returns true when the record cannot hold the env (too many entries, or a
 // value outside the entry's fields): the caller then writes the full row.  n_out: the entry count (0 on overflow).
+// The words are STAGED in the env's per-step scratch (EnvS: act / bk / draws, dead by now) and leave as coalesced rows at the end
+// (compact_flush): written to pinned host memory piece by piece as the rounds produce them they took 12 us longer to drain
+// over PCIe than the same bytes in 128-byte rows (profiles/r02_e2e_host_step.txt).  Words beyond the scratch go out directly.
+template <int MPC> __host__ __device__ constexpr int compact_stage_words() { return (int)(offsetof(EnvS<MPC>, zb) / sizeof(uint32_t)); }
+ZS_TPL __device__ __forceinline__ void compact_flush(Env& e, uint32_t* __restrict__ rec, int n_words) {
+    const uint32_t* const stage = reinterpret_cast<const uint32_t*>(zs_smem + e.b);  // (EnvS::act is the struct's first member)
+    const int n = n_words < compact_stage_words<MPC>() ? n_words : compact_stage_words<MPC>();
+    gsync<G, CV>(e);
+    for (int i = e.gl; i < n; i += G) rec[i] = stage[i];
+}
 ZS_TPL __device__ __forceinline__ bool obs_world_compact(const ZsParams& p, Env& e, uint32_t* __restrict__ rec, int cap_words, int& n_out) {
     ZS_CONSTS; ZS_VIEWS;
     const int lane = e.gl;
@@ -180,18 +190,20 @@ ZS_TPL __device__ __forceinline__ bool obs_world_compact(const ZsParams& p, Env&
     const int cap = simple ? cap_words : (cap_words >> 1);
     int n = 0;
     bool bad = false;
+    uint32_t* const stage = reinterpret_cast<uint32_t*>(&S.act[0]);
+    auto put = [&](int w, uint32_t v) { if (w < compact_stage_words<MPC>()) stage[w] = v; else rec[w] = v; };
     auto emit = [&](bool on, int cell, int v0, int v1, int v2) {
         const unsigned m = gballot<G, CV>(e, on);
         const int pos = n + __popc(m & below_l);
         if (on) {
             if (simple) {
                 bad |= (unsigned)v0 > 0xffffu;
-                if (pos < cap) rec[ZS_COMPACT_HEADER + pos] = (uint32_t)cell | ((uint32_t)v0 << 16);
+                if (pos < cap) put(ZS_COMPACT_HEADER + pos, (uint32_t)cell | ((uint32_t)v0 << 16));
             } else {
                 bad |= (unsigned)v0 > 0xffffu || (unsigned)v2 > 0xffffu || v1 < -32768 || v1 > 32767;
                 if (pos < cap) {
-                    rec[ZS_COMPACT_HEADER + 2 * pos] = (uint32_t)cell | ((uint32_t)v0 << 16);
-                    rec[ZS_COMPACT_HEADER + 2 * pos + 1] = ((uint32_t)v1 & 0xffffu) | ((uint32_t)v2 << 16);
+                    put(ZS_COMPACT_HEADER + 2 * pos, (uint32_t)cell | ((uint32_t)v0 << 16));
+                    put(ZS_COMPACT_HEADER + 2 * pos + 1, ((uint32_t)v1 & 0xffffu) | ((uint32_t)v2 << 16));
                 }
             }
         }

@@ -197,6 +197,60 @@ class ZsEngine(object):
                                        1 if first_call else 0, int(n_threads)))
         return overflow_host[:n_over.value]
 
+    def host_stepper(self, records, prev_host, obs_dev, obs_host, reward_host, term_host, trunc_host, overflow_host, n_threads=0):
+        """zs_step_host bound to one set of buffers: ``step(actions, fmt, first_call)`` runs one transition whose actions
+        come from host memory and whose records are written to pinned host memory by the kernel itself, the host
+        threads expanding each env as its record arrives.  Returns the envs whose rows must be fetched from ``obs_dev``, or None."""
+        words = int(records.shape[-1])
+        for name, t in (("records", records),):
+            if not (t.device.type == "cpu" and t.is_pinned()):
+                raise ValueError("%s must be pinned host memory" % name)
+        N = self.N
+        ptrs = (self._arg(records, torch.int32, N * words, "records"), self._host_arg(prev_host, torch.int32, N * words, "prev"), words,
+                self._arg(obs_dev, torch.int32, N * self.obs_elems, "obs_dev"),
+                self._host_arg(obs_host, torch.int32, N * self.obs_elems, "obs_host"),
+                self._host_arg(reward_host, torch.float64, N, "reward"), self._host_arg(term_host, self._FLAG_DTYPES, N, "terminated"),
+                self._host_arg(trunc_host, self._FLAG_DTYPES, N, "truncated"), self._host_arg(overflow_host, torch.int32, N, "overflow"))
+        n_over = C.c_int32(0)
+        n_over_p = C.addressof(n_over)
+        call, h, A, nthr = self.L.zs_step_host, self.h, self.A, int(n_threads)
+        keep = (records, prev_host, obs_dev, obs_host, reward_host, term_host, trunc_host, overflow_host, n_over)
+
+        current_stream, device = torch.cuda.current_stream, self.device
+
+        def raw(actions_ptr, fmt, first_call):
+            """(no checks: ``actions_ptr`` addresses N * A (* 3) int32 in host memory)"""
+            rc = call(h, actions_ptr, fmt, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6], ptrs[7], ptrs[8],
+                      n_over_p, 1 if first_call else 0, nthr, current_stream(device).cuda_stream)
+            if rc:
+                check(rc)
+            return overflow_host[:n_over.value] if n_over.value else None
+
+        def step(actions, fmt, first_call):
+            per = 3 if fmt == abi.ACTIONS_FULL else 1
+            if (not isinstance(actions, torch.Tensor) or actions.dtype != torch.int32 or actions.device.type != "cpu"
+                    or not actions.is_contiguous() or actions.numel() < N * A * per):
+                raise ValueError("actions must be a contiguous int32 host tensor of %d elements" % (N * A * per))
+            return raw(actions.data_ptr(), fmt, first_call)
+        step.raw = raw
+        step.keep = keep
+        return step
+
+    def step_host_stats(self):
+        """(calls, mean us from entry to: launches issued, flag seen = records in host memory, return) since the last read."""
+        out = (C.c_double * 4)()
+        check(self.L.zs_step_host_stats(self.h, out))
+        return tuple(out)
+
+    def _host_arg(self, t, dtypes, numel, name):
+        """Pointer of a HOST tensor argument (read or written by the library's host threads)."""
+        if not isinstance(dtypes, tuple):
+            dtypes = (dtypes,)
+        if not isinstance(t, torch.Tensor) or t.device.type != "cpu" or t.dtype not in dtypes or not t.is_contiguous() or t.numel() < numel:
+            raise ValueError("%s must be a contiguous host tensor of %s with at least %d elements" % (
+                name, " or ".join(str(d) for d in dtypes), numel))
+        return t.data_ptr()
+
     def encode_obs(self, obs):
         check(self.L.zs_encode_obs(self.h, self._arg(obs, torch.int32, self.N * self.obs_elems, "obs"), self._stream()))
         return obs

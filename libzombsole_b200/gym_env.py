@@ -90,8 +90,14 @@ class ZombsoleVectorEnv(object):
         # host_outputs="compact": the same host tensors, but what crosses PCIe every step is one small record per env
         # (the cells that differ from the map's pristine layer, the reward, the flags: about 0.5 KB instead of the
         # 5-16 KB observation row) which a threaded host routine of the library expands in place into the env's host
-        # observation tensor — byte-identical results (zs_step_compact / zs_expand_compact, include/zs_b200.h)
-        self.compact = host_outputs == "compact"
+        # observation tensor — byte-identical results.  "compact" is ONE library call per step: the kernel writes the pinned
+        # records itself and the host threads, already waiting, expand them the moment a flag kernel behind it says they
+        # are complete (zs_step_host); "compact-copy" is the same with explicit copies and a stream
+        # synchronisation between the stages (zs_step_compact / zs_expand_compact, include/zs_b200.h)
+        if isinstance(host_outputs, str) and host_outputs not in ("compact", "compact-copy"):
+            raise ValueError("host_outputs must be False, True, 'compact' or 'compact-copy'")
+        self.compact = host_outputs in ("compact", "compact-copy")
+        self.streamed = host_outputs == "compact"
         self.host_outputs = bool(host_outputs)
         self.host_threads = int(host_threads)
         if self.compact:
@@ -102,6 +108,8 @@ class ZombsoleVectorEnv(object):
             self._dev_obs = self.engine.new_obs()  # full rows of the rare envs a record cannot hold
             self._overflow = torch.zeros(num_envs, dtype=torch.int32)
             self.compact_overflows = 0
+            self._act_pin = torch.zeros((num_envs, 1), dtype=torch.int32).pin_memory()
+            self._actions_pin = torch.zeros((num_envs, 1, 3), dtype=torch.int32).pin_memory()
             self._size_records(int(compact_words) if compact_words else words)
         elif self.host_outputs:
             self.obs, self.reward, self._term, self._trunc = self.engine.new_host_outputs()
@@ -160,6 +168,8 @@ class ZombsoleVectorEnv(object):
     def step(self, actions):
         """One transition of every world (gym_env.py:99-145).  The returned tensors are the env's own
         output buffers: they are overwritten by the next call."""
+        if self.compact and self.streamed:
+            return self._step_streamed(actions)
         a, fmt = self._stage_actions(actions)
         if self.compact:
             return self._step_compact(a, fmt)
@@ -175,11 +185,64 @@ class ZombsoleVectorEnv(object):
         """(Re)allocate the record buffers: ``words`` 32-bit words per env (header + entries)."""
         words = min(int(words), self.engine.compact_max_words())
         self.compact_words = words
-        self._records = torch.zeros((self.num_envs, words), dtype=torch.int32, device=self.device)
         self._records_host = torch.zeros((self.num_envs, words), dtype=torch.int32).pin_memory()
         self._records_prev = torch.zeros((self.num_envs, words), dtype=torch.int32)
         self._compact_first = True
         self._overflows_since_resize = 0
+        if self.streamed:
+            torch.cuda.current_stream(self.device).synchronize()  # (nothing in flight still writes the old records)
+            self._host_step = self.engine.host_stepper(self._records_host, self._records_prev, self._dev_obs, self.obs, self.reward,
+                                                       self._term, self._trunc, self._overflow, self.host_threads)
+            self._host_step_raw = self._host_step.raw
+            # (what step() returns never changes: the env's own buffers, the flag bytes as bool views)
+            self._step_result = (self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool))
+        else:
+            self._records = torch.zeros((self.num_envs, words), dtype=torch.int32, device=self.device)
+
+    def _step_streamed(self, actions):
+        """host_outputs="compact": the actions go over from host memory as they are, the kernel writes the pinned records in
+        place (zs_step_host)."""
+        N = self.num_envs
+        if isinstance(actions, torch.Tensor) and actions.dtype == torch.int32 and actions.device.type == "cpu" \
+                and actions.is_contiguous() and actions.numel() in (N, 3 * N):
+            a = actions  # the caller's own buffer, in place: it is free again when step() returns
+        elif isinstance(actions, (list, tuple)) and len(actions) and isinstance(actions[0], dict):
+            a = self._actions_pin
+            a.copy_(torch.from_numpy(np.array([encode_action(x) for x in actions], dtype=np.int32).reshape(N, 1, 3)))
+        else:
+            t = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+            if t.numel() == N:
+                a = self._act_pin
+            elif t.numel() == 3 * N:
+                a = self._actions_pin
+            else:
+                raise ValueError("actions must hold %d discrete ids or %d (type, dx, dy) rows" % (N, N))
+            a.copy_(t.reshape(a.shape))  # (any dtype / device: converted into the env's pinned buffer)
+        over = self._host_step_raw(a.data_ptr(), abi.ACTIONS_DISCRETE if a.numel() == N else abi.ACTIONS_FULL, self._compact_first)
+        self._compact_first = False
+        if over is not None:
+            self._fetch_overflow_rows(over)
+        return self._step_result + ({},)
+
+    def _fetch_overflow_rows(self, over):
+        """Rare: more differing cells than a record holds — those rows come over as they are."""
+        stream = torch.cuda.current_stream(self.device)
+        stream.synchronize()
+        self.compact_overflows += len(over)
+        if len(over) > 16:  # many: one gather on the device, one copy
+            idx = over.to(self.device, dtype=torch.long)
+            self.obs[over.long()] = self._dev_obs[idx].cpu()
+        else:
+            for e in over.tolist():
+                self.obs[e].copy_(self._dev_obs[e], non_blocking=True)
+            stream.synchronize()
+        # box/wall damage persists across episodes, so the differing cells of long-running envs creep up: when more
+        # than one env in 64 no longer fits, or full rows keep being fetched, the records double (up to the size nothing
+        # can overflow)
+        self._overflows_since_resize += len(over)
+        if ((len(over) * 64 > self.num_envs or self._overflows_since_resize > 64)
+                and self.compact_words < self.engine.compact_max_words()):
+            self._size_records(2 * self.compact_words)
 
     def _step_compact(self, a, fmt):
         eng = self.engine
@@ -191,22 +254,8 @@ class ZombsoleVectorEnv(object):
         over = eng.expand_compact(self._records_host, self._records_prev, self.obs, self.reward, self._term, self._trunc,
                                   self._overflow, self._compact_first, self.host_threads)
         self._compact_first = False
-        if len(over):  # rare: more differing cells than a record holds — fetch those rows as they are
-            self.compact_overflows += len(over)
-            if len(over) > 16:  # many: one gather on the device, one copy
-                idx = over.to(self.device, dtype=torch.long)
-                self.obs[over.long()] = self._dev_obs[idx].cpu()
-            else:
-                for e in over.tolist():
-                    self.obs[e].copy_(self._dev_obs[e], non_blocking=True)
-                stream.synchronize()
-            # box/wall damage persists across episodes, so the differing cells of long-running envs creep up: when more
-            # than one env in 64 no longer fits, or full rows keep being fetched, the records double (up to the size nothing
-            # can overflow)
-            self._overflows_since_resize += len(over)
-            if ((len(over) * 64 > self.num_envs or self._overflows_since_resize > 64)
-                    and self.compact_words < eng.compact_max_words()):
-                self._size_records(2 * self.compact_words)
+        if len(over):
+            self._fetch_overflow_rows(over)
         return self.obs, self.reward, self._term.view(torch.bool), self._trunc.view(torch.bool), {}
 
     def reset(self, seed=None, options=None, mask=None):

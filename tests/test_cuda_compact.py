@@ -2,7 +2,9 @@
 pristine layer, reward, flags); a threaded host routine of the library expands the records into the reference's
 observation tensor.  The result must be byte-identical to the device tensors of a plain env on the same inputs, step
 after step (the expansion is incremental: it undoes the previous record's cells), across auto-resets, masked resets,
-and for envs whose differing cells do not fit a record (overflow: the full row is fetched)."""
+and for envs whose differing cells do not fit a record (overflow: the full row is fetched).  Both flavours: "compact"
+(zs_step_host: the records in pinned host memory, written by the kernel in place, every env expanded as its record
+arrives) and "compact-copy" (zs_step_compact, copies, zs_expand_compact)."""
 import numpy as np
 import pytest
 import torch
@@ -15,11 +17,15 @@ KW = dict(rules_name="extermination", player_names=["terminator", "terminator"],
           initial_zombies=10, minimum_zombies=0, observation_scope="world", agent_weapon="rifle")
 
 
+MODES = ["compact", "compact-copy"]
+
+
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("enc,N,threads", [("simple", 4096, 0), ("simple", 333, 3), ("channels", 1024, 0)])
-def test_compact_outputs_equal_device_outputs(enc, N, threads):
+def test_compact_outputs_equal_device_outputs(enc, N, threads, mode):
     plain = ZombsoleVectorEnv(num_envs=N, seed=9, max_episode_steps=30, observation_position_encoding=enc, **KW)
     comp = ZombsoleVectorEnv(num_envs=N, seed=9, max_episode_steps=30, observation_position_encoding=enc,
-                             host_outputs="compact", host_threads=threads, **KW)
+                             host_outputs=mode, host_threads=threads, **KW)
     o0, _ = plain.reset()
     c0, _ = comp.reset()
     assert torch.equal(o0.cpu(), c0)
@@ -45,11 +51,12 @@ def test_compact_outputs_equal_device_outputs(enc, N, threads):
     comp.close()
 
 
-def test_compact_overflow_fetches_the_full_row():
+@pytest.mark.parametrize("mode", MODES)
+def test_compact_overflow_fetches_the_full_row(mode):
     """More differing cells than a record holds (here: 150 damaged walls in some envs): those envs come over as full rows."""
     N = 64
     plain = ZombsoleVectorEnv(num_envs=N, seed=2, **KW)
-    comp = ZombsoleVectorEnv(num_envs=N, seed=2, host_outputs="compact", **KW)
+    comp = ZombsoleVectorEnv(num_envs=N, seed=2, host_outputs=mode, **KW)
     for env in (plain, comp):
         sl = env.engine.fields["static_life"]
         sl[::5, :150] = torch.where(sl[::5, :150] == 200, torch.full_like(sl[::5, :150], 55), sl[::5, :150])
@@ -68,12 +75,13 @@ def test_compact_overflow_fetches_the_full_row():
     comp.close()
 
 
-def test_compact_overflow_without_growth():
+@pytest.mark.parametrize("mode", MODES)
+def test_compact_overflow_without_growth(mode):
     """Records at the size nothing can grow beyond... here held small on purpose: a few envs overflow on every step and
     come over as full rows each time (few enough not to trigger the growth)."""
     N = 256
     plain = ZombsoleVectorEnv(num_envs=N, seed=4, **KW)
-    comp = ZombsoleVectorEnv(num_envs=N, seed=4, host_outputs="compact", compact_words=48, **KW)
+    comp = ZombsoleVectorEnv(num_envs=N, seed=4, host_outputs=mode, compact_words=48, **KW)
     for env in (plain, comp):
         sl = env.engine.fields["static_life"]
         sl[7, :60] = 77
@@ -94,3 +102,33 @@ def test_compact_overflow_without_growth():
 def test_compact_needs_a_world_observation():
     with pytest.raises(ValueError):
         ZombsoleVectorEnv(num_envs=8, host_outputs="compact", **dict(KW, observation_scope="surroundings:11"))
+
+
+def test_streamed_step_takes_any_action_container():
+    """host_outputs="compact" takes an int32 host tensor as it is; everything else (device tensors, numpy arrays, int64,
+    lists of reference action dicts) goes through the env's own pinned buffer — the same transition either way."""
+    N = 96
+    envs = [ZombsoleVectorEnv(num_envs=N, seed=11, host_outputs="compact", **KW) for _ in range(5)]
+    plain = ZombsoleVectorEnv(num_envs=N, seed=11, **KW)
+    rs = np.random.RandomState(3)
+    for t in range(15):
+        ids = rs.randint(0, 6, size=N)
+        a32 = torch.from_numpy(ids.astype(np.int32))
+        o, r, te, tr, _ = plain.step(a32.cuda())
+        outs = [envs[0].step(a32.pin_memory()), envs[1].step(a32.cuda()), envs[2].step(ids.astype(np.int64)),
+                envs[3].step([ZombsoleVectorEnv.game_actions[i] for i in ids]), envs[4].step(a32)]
+        for co, cr, cte, ctr, _ in outs:
+            assert torch.equal(o.cpu(), co) and torch.equal(r.cpu().view(torch.int64), cr.view(torch.int64))
+            assert torch.equal(te.cpu(), cte) and torch.equal(tr.cpu(), ctr)
+    for e in envs + [plain]:
+        e.close()
+
+
+def test_step_host_rejects_pageable_buffers():
+    env = ZombsoleVectorEnv(num_envs=32, seed=1, host_outputs="compact", **KW)
+    with pytest.raises(ValueError):
+        env._host_step(torch.zeros((32, 1), dtype=torch.int64), 1, True)  # not int32
+    with pytest.raises(ValueError):  # records the device cannot reach
+        env.engine.host_stepper(torch.zeros((32, env.compact_words), dtype=torch.int32), env._records_prev, env._dev_obs, env.obs,
+                                env.reward, env._term, env._trunc, env._overflow)
+    env.close()
