@@ -428,8 +428,10 @@ def run_ours(args, rank, world, local_rank):
     e2e_host_ms = max_over_ranks(max(ev[0].elapsed_time(ev[1]), e2e_host_wall_ms))
     env_h.close()
 
-    # compact host outputs: one small record per env crosses PCIe (the cells that differ from the map's pristine layer,
-    # reward, flags); the library's threaded host routine expands it into the same pinned host observation tensor
+    # compact host outputs (zs_step_host, ONE library call per step): the actions go over with the copy engine, the kernel
+    # writes one small record per env (the cells that differ from the map's pristine layer, reward, flags) straight into
+    # pinned host memory and raises a flag there; the library's host threads, already waiting, expand the records into
+    # the host observation tensor
     threads_per_rank = max(1, host_threads() // max(1, world))
     env_c = ZombsoleVectorEnv(num_envs=N, device=dev, seed=args.seed, env_index_base=rank * N, max_episode_steps=1000,
                               auto_reset=True, host_outputs="compact", host_threads=threads_per_rank, **ENV_KW)
@@ -443,7 +445,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     e2e_compact_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_compact_ms = max_over_ranks(e2e_compact_wall_ms)  # (host work is part of the step: wall clock, max over ranks)
-    compact_bytes = env_c._records.numel() * 4
+    # what the kernel wrote to host memory in the last step: header + entries of every record (the unused rest of a record stays put)
+    wpe = 1 if env_c.engine.obs_shape[0] == 1 else 2
+    compact_bytes = int((env_c._records_host[:, 0] & 0xffff).sum().item()) * 4 * wpe + N * 16
+    compact_buffer_bytes = env_c._records_host.numel() * 4
     compact_overflows = env_c.compact_overflows
     env_c.close()
     e2e_ms = min(e2e_copy_ms, e2e_host_ms, e2e_compact_ms)
@@ -495,13 +500,15 @@ def run_ours(args, rank, world, local_rank):
                     "h2d_bytes_per_step": N * 4,
                     "d2h_bytes_per_step": compact_bytes if e2e_best == "compact" else obs_bytes + N * 8 + 2 * N,
                     "api": {"compact": "ZombsoleVectorEnv(host_outputs='compact').step(pinned host actions) -> host int32 obs "
-                                       "(N,1,12,111) / float64 reward / flags: one 512-byte record per env copied device->host, "
-                                       "expanded in place by the library's host routine on %d threads; timed by the host "
-                                       "clock around the loop" % threads_per_rank,
+                                       "(N,1,12,111) / float64 reward / flags: one zs_step_host call per step — actions to the device by the "
+                                       "copy engine, one record per env (header + the cells that differ) written by the kernel straight "
+                                       "into pinned host memory, expanded in place by the library's host routine on %d threads; "
+                                       "timed by the host clock around the loop" % threads_per_rank,
                             "host": "ZombsoleVectorEnv(host_outputs=True).step(pinned host actions) -> pinned host obs/reward/flags "
                                     "written by the kernel over PCIe (zero-copy), stream synchronised before step() returns",
                             "copy": "ZombsoleVectorEnv.step(pinned host actions) + obs/reward/flags copied to pinned host"}[e2e_best],
                     "compact_variant": {"value": total_envs * Ke / (e2e_compact_ms * 1e-3), "d2h_bytes_per_step": compact_bytes,
+                                        "record_buffer_bytes": compact_buffer_bytes,
                                         "host_threads": threads_per_rank, "rows_fetched_in_full": compact_overflows},
                     "copy_variant": {"value": total_envs * Ke / (e2e_copy_ms * 1e-3), "d2h_bytes_per_step": obs_bytes + N * 8 + 2 * N,
                                      "api": "ZombsoleVectorEnv.step(pinned host actions) + obs/reward/flags copied to pinned host"},
