@@ -262,7 +262,8 @@ int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t*
  * ahead of the launch.  The kernel writes `compact_pinned` (uint32 [N, compact_words]) in place — it must be page-locked
  * host memory the device can address (cudaHostAlloc / cudaHostRegister / torch pin_memory) — as coalesced rows, and the
  * warp that completes the batch raises a flag in pinned memory behind one system-scope fence; n_threads host threads,
- * already spinning on that flag inside their parallel region, expand the records into obs_host / reward_host / terminated_host / truncated_host (ordinary
+ * which have meanwhile put the cells of the previous records back to the pristine layer and are spinning on that flag
+ * inside their parallel region, expand the records into obs_host / reward_host / terminated_host / truncated_host (ordinary
  * host memory, as for zs_expand_compact) the moment it shows.  No device-to-host copy, no stream synchronisation and no
  * thread wake-up are on the way of a step; when the call returns every env has been expanded, the action buffer is the
  * caller's again, and obs_dev holds the rows of the envs listed in overflow_envs_host (as for zs_expand_compact; the
@@ -273,8 +274,9 @@ int zs_step_host(ZsHandle* h, const int32_t* actions_host, int32_t action_format
                  uint32_t* prev_host, int32_t compact_words, int32_t* obs_dev, int32_t* obs_host, double* reward_host,
                  uint8_t* terminated_host, uint8_t* truncated_host, int32_t* overflow_envs_host, int32_t* n_overflow,
                  int32_t first_call, int32_t n_threads, void* stream);
-/* diagnostics: out[4] = zs_step_host calls since the last read, and the mean microseconds from entry until the launches
- * were issued / the flag showed (every record in host memory) / the call returned (every env expanded) */
+/* diagnostics: out[5] = zs_step_host calls since the last read, and the mean microseconds from entry until the launches
+ * were issued / thread 0 had restored the cells of its previous records / the flag showed (every record in host memory) /
+ * the call returned (every env expanded) */
 int zs_step_host_stats(ZsHandle* h, double* out);
 
 /* actions_dev int32 [N, A]: uniform discrete ids for step `step_index` (Philox action stream). */

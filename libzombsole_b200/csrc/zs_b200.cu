@@ -594,7 +594,7 @@ struct ZsHandle {
     int32_t* host_group_count = nullptr;     // device: envs of each group done in this step
     int host_groups = 0;
     const void* host_records_checked = nullptr;
-    double host_stats[4] = {0, 0, 0, 0};  // zs_step_host: calls, and summed us from entry to: launched / flag seen / return
+    double host_stats[5] = {0, 0, 0, 0, 0};  // zs_step_host: calls, and summed us from entry to: launched / previous cells restored / flag seen / return
     std::vector<int32_t> tmpl_obs_host;  // the pristine observation planes [obs_C][cells] (zs_expand_compact)
     int tmpl_single_step;  // launches of fewer than four steps stage the observation template for the TMA as well
     bool img_valid;  // the parked images (ZsParams::img) match the canonical state of every env
@@ -1246,26 +1246,30 @@ struct ExpandCtx {
     bool first_call;
     int32_t* obs; double* reward; uint8_t* terminated; uint8_t* truncated;
 };
-static inline bool expand_one(const ExpandCtx& cx, int e, const uint32_t* r, uint32_t* pv) {
+// The two halves of an env's expansion.  expand_restore needs the PREVIOUS record only: the cells it patched go back to the
+// pristine value (the whole row when there is no usable previous record) — zs_step_host runs it while the device is still
+// working on the step.  expand_write applies the new record.
+static inline void expand_restore(const ExpandCtx& cx, int e, const uint32_t* pv) {
     const int cells = cx.cells, C = cx.C, wpe = cx.wpe;
     const int32_t* T = cx.T;
     const size_t row = (size_t)C * cells;
     int32_t* o = cx.obs + (size_t)e * row;
+    if (cx.first_call || ((pv[0] >> 18) & 1u)) { memcpy(o, T, row * sizeof(int32_t)); return; }
+    const int pn = (int)(pv[0] & 0xffffu);
+    for (int i = 0; i < pn; ++i) {
+        const int cell = (int)(pv[ZS_COMPACT_HEADER + i * wpe] & 0xffffu);
+        for (int c = 0; c < C; ++c) o[(size_t)c * cells + cell] = T[(size_t)c * cells + cell];
+    }
+}
+static inline bool expand_write(const ExpandCtx& cx, int e, const uint32_t* r, uint32_t* pv) {
+    const int cells = cx.cells, wpe = cx.wpe;
+    int32_t* o = cx.obs + (size_t)e * cx.C * cells;
     const uint32_t h0 = r[0];
     const int n = (int)(h0 & 0xffffu);
     if (cx.terminated) cx.terminated[e] = (uint8_t)((h0 >> 16) & 1u);
     if (cx.truncated) cx.truncated[e] = (uint8_t)((h0 >> 17) & 1u);
     if (cx.reward) memcpy(cx.reward + e, r + 2, sizeof(double));
-    const bool prev_unknown = cx.first_call || ((pv[0] >> 18) & 1u);
-    if ((h0 >> 18) & 1u) { pv[0] = h0; return true; }
-    if (prev_unknown) memcpy(o, T, row * sizeof(int32_t));
-    else {
-        const int pn = (int)(pv[0] & 0xffffu);
-        for (int i = 0; i < pn; ++i) {
-            const int cell = (int)(pv[ZS_COMPACT_HEADER + i * wpe] & 0xffffu);
-            for (int c = 0; c < C; ++c) o[(size_t)c * cells + cell] = T[(size_t)c * cells + cell];
-        }
-    }
+    if ((h0 >> 18) & 1u) { pv[0] = h0; return true; }  // the record could not hold this env: the caller copies its row from the device
     if (wpe == 1) {
         for (int i = 0; i < n; ++i) { const uint32_t w = r[ZS_COMPACT_HEADER + i]; o[w & 0xffffu] = (int32_t)(w >> 16); }
     } else {
@@ -1279,6 +1283,10 @@ static inline bool expand_one(const ExpandCtx& cx, int e, const uint32_t* r, uin
     }
     memcpy(pv, r, (size_t)(ZS_COMPACT_HEADER + n * wpe) * sizeof(uint32_t));
     return false;
+}
+static inline bool expand_one(const ExpandCtx& cx, int e, const uint32_t* r, uint32_t* pv) {
+    if (!((r[0] >> 18) & 1u)) expand_restore(cx, e, pv);
+    return expand_write(cx, e, r, pv);
 }
 
 // HOST code: records -> the reference's observation tensor (include/zs_b200.h).  Incremental: the cells the previous
@@ -1382,7 +1390,7 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
     if (groups <= 0) { zs_host_flag_kernel<<<1, 1, 0, st>>>(h->host_flag, ticket); h->launches++; }
     if (int rc = launched(h)) return rc;
     const double us_launched = us_since();
-    double us_flag = 0;
+    double us_flag = 0, us_restored = 0;
     n_threads = host_threads(n_threads, N);
     const ExpandCtx cx{h->tmpl_obs_host.data(), h->p.cells, h->p.obs_C, h->p.obs_enc == ZS_OBS_SIMPLE ? 1 : 2, words, first_call != 0,
                        obs_host, reward_host, terminated_host, truncated_host};
@@ -1395,6 +1403,14 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
         // group as the group arrives, while the records of later groups are still on their way
         // (shares cut by hand: a thread that gave up must not leave the others stuck in a work-sharing construct)
         const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
+        // while the device works on the step: what the previous records patched goes back to the pristine layer (half of an
+        // expansion's stores need nothing from the new records)
+        for (int g = 0; g < n_flags; ++g) {
+            const int g0 = g * group_envs, gn = (g0 + group_envs < N ? g0 + group_envs : N) - g0;
+            const int e0 = g0 + (int)((long long)gn * tid / nt), e1 = g0 + (int)((long long)gn * (tid + 1) / nt);
+            for (int e = e0; e < e1; ++e) expand_restore(cx, e, prev_host + (size_t)e * words);
+        }
+        if (tid == 0) us_restored = us_since();
         struct timespec t0;
         clock_gettime(CLOCK_MONOTONIC, &t0);
         for (int g = 0; g < n_flags; ++g) {
@@ -1417,7 +1433,7 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
             const int g0 = g * group_envs, gn = (g0 + group_envs < N ? g0 + group_envs : N) - g0;
             const int e0 = g0 + (int)((long long)gn * tid / nt), e1 = g0 + (int)((long long)gn * (tid + 1) / nt);
             for (int e = e0; e < e1; ++e) {
-                if (expand_one(cx, e, compact_pinned + (size_t)e * words, prev_host + (size_t)e * words)) {
+                if (expand_write(cx, e, compact_pinned + (size_t)e * words, prev_host + (size_t)e * words)) {
                     int at;
 #pragma omp atomic capture
                     at = n_over++;
@@ -1433,17 +1449,17 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
     }
     // rows of overflowing envs: obs_dev is complete when the launch is (the caller reads them next)
     if (n_over > 0) CU(cudaStreamSynchronize(st));
-    h->host_stats[0] += 1; h->host_stats[1] += us_launched; h->host_stats[2] += us_flag; h->host_stats[3] += us_since();
+    h->host_stats[0] += 1; h->host_stats[1] += us_launched; h->host_stats[2] += us_restored; h->host_stats[3] += us_flag; h->host_stats[4] += us_since();
     return 0;
 }
 
-// diagnostics: out[4] = zs_step_host calls since the last read, and the mean microseconds from entry until the launches were
-// issued / the flag showed (all records in host memory) / the call returned (all envs expanded)
+// diagnostics: out[5] = zs_step_host calls since the last read, and the mean microseconds from entry until the launches were
+// issued / thread 0 had restored its previous cells / the flag showed (all records in host memory) / the call returned
 extern "C" __attribute__((visibility("default"))) int zs_step_host_stats(ZsHandle* h, double* out) {
     if (!h || !out) return fail("null argument");
     const double n = h->host_stats[0] > 0 ? h->host_stats[0] : 1;
     out[0] = h->host_stats[0];
-    for (int i = 1; i < 4; ++i) out[i] = h->host_stats[i] / n;
+    for (int i = 1; i < 5; ++i) out[i] = h->host_stats[i] / n;
     for (double& v : h->host_stats) v = 0;
     return 0;
 }

@@ -237,8 +237,9 @@ class ZsEngine(object):
         return step
 
     def step_host_stats(self):
-        """(calls, mean us from entry to: launches issued, flag seen = records in host memory, return) since the last read."""
-        out = (C.c_double * 4)()
+        """(calls, mean us from entry to: launches issued, previous cells restored, flag seen = records in host memory,
+        return) since the last read."""
+        out = (C.c_double * 5)()
         check(self.L.zs_step_host_stats(self.h, out))
         return tuple(out)
 

@@ -25,7 +25,7 @@ if streamed:
     for s in range(300):
         env.step(acts[50 + s])
     dt = time.perf_counter() - t0
-    print("   inside zs_step_host: calls %d, mean us from entry to launches issued %.1f / flag seen %.1f / return %.1f"
+    print("   inside zs_step_host: calls %d, mean us from entry to launches issued %.1f / previous cells restored %.1f / flag seen %.1f / return %.1f"
           % env.engine.step_host_stats())
     print("streamed threads", threads, "%.1f us per step -> %.3e env-steps/s" % (dt / 300 * 1e6, N * 300 / dt))
     env.close()

@@ -24,7 +24,7 @@ for s in range(100, 160):
         pass
     env.step(acts[s])
 torch.cuda.synchronize()
-print("host side: calls %d, mean us from entry to launches issued %.1f / flag seen %.1f / return %.1f"
+print("host side: calls %d, mean us from entry to launches issued %.1f / previous cells restored %.1f / flag seen %.1f / return %.1f"
       % env.engine.step_host_stats())
 t = grab(L)
 t = t[t[:, 0] > 0].astype(np.int64)
