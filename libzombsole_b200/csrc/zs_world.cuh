@@ -1259,11 +1259,12 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
             // The scripted actors decide with as little divergence as possible: the lanes of a warp are zombies, terminators
             // and others side by side, and every branch one kind takes is issued for the whole warp.
             // the four adjacent cells: how far they are from the target, which are free, which hold a box/wall
-            int dd[4];
+            // (with e = target - self, the squared distance from the cell at (0,+1), (0,-1), (+1,0), (-1,0) is |e|^2 + 1 plus
+            // -2ey, +2ey, -2ex, +2ex: the order of the four, ties included, is the order of these)
+            const int dd[4] = {y - gy, gy - y, x - gx, gx - x};
             unsigned staticmask = 0;
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
-                dd[d] = dist2(gx, gy, x + adj_dx(d), y + adj_dy(d));
                 if (!g_is_thing(gs[d])) freemask |= 1u << d;
                 if (g_is_static(gs[d])) staticmask |= 1u << d;
             }
@@ -1298,21 +1299,23 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
                 type = attack_tg ? D_ATTACK : heal_self ? D_HEAL : wander ? D_WANDER : bkind == ZS_KIND_RANDOMAN ? D_RANDOM : D_IDLE;
                 a = attack_tg ? tg : heal_self ? s : 0;
             }
-        } else {  // Agent.next_step (players/agent.py:28-96)
-            // (a step of two cells or more fails whatever its length, core.py:149-153: clamped, so nothing can overflow)
-            if (at == ZS_ACT_MOVE) { type = D_MOVE; a = x + max(-2, min(2, adx)); b = y + max(-2, min(2, ady)); }
-            else if (at == ZS_ACT_ATTACK_CLOSEST) { if (tg >= 0) { type = D_ATTACK; a = tg; } }
-            else if (at == ZS_ACT_HEAL_CLOSEST) { type = D_HEAL; a = tg >= 0 ? tg : s; }
-            else if (at == ZS_ACT_ATTACK || at == ZS_ACT_HEAL) {
-                if (at == ZS_ACT_HEAL && adx == 0 && ady == 0) { type = D_HEAL; a = s; }
-                else {
-                    adx = max(-4096, min(4096, adx)); ady = max(-4096, min(4096, ady));  // (off the map either way)
-                    const int g = grid_at(p, GRIDP, x + adx, y + ady);
-                    // attack: any thing; heal: Player / Box / Wall only (agent.py:69-75)
-                    const bool ok = at == ZS_ACT_ATTACK ? g_is_thing(g)
-                                                        : (g_is_static(g) || (g_is_thing(g) && (g - 1) < NP));
-                    if (ok) { type = at == ZS_ACT_ATTACK ? D_ATTACK : D_HEAL; a = target_of_cell(p, g, (y + ady) * p.W + (x + adx)); }
-                }
+        }
+        // Agent.next_step (players/agent.py:28-96), by selects: `at` is ZS_ACT_NONE in every lane that is not a live agent, so
+        // the two or so agent lanes of a warp do not cost the others a divergent branch
+        // (a step of two cells or more fails whatever its length, core.py:149-153: clamped, so nothing can overflow)
+        {
+            const bool mv = at == ZS_ACT_MOVE, ac = at == ZS_ACT_ATTACK_CLOSEST && tg >= 0, hc = at == ZS_ACT_HEAL_CLOSEST;
+            const bool hs = at == ZS_ACT_HEAL && adx == 0 && ady == 0;
+            type = mv ? D_MOVE : ac ? D_ATTACK : (hc || hs) ? D_HEAL : type;
+            a = mv ? x + max(-2, min(2, adx)) : (ac || (hc && tg >= 0)) ? tg : (hc || hs) ? s : a;
+            b = mv ? y + max(-2, min(2, ady)) : b;
+            if (at == ZS_ACT_ATTACK || (at == ZS_ACT_HEAL && !hs)) {  // a target named by its offset: rare
+                adx = max(-4096, min(4096, adx)); ady = max(-4096, min(4096, ady));  // (off the map either way)
+                const int g = grid_at(p, GRIDP, x + adx, y + ady);
+                // attack: any thing; heal: Player / Box / Wall only (agent.py:69-75)
+                const bool ok = at == ZS_ACT_ATTACK ? g_is_thing(g)
+                                                    : (g_is_static(g) || (g_is_thing(g) && (g - 1) < NP));
+                if (ok) { type = at == ZS_ACT_ATTACK ? D_ATTACK : D_HEAL; a = target_of_cell(p, g, (y + ady) * p.W + (x + adx)); }
             }
         }
     }
