@@ -1215,28 +1215,29 @@ ZS_TPL __device__ __forceinline__ int world_step_one(const ZsParams& p, Env& e, 
     {
         // (0,+1), (0,-1), (+1,0), (-1,0) from ONE cell index: a thing in the world stands inside the map, so a neighbour is
         // outside exactly at the map's edges — four compares instead of a bounds check per neighbour
-        const bool look = live && !agent;
+        // (every lane reads: a lane without a thing in the world stands at (0, 0), inside the map; only the scripted actors use the result)
         const int c0 = y * p.W + x;
-        gs[0] = !look ? (unsigned)G_STATIC : (y + 1 < p.H ? (unsigned)GRIDP[c0 + p.W] : (unsigned)G_EMPTY);
-        gs[1] = !look ? (unsigned)G_STATIC : (y > 0 ? (unsigned)GRIDP[c0 - p.W] : (unsigned)G_EMPTY);
-        gs[2] = !look ? (unsigned)G_STATIC : (x + 1 < p.W ? (unsigned)GRIDP[c0 + 1] : (unsigned)G_EMPTY);
-        gs[3] = !look ? (unsigned)G_STATIC : (x > 0 ? (unsigned)GRIDP[c0 - 1] : (unsigned)G_EMPTY);
+        gs[0] = y + 1 < p.H ? (unsigned)GRIDP[c0 + p.W] : (unsigned)G_EMPTY;
+        gs[1] = y > 0 ? (unsigned)GRIDP[c0 - p.W] : (unsigned)G_EMPTY;
+        gs[2] = x + 1 < p.W ? (unsigned)GRIDP[c0 + 1] : (unsigned)G_EMPTY;
+        gs[3] = x > 0 ? (unsigned)GRIDP[c0 - 1] : (unsigned)G_EMPTY;
     }
     const int my_tm = in_cap ? (int)TM(s) : 0;
-    const bool has_humans = gany<G, CV>(e, live && !zombie);
+    bool has_humans = false;  // any player (bot or agent) in the world: every lane sees all of them in the pass below
 
     // ---- closest(self, others) (utils.py:23-31) for everybody from ONE pass over the (thing, player) distances:
     // a zombie (things.py:73-82) or a heal_closest agent (agent.py:79-86) takes the minimum over the players in its
     // own lane; a player's closest zombie is the minimum of the same distances across the zombie lanes (redux.sync)
     // and lands in the player's lane.  Key = (d^2 << 8) | dict rank: sorted() is stable, ties go to the earlier thing.
-    const bool wantp = live && (zombie || at == ZS_ACT_HEAL_CLOSEST);
+    // (bestp is only read by a live zombie or heal_closest agent)
     const uint32_t zkey = (live && zombie) ? rk : 0xffffffffu;
     uint32_t bestp = 0xffffffffu, zb = 0xffffffffu;
     auto one_player = [&](int q) {
         const uint32_t rq = RK(q), qxy = TXY(q);
         const bool hq = rq != RK_NONE;  // player q is in the world
         const uint32_t d = (uint32_t)dist2(x, y, xy_x(qxy), xy_y(qxy)) << 8;
-        if (hq && wantp && q != s) bestp = min(bestp, d | rq);
+        has_humans |= hq;
+        if (hq && q != s) bestp = min(bestp, d | rq);
         const uint32_t m = gminu<G, CV>(e, hq ? (d | zkey) : 0xffffffffu);
         if (q == s) zb = m;
     };
