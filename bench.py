@@ -432,7 +432,7 @@ def run_ours(args, rank, world, local_rank):
     # writes one small record per env (the cells that differ from the map's pristine layer, reward, flags) straight into
     # pinned host memory and raises a flag there; the library's host threads, already waiting, expand the records into
     # the host observation tensor
-    threads_per_rank = max(1, host_threads() // max(1, world))
+    threads_per_rank = args.host_threads if args.host_threads > 0 else max(1, host_threads() // max(1, world))
     env_c = ZombsoleVectorEnv(num_envs=N, device=dev, seed=args.seed, env_index_base=rank * N, max_episode_steps=1000,
                               auto_reset=True, host_outputs="compact", host_threads=threads_per_rank, **ENV_KW)
     for s in range(W):
@@ -541,6 +541,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=300)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=0,
+                    help="host threads per rank for the end-to-end step (0 = this rank's share of the box's CPUs)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))

@@ -19,6 +19,9 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# (torch.cuda.current_stream() builds a Stream object per call: 1.5 us on the step path; the raw accessor is 0.2 us)
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
 class ZsEngine(object):
     def __init__(self, cfg, map_, device="cuda"):
         if not torch.cuda.is_available():
@@ -68,6 +71,9 @@ class ZsEngine(object):
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
+        """The caller's current stream on this engine's device, as the raw handle the C ABI takes."""
+        if _RAW_STREAM is not None:
+            return _RAW_STREAM(self.device.index)
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def state_written(self):
@@ -216,12 +222,12 @@ class ZsEngine(object):
         call, h, A, nthr = self.L.zs_step_host, self.h, self.A, int(n_threads)
         keep = (records, prev_host, obs_dev, obs_host, reward_host, term_host, trunc_host, overflow_host, n_over)
 
-        current_stream, device = torch.cuda.current_stream, self.device
+        stream_of = self._stream
 
         def raw(actions_ptr, fmt, first_call):
             """(no checks: ``actions_ptr`` addresses N * A (* 3) int32 in host memory)"""
             rc = call(h, actions_ptr, fmt, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6], ptrs[7], ptrs[8],
-                      n_over_p, 1 if first_call else 0, nthr, current_stream(device).cuda_stream)
+                      n_over_p, 1 if first_call else 0, nthr, stream_of())
             if rc:
                 check(rc)
             return overflow_host[:n_over.value] if n_over.value else None
