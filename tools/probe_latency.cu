@@ -70,6 +70,26 @@ int main() {
         printf("%-34s launch call %.1f us, flag seen after %.1f us\n", names[mode], sum_launch / R, sum / R);
         cudaDeviceSynchronize();
     }
+    {   // what does a 16 KB host-to-device copy in front of the kernel cost?  (zs_step_host sends the actions that way)
+        uint32_t *hsrc, *ddst;
+        cudaHostAlloc((void**)&hsrc, 16384, 0); cudaMalloc((void**)&ddst, 16384);
+        struct Acts { unsigned char a[4096]; } acts; memset(&acts, 1, sizeof(acts));
+        for (int mode = 0; mode < 2; ++mode) {
+            double sum = 0, sum_launch = 0;
+            for (int i = 1; i <= R + 20; ++i) {
+                idle(60);
+                const double t0 = now();
+                const uint32_t t = 70000 + mode * 1000 + i;
+                if (mode == 1) cudaMemcpyAsync(ddst, hsrc, 16384, cudaMemcpyHostToDevice, 0);
+                k_spin<<<2048, 64>>>(flag, t, 19000);
+                const double t1 = now();
+                while (*flag != t) { }
+                if (i > 20) { sum += now() - t0; sum_launch += t1 - t0; }
+            }
+            printf("%-34s launch calls %.1f us, flag seen after %.1f us\n", mode ? "16 KB H2D copy + 10 us kernel" : "10 us kernel alone", sum_launch / R, sum / R);
+            cudaDeviceSynchronize();
+        }
+    }
     {   // records: host memory in pieces / coalesced, device memory + a copy of the whole buffer
         uint32_t *hrec, *drec, *hcopy;
         const size_t bytes = 4096 * 96 * 4;
