@@ -586,7 +586,7 @@ struct ZsHandle {
         int prod_off, prod_cap, prod_smem_bytes;  // the producer-warp variant of the standard rollout shape (0 bytes = not available)
     } shape[2];
     int short_steps;       // launches of fewer steps than this take shape[1]
-    int use_pdl;           // launch with programmatic stream serialization (launch_sim)
+    int use_pdl;           // launch with programmatic stream serialization (launch_sim): 0 never, 1 always, 2 short step launches
     int compact_words;     // words per compact observation record, 0 = this configuration has no compact form
     int32_t* host_actions_dev = nullptr;  // zs_step_host: this step's actions on the device
     uint32_t host_ticket = 0;  // zs_step_host: the value that marks the current step's records as arrived
@@ -719,7 +719,10 @@ static void launch_sim(const ZsHandle* h, const ZsIO& io, cudaStream_t st) {
     cudaLaunchAttribute la[1];
     la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     la[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = la; lc.numAttrs = h->use_pdl ? 1 : 0;
+    // (measured, profiles/r02_pdl.txt: back-to-back single steps 16.4 -> 14.5 us per launch, nothing lost on an idle stream; fused
+    // rollouts lose 1-1.5 % — the early CTAs of the next launch sit on the SMs — so only short step launches ask for it)
+    const bool pdl = h->use_pdl == 1 || (h->use_pdl == 2 && MODE == MODE_STEP && io.n_steps < h->short_steps);
+    lc.attrs = la; lc.numAttrs = pdl ? 1 : 0;
 #define ZS_LAUNCH(MPC_, G_, SH_, O_) cudaLaunchKernelEx(&lc, zs_sim_kernel<MODE, MPC_, G_, ((SH_) == 1 && MODE != MODE_STEP) ? 0 : (SH_), MODE == MODE_STEP ? (O_) : ZS_MIN_CTAS>, pp, io)
 #define ZS_LAUNCH_F(MPC_, G_, O_) do { if (fast) ZS_LAUNCH(MPC_, G_, 1, O_); else if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
 #define ZS_LAUNCH_G(MPC_, G_, O_) do { if (surr) ZS_LAUNCH(MPC_, G_, 2, O_); else ZS_LAUNCH(MPC_, G_, 0, O_); } while (0)
@@ -1012,7 +1015,8 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
         if ((v == 16 && p.mpc == 16 && p.N % 2 == 0) || v == 32) lanes0 = lanes1 = v;
     }
     h->short_steps = 8;
-    h->use_pdl = getenv("ZS_PDL") ? 1 : 0;  // (measured: -8 % on back-to-back single steps, but a launch on an idle stream starts later)
+    h->use_pdl = 2;  // programmatic dependent launch: 2 = short step launches only (launch_sim), ZS_PDL=1 every launch, ZS_PDL=0 none
+    if (const char* force = getenv("ZS_PDL")) h->use_pdl = atoi(force) ? 1 : 0;
     if (const char* force = getenv("ZS_SHORT_STEPS")) h->short_steps = atoi(force);
     h->tmpl_single_step = getenv("ZS_NO_TMA_SINGLE") ? 0 : 1;
     h->compact_words = (p.mpc <= 32 && p.obs_scope == ZS_OBS_WORLD && !p.obs_per_agent)

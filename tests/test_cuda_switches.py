@@ -35,6 +35,7 @@ CASES = [
     ("ZS_ONE_SHAPE", "1", "c1_bridge_ext", 4000, 48),
     ("ZS_SHORT_STEPS", "1000", "c1_bridge_ext", 4000, 48),
     ("ZS_PDL", "1", "c1_bridge_ext", 2048, 48),
+    ("ZS_PDL", "0", "c1_bridge_ext", 2048, 5),
     ("ZS_TMA_PAIR", "1", "c1_bridge_ext", 4000, 48),
     # observations written by a producer warp per CTA instead of by the game warps themselves (an experiment kept correct)
     ("ZS_PRODUCER", "1", "c1_bridge_ext", 4000, 48),
