@@ -219,6 +219,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
     size_t sn = env;  // step * N + env
 #pragma unroll 1
     for (int step = 0; step < io.n_steps; ++step, sn += p.N) {
+        TR_STEP_BEGIN();
         int32_t* const obs_out = obs_cur;
         if (FAST || obs_out) {
             { const bool wrap = ++oslot >= io.obs_slots; oslot = wrap ? 0 : oslot; obs_cur = wrap ? obs_first : obs_cur + obs_stride; }
@@ -362,6 +363,7 @@ __device__ __forceinline__ void step_loop_one(const ZsParams& p, const ZsIO& io,
         gsync<G, CV>(e);
         PH(11);
         if (step < 16) TR(4 + step);
+        TR_STEP_END(step);
     }
 #ifdef ZS_PHASE_CLOCKS
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -970,8 +972,6 @@ extern "C" __attribute__((visibility("default"))) int zs_create(const ZsConfig* 
     if (getenv("ZS_NO_FAST_INIT")) p.fast_init = 0;
     if (p.fast_init) {
         cand = p.n_ps + p.n_zs;  // both index lists side by side
-        for (int i = 0; i < p.n_ps; ++i) p.spawn_cells[i] = ps[i];
-        for (int i = 0; i < p.n_zs; ++i) p.spawn_cells[p.n_ps + i] = zs[i];
     }
     p.cand_cap = cand;
     // the candidate list is only touched while things are being placed: long ones (a map without spawn cells offers every

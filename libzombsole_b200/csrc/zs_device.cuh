@@ -68,8 +68,6 @@ struct ZsParams {
     uint8_t agent_weapons[ZS_MAX_AGENTS];
     uint8_t bot_kinds[ZS_MAX_BOTS];
     int32_t agent_obs_ids[ZS_MAX_AGENTS];
-    uint16_t spawn_cells[256];     // fast_init: the player spawn cells, then the zombie spawn cells (n_ps + n_zs <= 256), in
-                                   // the kernel parameters so that a world init reads them through the constant cache
     // ---- map tables (device, read-only)
     const int16_t* cell_static;    // [cells] static index or -1
     const uint16_t* static_cell;   // [Sp] cell of static i
@@ -370,7 +368,7 @@ __device__ unsigned long long zs_ph[24];  // 0-19: the step loop; 20-23: staging
 // prologue, after each of the first 24 steps and at exit (tools/trace_launch.sh): where a launch's fixed cost goes.
 #ifdef ZS_TRACE
 #define ZS_TRACE_WARPS 8192
-#define ZS_TRACE_SLOTS 32
+#define ZS_TRACE_SLOTS 40
 __device__ unsigned long long zs_trace_buf[ZS_TRACE_WARPS * ZS_TRACE_SLOTS];
 __device__ __forceinline__ unsigned long long zs_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned zs_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
@@ -384,11 +382,36 @@ __device__ __forceinline__ unsigned zs_smid() { unsigned r; asm volatile("mov.u3
 #define TRF(bit)                                                                                      \
     do {                                                                                              \
         const int _w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);                           \
-        if ((threadIdx.x & 31) == 0 && _w < ZS_TRACE_WARPS) zs_trace_buf[_w * ZS_TRACE_SLOTS + 28] |= (1ull << (bit)); \
+        if ((threadIdx.x & 31) == 0 && _w < ZS_TRACE_WARPS) {                                         \
+            zs_trace_buf[_w * ZS_TRACE_SLOTS + 28] |= (1ull << (bit));                                \
+            zs_trace_buf[_w * ZS_TRACE_SLOTS + 34] |= (1ull << (bit));                                \
+        }                                                                                             \
+    } while (0)
+// the warp's slowest step of the launch: its duration (slot 32), the paths it took (slot 33) and its index (slot 35); slot 34
+// collects the paths of the step in progress.  TR_STEP_BEGIN / TR_STEP_END bracket a step of the step loops.
+#define TR_STEP_BEGIN()                                                                               \
+    unsigned long long _tr_t0 = 0;                                                                    \
+    do {                                                                                              \
+        const int _w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);                           \
+        if ((threadIdx.x & 31) == 0 && _w < ZS_TRACE_WARPS) { zs_trace_buf[_w * ZS_TRACE_SLOTS + 34] = 0; _tr_t0 = zs_globaltimer(); } \
+    } while (0)
+#define TR_STEP_END(step)                                                                             \
+    do {                                                                                              \
+        const int _w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);                           \
+        if ((threadIdx.x & 31) == 0 && _w < ZS_TRACE_WARPS) {                                         \
+            const unsigned long long _d = zs_globaltimer() - _tr_t0;                                  \
+            if (_d > zs_trace_buf[_w * ZS_TRACE_SLOTS + 32]) {                                        \
+                zs_trace_buf[_w * ZS_TRACE_SLOTS + 32] = _d;                                          \
+                zs_trace_buf[_w * ZS_TRACE_SLOTS + 33] = zs_trace_buf[_w * ZS_TRACE_SLOTS + 34];      \
+                zs_trace_buf[_w * ZS_TRACE_SLOTS + 35] = (unsigned long long)(step);                  \
+            }                                                                                         \
+        }                                                                                             \
     } while (0)
 #else
 #define TR(i) do { } while (0)
 #define TRF(bit) do { } while (0)
+#define TR_STEP_BEGIN() do { } while (0)
+#define TR_STEP_END(step) do { } while (0)
 #endif
 
 // ---------------------------------------------------------------- lane-group primitives

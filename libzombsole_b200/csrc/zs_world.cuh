@@ -1843,10 +1843,21 @@ ZS_TPL __device__ __forceinline__ int initialize_world_fast(const ZsParams& p, E
     const int life = s < NP ? 100 : 50 + below(word_of(o2, kl & 3), 51);
     int q = placed ? j : -1;
     const int tmax = max(max(P, A), Z0);
+    if constexpr (MPC <= 16) {
+        // (unrolled: the shuffles do not depend on one another and go out back to back; only the compare-select chain is serial)
+#pragma unroll
+        for (int t = MPC - 1; t >= 0; --t) {
+            if (t < tmax) {
+                const int jt = gbcast<G, CV>(e, j, (base + t) & (G - 1));
+                if (t < it && jt == q) q = n - 1 - t;
+            }
+        }
+    } else {
 #pragma unroll 1
-    for (int t = tmax - 1; t >= 0; --t) {
-        const int jt = gbcast<G, CV>(e, j, base + t);
-        if (t < it && jt == q) q = n - 1 - t;
+        for (int t = tmax - 1; t >= 0; --t) {
+            const int jt = gbcast<G, CV>(e, j, base + t);
+            if (t < it && jt == q) q = n - 1 - t;
+        }
     }
     if (P > 0) {  // (an agent's q counts the player spawn cells the bots left)
         int x = q;
@@ -1859,7 +1870,9 @@ ZS_TPL __device__ __forceinline__ int initialize_world_fast(const ZsParams& p, E
         }
         if (is_agent) q = x;
     }
-    const int c = placed ? (int)p.spawn_cells[s < NP ? q : n1 + q] : 0;  // (kernel parameters: constant cache, no trip to memory)
+    // (one gather from the map's spawn lists, L1-resident; the copy in the kernel parameters costs a constant-cache access per
+    // distinct index: a dozen in a row here)
+    const int c = placed ? (int)__ldg((s < NP ? p.ps_cells : p.zs_cells) + q) : 0;
     const int flags_in = e.flags;
     TR(21);
     // The grid of a new world is the pristine template: every box/wall is back, nothing else is on it.  It is reached from

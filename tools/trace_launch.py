@@ -9,7 +9,7 @@ import parity_util as pu
 from libzombsole_b200 import abi, _native
 from libzombsole_b200.engine import ZsEngine
 
-W, S = 8192, 32
+W, S = 8192, 40
 
 
 def grab(L, clear=True):
@@ -65,6 +65,13 @@ def main():
             print("  LAST step: reward/rules/out", q(t[:, 26] - t[:, 25]))
             print("  LAST step: world init      ", q(t[:, 27] - t[:, 26]), " (%d warps > 1 us)" % int(((t[:, 27] - t[:, 26]) > 1000).sum()))
             print("  LAST step: obs patches     ", q(t[:, 4 + K - 1] - t[:, 27]))
+        if K <= 16:  # what a world init costs the step it happens in, phase by phase
+            ini = (t[:, 27] - t[:, 26]) > 1000
+            if ini.any() and (~ini).any():
+                ph = [("template issue", t[:, 24] - last0), ("world_step", t[:, 25] - t[:, 24]), ("reward/rules/out", t[:, 26] - t[:, 25]),
+                      ("world init", t[:, 27] - t[:, 26]), ("obs patches", t[:, 4 + K - 1] - t[:, 27]), ("whole step", t[:, 4 + K - 1] - last0)]
+                print("  LAST step, warps with a world init (%d) against the others, mean us: " % int(ini.sum()) +
+                      ", ".join("%s %.2f / %.2f" % (nm, v[ini].mean() / 1e3, v[~ini].mean() / 1e3) for nm, v in ph))
         did = t[:, 23] > t[:, 20]
         did &= t[:, 20] > t0
         if did.any():
@@ -92,6 +99,23 @@ def main():
                 if took.any():
                     print("    path %-20s taken by %4d warps: world_step mean %.2f us (others %.2f); %d of the slow warps" % (
                         nm, int(took.sum()), ws[took].mean() / 1e3, ws[~took].mean() / 1e3 if (~took).any() else 0, int((took & slow).sum())))
+        # every warp's slowest step of the launch, and which of the less common paths it took in that step
+        names = ["wander", "idle", "hits", "static hit", "sequential execute", "deaths", "re-rank", "fresh world", "world init"]
+        dmax, fmax = t[:, 32], t[:, 33]
+        print("  slowest step of a warp       ", q(dmax))
+        slowest = dmax > np.percentile(dmax, 90)
+        for b, nm in enumerate(names):
+            took = (fmax >> b) & 1 == 1
+            if took.any():
+                print("    its path %-20s in %4d warps: that step mean %6.2f us (others %6.2f); %3d of the %d warps with the slowest tenth" % (
+                    nm, int(took.sum()), dmax[took].mean() / 1e3, dmax[~took].mean() / 1e3 if (~took).any() else 0,
+                    int((took & slowest).sum()), int(slowest.sum())))
+        combo = {}
+        for f, d in zip(fmax[slowest].tolist(), dmax[slowest].tolist()):
+            key = "+".join(nm for b, nm in enumerate(names) if (f >> b) & 1 and nm not in ("hits", "re-rank", "deaths")) or "-"
+            combo.setdefault(key, []).append(d)
+        for key, v in sorted(combo.items(), key=lambda kv: -len(kv[1]))[:8]:
+            print("    slowest tenth: %4d warps took {%s}: mean %.2f us" % (len(v), key, np.mean(v) / 1e3))
         # per SM: warps, span
         sm = t[:, 31]
         per = [(int(i), int((sm == i).sum()), (t[sm == i, 30].max() - t0) / 1e3) for i in sorted(set(sm.tolist()))]
