@@ -1843,8 +1843,10 @@ ZS_TPL __device__ __forceinline__ int initialize_world_fast(const ZsParams& p, E
     const int life = s < NP ? 100 : 50 + below(word_of(o2, kl & 3), 51);
     int q = placed ? j : -1;
     const int tmax = max(max(P, A), Z0);
-    if constexpr (MPC <= 16) {
-        // (unrolled: the shuffles do not depend on one another and go out back to back; only the compare-select chain is serial)
+    if constexpr (MPC <= 16 && CV) {
+        // (the step loop's converged call, which is latency-bound: unrolled, the shuffles do not depend on one another and go
+        // out back to back, only the compare-select chain is serial.  The reset kernel, which is throughput-bound and runs the
+        // member-mask flavour, is 8 % faster with the loop)
 #pragma unroll
         for (int t = MPC - 1; t >= 0; --t) {
             if (t < tmax) {
