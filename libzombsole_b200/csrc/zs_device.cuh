@@ -52,65 +52,69 @@
 #define ZS_NP_MAX (ZS_MAX_BOTS + ZS_MAX_AGENTS)
 
 struct ZsParams {
-    // ---- configuration
+    // (kernel parameters live in the constant bank: what the step loop reads every step comes first, packed, so that it
+    // takes few constant-cache lines; what only world inits, other scopes or other kernels read follows)
+    // ---- configuration, hot
     int32_t N;
     uint32_t env_base;        // low 32 bits of the global index of env 0
-    uint32_t key0, key1;      // Philox key = seed
-    uint32_t rkey0[10], rkey1[10];  // its round keys (key + r * Weyl constants), so the key schedule costs no instructions
     int32_t rules, P, A, Z, M, Mp, Ap, S, Sp, W, H, cells, cells_pad, dead_words;
     int32_t initial_zombies, minimum_zombies;
     int32_t obs_scope, obs_enc, sw, obs_count, obs_C;
     int32_t obs_per_agent, max_steps, auto_reset, n_discrete;
-    int32_t n_ps, n_zs;
     int32_t has_randoman;     // some bot is a randoman: decide-phase draws are resolved sequentially in dict order
     int32_t fast_init;        // world inits take initialize_world_lists (spawn cells for everybody, fixed weapons)
     int64_t obs_elems;
-    uint8_t agent_weapons[ZS_MAX_AGENTS];
-    uint8_t bot_kinds[ZS_MAX_BOTS];
-    int32_t agent_obs_ids[ZS_MAX_AGENTS];
-    // ---- map tables (device, read-only)
-    const int16_t* cell_static;    // [cells] static index or -1
-    const uint16_t* static_cell;   // [Sp] cell of static i
-    const int16_t* static_max;     // [Sp] MAX_LIFE of static i (0 in the padding)
-    const uint8_t* static_label;   // [Sp]
-    const uint8_t* tmpl_grid;      // [cells_pad] G_STATIC on box/wall cells, else 0
-    const int32_t* tmpl_obs;       // [2][cells] world-scope observation of the pristine static layer
-    const uint16_t* tmpl_pad;      // surroundings scope: the same planes with a border of fresh Walls sw/2 cells wide,
-    int32_t pad_w, pad_plane;      // [1 or 2][H + sw - 1][pad_w = W + sw - 1]; pad_plane = elements per plane
-    uint32_t sw_magic;             // ceil(2^32 / sw): i / sw == umulhi(i, sw_magic) for i < 65536
-    const int32_t* win_table;      // [cells][win_pitch] pristine window planes (label / label+life; win_ints words) of an
-    int32_t win_ints, win_pitch;   // agent standing on the cell, laid out like the output; rows start on 128-byte
-                                   // boundaries (L2-resident; NULL when it would be too large)
-    const uint32_t* objective_bits;// [dead_words]
-    const uint16_t* free_xm;       // [n_free0] the cells without a box/wall in x-major order: World.spawn_in_random's candidates
-    const uint16_t* free_index;    // [cells] position of a cell in free_xm (maps where some group has no spawn cells; else NULL)
-    int32_t n_free0;
-    const uint16_t* ps_cells;      // [n_ps] player spawn cells, file order
-    const uint16_t* zs_cells;      // [n_zs]
-    // ---- state (device, caller-owned buffer; see ZsLayout)
-    int16_t* X; int16_t* Y; int16_t* LIFE; int32_t* STAMP; uint8_t* META;
-    int16_t* PREV; int16_t* SLIFE; uint32_t* DEAD; int32_t* SCAL;
-    unsigned long long* stats;     // [4]
+    uint32_t rkey0[10], rkey1[10];  // Philox round keys (key + r * Weyl constants), so the key schedule costs no instructions
     // ---- shared memory: run-time sized tail behind EnvS<MPC> (byte offsets from the end of the struct)
     int32_t off_dead, off_sl, off_cand, off_spl, off_sidx;
-    int32_t cand_cap;
-    uint32_t* spl_global;          // static patch lists + SIDX bytes in device memory [N, spl_pitch words] for the kernels with
-    int32_t spl_pitch;             // more slots than lanes on maps with many boxes/walls (keeps CTAs resident); NULL = shared
-    uint16_t* cand_global;         // spawn candidate lists in device memory [N, cand_cap] when they are too long for shared
-                                   // memory (maps without spawn cells: every cell is a candidate); NULL = in shared memory
-    int32_t prefetch_ahead;        // load_state also prefetches the state of env + prefetch_ahead into the L2 (0 = off)
-    int32_t sl_global;             // same kernels, same maps: box/wall lives are used where they are, in the state buffer
-    unsigned char* img;            // the parked on-chip images [N, img_pitch bytes] (EnvS: "the IMAGE"), NULL = not kept
-    int32_t img_pitch, img_bytes;  // bytes between two envs' images / bytes of one (multiples of 16)
-    int32_t img_load;              // the images are current: a launch starts from them instead of load_state + build_grid
     int32_t smem_per_env;          // sizeof(EnvS<MPC>) + tail, multiple of 16
     int32_t tmpl_smem_off;         // CTA-shared copy of the pristine observation planes (TMA source), -1 if unused
     int32_t tmpl_planes;           // planes staged there: 1 (simple) or 3 (channels: label, life, zeros)
     int32_t tmpl_pair;             // the planes are staged twice back to back: one bulk copy serves both envs of a warp
     int32_t tmpl_bytes;            // bytes of one staged copy of the planes (tmpl_planes * cells * 4)
+    // ---- map tables (device, read-only), hot
+    const int16_t* cell_static;    // [cells] static index or -1
+    const uint16_t* static_cell;   // [Sp] cell of static i
+    const int16_t* static_max;     // [Sp] MAX_LIFE of static i (0 in the padding)
+    const int32_t* tmpl_obs;       // [2][cells] world-scope observation of the pristine static layer
+    unsigned long long* stats;     // [4]
+    uint8_t bot_kinds[ZS_MAX_BOTS];
+    uint8_t agent_weapons[ZS_MAX_AGENTS];
+    // ---- the parked images
+    unsigned char* img;            // the parked on-chip images [N, img_pitch bytes] (EnvS: "the IMAGE"), NULL = not kept
+    int32_t img_pitch, img_bytes;  // bytes between two envs' images / bytes of one (multiples of 16)
+    int32_t img_load;              // the images are current: a launch starts from them instead of load_state + build_grid
+    int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
+    // ---- state (device, caller-owned buffer; see ZsLayout)
+    int16_t* X; int16_t* Y; int16_t* LIFE; int32_t* STAMP; uint8_t* META;
+    int16_t* PREV; int16_t* SLIFE; uint32_t* DEAD; int32_t* SCAL;
+    // ---- world init, other scopes, other kernels
+    uint32_t key0, key1;      // Philox key = seed
+    int32_t n_ps, n_zs;
+    const uint16_t* ps_cells;      // [n_ps] player spawn cells, file order
+    const uint16_t* zs_cells;      // [n_zs]
+    const uint8_t* static_label;   // [Sp]
+    const uint8_t* tmpl_grid;      // [cells_pad] G_STATIC on box/wall cells, else 0
+    const uint16_t* tmpl_pad;      // surroundings scope: the same planes with a border of fresh Walls sw/2 cells wide,
+    int32_t pad_w, pad_plane;      // [1 or 2][H + sw - 1][pad_w = W + sw - 1]; pad_plane = elements per plane
+    uint32_t sw_magic;             // ceil(2^32 / sw): i / sw == umulhi(i, sw_magic) for i < 65536
+    int32_t win_ints, win_pitch;   // agent standing on the cell, laid out like the output; rows start on 128-byte
+                                   // boundaries (L2-resident; NULL when it would be too large)
+    const int32_t* win_table;      // [cells][win_pitch] pristine window planes (label / label+life; win_ints words) of an
+    const uint32_t* objective_bits;// [dead_words]
+    const uint16_t* free_xm;       // [n_free0] the cells without a box/wall in x-major order: World.spawn_in_random's candidates
+    const uint16_t* free_index;    // [cells] position of a cell in free_xm (maps where some group has no spawn cells; else NULL)
+    int32_t n_free0;
+    int32_t cand_cap;
+    uint32_t* spl_global;          // static patch lists + SIDX bytes in device memory [N, spl_pitch words] for the kernels with
+    int32_t spl_pitch;             // more slots than lanes on maps with many boxes/walls (keeps CTAs resident); NULL = shared
+    int32_t prefetch_ahead;        // load_state also prefetches the state of env + prefetch_ahead into the L2 (0 = off)
+    uint16_t* cand_global;         // spawn candidate lists in device memory [N, cand_cap] when they are too long for shared
+                                   // memory (maps without spawn cells: every cell is a candidate); NULL = in shared memory
+    int32_t sl_global;             // same kernels, same maps: box/wall lives are used where they are, in the state buffer
     int32_t prod_off;              // producer-warp launches: CTA-shared mailboxes (ObsMail + record) of the CTA's envs, -1 if unused
     int32_t prod_cap;              // entries one record holds
-    int32_t mpc;                   // slot capacity the kernels are instantiated for (16, 32, 128 or 256)
+    int32_t agent_obs_ids[ZS_MAX_AGENTS];
 };
 
 struct ZsIO {
