@@ -94,8 +94,10 @@ class ZombsoleVectorEnv(object):
         # records itself and the host threads, already waiting, expand them the moment a flag kernel behind it says they
         # are complete (zs_step_host); "compact-copy" is the same with explicit copies and a stream
         # synchronisation between the stages (zs_step_compact / zs_expand_compact, include/zs_b200.h)
-        if isinstance(host_outputs, str) and host_outputs not in ("compact", "compact-copy"):
-            raise ValueError("host_outputs must be False, True, 'compact' or 'compact-copy'")
+        if isinstance(host_outputs, str) and host_outputs not in ("compact", "compact-copy", "compact-if-available"):
+            raise ValueError("host_outputs must be False, True, 'compact', 'compact-copy' or 'compact-if-available'")
+        if host_outputs == "compact-if-available":  # (device outputs where the configuration has no compact record form)
+            host_outputs = "compact" if self.engine.compact_words() else False
         self.compact = host_outputs in ("compact", "compact-copy")
         self.streamed = host_outputs == "compact"
         self.host_outputs = bool(host_outputs)
@@ -320,27 +322,34 @@ class ZombsoleGymEnv(_GymEnv):
     def __init__(self, rules_name, player_names, map_name, agent_id, initial_zombies=0, minimum_zombies=0,
                  render_mode=None, observation_scope="world", observation_position_encoding="simple",
                  agent_weapon="rifle", debug=False, *, device="cuda", seed=0, env_index_base=0):
-        self.vec = ZombsoleVectorEnv(rules_name, player_names, map_name, agent_id, initial_zombies, minimum_zombies,
-                                     render_mode, observation_scope, observation_position_encoding, agent_weapon, debug,
-                                     num_envs=1, device=device, seed=seed, env_index_base=env_index_base,
-                                     max_episode_steps=None, auto_reset=False)
+        kw = dict(num_envs=1, device=device, seed=seed, env_index_base=env_index_base, max_episode_steps=None, auto_reset=False)
+        args = (rules_name, player_names, map_name, agent_id, initial_zombies, minimum_zombies, render_mode, observation_scope,
+                observation_position_encoding, agent_weapon, debug)
+        # one world answers a host caller: where the configuration has a compact record form the whole step is ONE library
+        # call that leaves observation, reward and flags in host memory (zs_step_host) instead of a launch and four copies
+        self.vec = ZombsoleVectorEnv(*args, host_outputs="compact-if-available", host_threads=1, **kw)
         self.render_mode = render_mode
         self.observation_space = self.vec.single_observation_space
         self.game = self.vec.game(0)
 
+    @staticmethod
+    def _fresh(row):
+        """The caller gets an array of its own, as from the reference (the env's buffers are overwritten by the next call)."""
+        return row.cpu().numpy() if row.is_cuda else row.numpy().copy()
+
     def get_observation(self):
-        return self.vec.get_observation()[0].cpu().numpy()
+        return self._fresh(self.vec.get_observation()[0])
 
     def get_frame_size(self):
         return self.vec.get_frame_size()
 
     def step(self, action):
         obs, reward, terminated, truncated, info = self.vec.step([action])
-        return (obs[0].cpu().numpy(), float(reward[0].item()), bool(terminated[0].item()), bool(truncated[0].item()), {})
+        return (self._fresh(obs[0]), float(reward[0].item()), bool(terminated[0].item()), bool(truncated[0].item()), {})
 
     def reset(self, seed=None, options=None):
         obs, _ = self.vec.reset()
-        return obs[0].cpu().numpy(), {}
+        return self._fresh(obs[0]), {}
 
     def render(self):
         raise ValueError("mode={} is not supported".format(self.render_mode))
