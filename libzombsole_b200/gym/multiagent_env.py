@@ -36,7 +36,7 @@ class MultiagentZombsoleVectorEnv(object):
     def __init__(self, rules_name, player_names, map_name, agent_ids, initial_zombies=0, minimum_zombies=0,
                  render_mode=None, observation_surroundings_width=21, observation_position_encoding_style="channels",
                  agent_weapons="rifle", debug=False, *, num_envs=1, device="cuda", seed=0, env_index_base=0,
-                 max_episode_steps=None, auto_reset=True):
+                 max_episode_steps=None, auto_reset=True, host_outputs=False):
         if render_mode is not None:
             if render_mode not in self.metadata["render.modes"]:
                 raise ValueError("render_mode={} is not supported".format(render_mode))
@@ -68,10 +68,20 @@ class MultiagentZombsoleVectorEnv(object):
         self.action_spaces = {aid: Discrete(len(self.game_actions)) for aid in self.possible_agents}
         self.observation_spaces = {aid: Box(low=0, high=128, shape=(3, width, width), dtype=np.int32)
                                    for aid in self.possible_agents}
-        self.obs = self.engine.new_obs()
-        self.reward, self._term, self._trunc = self.engine.new_outputs()
-        self._mask = torch.ones((num_envs, self.num_agents), dtype=torch.uint8, device=self.device)
-        self._actions = torch.zeros((num_envs, self.num_agents, 3), dtype=torch.int32, device=self.device)
+        # host_outputs: the kernel writes observations, rewards, flags and the agent mask straight into pinned host memory and
+        # reads the actions from there; step() synchronises the stream once and also leaves the agents' lives after the step
+        # in `agent_life_host` (what a host loop needs to know who is still playing, multiagent_env.py:169)
+        self.host_outputs = bool(host_outputs)
+        if self.host_outputs:
+            self.obs, self.reward, self._term, self._trunc = self.engine.new_host_outputs()
+            self._mask = torch.ones((num_envs, self.num_agents), dtype=torch.uint8).pin_memory()
+            self._actions = torch.zeros((num_envs, self.num_agents, 3), dtype=torch.int32).pin_memory()
+            self.agent_life_host = torch.zeros((num_envs, self.num_agents), dtype=torch.int16).pin_memory()
+        else:
+            self.obs = self.engine.new_obs()
+            self.reward, self._term, self._trunc = self.engine.new_outputs()
+            self._mask = torch.ones((num_envs, self.num_agents), dtype=torch.uint8, device=self.device)
+            self._actions = torch.zeros((num_envs, self.num_agents, 3), dtype=torch.int32, device=self.device)
         self._h2d_done, self._h2d_pending = None, False
 
     def game(self, env=0):
@@ -79,7 +89,10 @@ class MultiagentZombsoleVectorEnv(object):
         return Game(self.engine, env, rules_name, player_names, agent_ids, iz, mz)
 
     def get_observation(self):
-        return self.engine.encode_obs(self.obs)
+        self.engine.encode_obs(self.obs)
+        if self.host_outputs:
+            torch.cuda.current_stream(self.device).synchronize()
+        return self.obs
 
     def _stage_actions(self, actions):
         N, A = self.num_envs, self.num_agents
@@ -90,10 +103,12 @@ class MultiagentZombsoleVectorEnv(object):
                 for i, aid in enumerate(self.possible_agents):
                     rows[n, i] = encode_action(dict(d[aid], parameter=d[aid].get("parameter", [0, 0]))) \
                         if aid in d else (abi.ACT_ABSENT, 0, 0)
-            self._actions.copy_(torch.from_numpy(rows), non_blocking=True)
+            self._actions.copy_(torch.from_numpy(rows), non_blocking=not self.host_outputs)
             return self._actions, abi.ACTIONS_FULL
         t = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
-        if t.dtype != torch.int32 or t.device != self.device:
+        if self.host_outputs and t.dtype == torch.int32 and t.device.type == "cpu" and t.is_pinned():
+            pass  # the kernel reads a pinned host action tensor in place
+        elif t.dtype != torch.int32 or t.device != self.device:
             pinned_src = t.device.type == "cpu" and t.is_pinned()
             t = t.to(device=self.device, dtype=torch.int32, non_blocking=True)
             if pinned_src:  # the copy is in flight: step() waits for it before the caller may refill the buffer
@@ -111,6 +126,11 @@ class MultiagentZombsoleVectorEnv(object):
         """One transition of every world (multiagent_env.py:111-171); discrete id -1 = key missing."""
         a, fmt = self._stage_actions(actions)
         self.engine.step(a, fmt, self.obs, self.reward, self._term, self._trunc, self._mask)
+        if self.host_outputs:  # the host owns the results (and any pinned action buffer) when step() returns
+            P = self.cfg.n_bots
+            self.agent_life_host.copy_(self.engine.fields["life"][:, P:P + self.num_agents], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._h2d_pending = False
         if self._h2d_pending:  # a pinned host action buffer is the caller's again when step() returns
             self._h2d_done.synchronize()
             self._h2d_pending = False
@@ -119,6 +139,8 @@ class MultiagentZombsoleVectorEnv(object):
 
     def reset(self, seed=None, options=None, mask=None):
         self.engine.reset(mask, self.obs)
+        if self.host_outputs:
+            torch.cuda.current_stream(self.device).synchronize()
         return self.obs, {}
 
     def rollout(self, n_steps, actions=None, first_step_index=0, obs=None, reward=None, terminated=None, truncated=None):
@@ -153,7 +175,7 @@ class MultiagentZombsoleEnv(object):
             rules_name, player_names, map_name, agent_ids, initial_zombies, minimum_zombies, render_mode,
             observation_surroundings_width, observation_position_encoding_style, agent_weapons, debug,
             num_envs=1, device=device, seed=seed, env_index_base=env_index_base, max_episode_steps=None,
-            auto_reset=False)
+            auto_reset=False, host_outputs=True)
         self.position_encoding_style = observation_position_encoding_style
         self.surroundings_width = observation_surroundings_width
         self.agents = list(agent_ids)
@@ -166,19 +188,21 @@ class MultiagentZombsoleEnv(object):
         self.game = self.vec.game(0)
 
     def get_observation(self):
-        obs = self.vec.get_observation()[0].cpu().numpy()
+        obs = self.vec.get_observation()[0].numpy().copy()  # (host memory; the caller gets arrays of its own)
         return {aid: obs[i] for i, aid in enumerate(self.possible_agents) if aid in self.agents}
 
     def step(self, action):
+        # one launch whose outputs land in pinned host memory, one synchronisation (the vector env's host_outputs mode)
         obs, reward, term, trunc, info = self.vec.step([action])
-        obs, reward = obs[0].cpu().numpy(), reward[0].cpu().numpy()
-        doneflag, truncatedflag = bool(term[0].item()), bool(trunc[0].item())
+        obs, reward = obs[0].numpy().copy(), reward[0].numpy()
+        doneflag, truncatedflag = bool(term[0]), bool(trunc[0])
         before = self.agents
         observations = {aid: obs[i] for i, aid in enumerate(self.possible_agents) if aid in before}
         rewards = {aid: float(reward[i]) for i, aid in enumerate(self.possible_agents) if aid in before}
         done = {aid: doneflag for aid in before}
         truncated = {aid: truncatedflag for aid in before}
-        self.agents = [a.agent_id for a in self.game.agents if a.life > 0]  # multiagent_env.py:169
+        life = self.vec.agent_life_host[0].numpy()
+        self.agents = [aid for i, aid in enumerate(self.possible_agents) if life[i] > 0]  # multiagent_env.py:169
         return observations, rewards, done, truncated, {}
 
     def reset(self, seed=None, options=None):

@@ -254,6 +254,30 @@ def test_host_output_mode_matches_device_outputs():
     host_env.close()
 
 
+def test_multiagent_host_output_mode_matches_device_outputs():
+    """MultiagentZombsoleVectorEnv(host_outputs=True): observations, per-agent rewards, flags and the agent mask land in pinned
+    host memory, the agents' lives after the step in agent_life_host; same values as the device-output env."""
+    from libzombsole_b200.gym.multiagent_env import MultiagentZombsoleVectorEnv
+    kw = dict(rules_name="evacuation", player_names=["terminator"], map_name="village_for_evacuation", agent_ids=["0", "1", "2"],
+              initial_zombies=15, minimum_zombies=0, num_envs=96, seed=5, max_episode_steps=40)
+    dev_env, host_env = MultiagentZombsoleVectorEnv(**kw), MultiagentZombsoleVectorEnv(host_outputs=True, **kw)
+    o0, _ = dev_env.reset()
+    h0, _ = host_env.reset()
+    assert h0.device.type == "cpu" and h0.is_pinned() and torch.equal(o0.cpu(), h0)
+    g = torch.Generator().manual_seed(2)
+    P = dev_env.cfg.n_bots
+    for t in range(90):
+        a = torch.randint(-1, 7, (96, 3), generator=g, dtype=torch.int32)
+        o, r, te, tr, info = dev_env.step(a.cuda())
+        ho, hr, hte, htr, hinfo = host_env.step(a.pin_memory() if t % 2 else a)
+        assert torch.equal(o.cpu(), ho) and torch.equal(r.cpu().view(torch.int64), hr.view(torch.int64))
+        assert torch.equal(te.cpu(), hte) and torch.equal(tr.cpu(), htr)
+        assert torch.equal(info["agent_mask"].cpu(), hinfo["agent_mask"])
+        assert torch.equal(dev_env.engine.fields["life"][:, P:P + 3].cpu(), host_env.agent_life_host)
+    dev_env.close()
+    host_env.close()
+
+
 def test_tape_fill_equals_per_step_fill():
     """zs_fill_synthetic_tape (one launch) writes the same ids as zs_fill_synthetic_actions step by step."""
     eng, cfg, _ = engine("c3_city_evac", 300, seed=9, base=17)
