@@ -595,6 +595,8 @@ struct ZsHandle {
     volatile uint32_t* host_flag = nullptr;  // pinned, one cache line each: [0] zs_host_flag_kernel's, [1 + g] group g's (the step kernel's)
     int32_t* host_group_count = nullptr;     // device: envs of each group done in this step
     int host_groups = 0;
+    int host_diff = -1;                      // zs_step_host's expansion: -1 timed and chosen by the handle, 0 restore ahead + write, 1 difference of the records (ZS_HOST_DIFF)
+    struct HostTune { int mode = 0; bool exploring = true; int left = 16; double sum = 0; int n = 0; double mean[2] = {-1, -1}; } host_tune;
     const void* host_records_checked = nullptr;
     double host_stats[5] = {0, 0, 0, 0, 0};  // zs_step_host: calls, and summed us from entry to: launched / previous cells restored / flag seen / return
     std::vector<int32_t> tmpl_obs_host;  // the pristine observation planes [obs_C][cells] (zs_expand_compact)
@@ -1288,6 +1290,58 @@ static inline bool expand_write(const ExpandCtx& cx, int e, const uint32_t* r, u
     memcpy(pv, r, (size_t)(ZS_COMPACT_HEADER + n * wpe) * sizeof(uint32_t));
     return false;
 }
+// One env's expansion as a DIFFERENCE of its two records: only the cells whose entry changed are touched.  For a host that
+// is bound by memory traffic (several ranks' observation rows do not fit its caches, so every scattered store is a DRAM line
+// fill and write-back) this is a third of the lines of restore + write; where the rows are cache-resident the comparisons
+// cost what the stores save, and restoring ahead of the flag (expand_restore) is the better half.
+// Records of equal length are compared position by position, others up to their first difference (entries keep their list
+// order: boxes/walls, dead bodies, mobile things).  Untouched entries keep their cells because a record names a cell once —
+// except a cell with several dead bodies, whose equal entries come and go together, so that an untouched one always has a
+// twin among the rewritten ones (new dead bodies only append; the list empties only with the world).
+static inline bool expand_diff(const ExpandCtx& cx, int e, const uint32_t* r, uint32_t* pv) {
+    const uint32_t h0 = r[0];
+    if (cx.first_call || ((pv[0] >> 18) & 1u) || ((h0 >> 18) & 1u)) {  // no usable previous record / the row comes from the device
+        if (!((h0 >> 18) & 1u)) expand_restore(cx, e, pv);
+        return expand_write(cx, e, r, pv);
+    }
+    const int cells = cx.cells, C = cx.C, wpe = cx.wpe;
+    const int32_t* T = cx.T;
+    int32_t* o = cx.obs + (size_t)e * C * cells;
+    const int n = (int)(h0 & 0xffffu), pn = (int)(pv[0] & 0xffffu);
+    if (cx.terminated) cx.terminated[e] = (uint8_t)((h0 >> 16) & 1u);
+    if (cx.truncated) cx.truncated[e] = (uint8_t)((h0 >> 17) & 1u);
+    if (cx.reward) memcpy(cx.reward + e, r + 2, sizeof(double));
+    const uint32_t* re = r + ZS_COMPACT_HEADER;
+    uint32_t* pe = pv + ZS_COMPACT_HEADER;
+    auto same = [&](int i) { return wpe == 1 ? pe[i] == re[i] : (pe[2 * i] == re[2 * i] && pe[2 * i + 1] == re[2 * i + 1]); };
+    auto restore = [&](int i) {
+        const int cell = (int)(pe[i * wpe] & 0xffffu);
+        for (int c = 0; c < C; ++c) o[(size_t)c * cells + cell] = T[(size_t)c * cells + cell];
+    };
+    auto write = [&](int i) {
+        if (wpe == 1) { const uint32_t w = re[i]; o[w & 0xffffu] = (int32_t)(w >> 16); }
+        else {
+            const uint32_t w0 = re[2 * i], w1 = re[2 * i + 1];
+            const int cell = (int)(w0 & 0xffffu);
+            o[cell] = (int32_t)(w0 >> 16);
+            o[(size_t)cells + cell] = (int32_t)(int16_t)(w1 & 0xffffu);
+            o[2 * (size_t)cells + cell] = (int32_t)(w1 >> 16);
+        }
+    };
+    if (n == pn) {
+        for (int i = 0; i < n; ++i) if (!same(i)) restore(i);
+        for (int i = 0; i < n; ++i) if (!same(i)) { write(i); for (int w = 0; w < wpe; ++w) pe[i * wpe + w] = re[i * wpe + w]; }
+    } else {
+        const int m = n < pn ? n : pn;
+        int k = 0;
+        while (k < m && same(k)) ++k;
+        for (int i = k; i < pn; ++i) restore(i);
+        for (int i = k; i < n; ++i) write(i);
+        memcpy(pe + k * wpe, re + k * wpe, (size_t)(n - k) * wpe * sizeof(uint32_t));
+    }
+    pv[0] = h0; pv[1] = r[1]; pv[2] = r[2]; pv[3] = r[3];
+    return false;
+}
 static inline bool expand_one(const ExpandCtx& cx, int e, const uint32_t* r, uint32_t* pv) {
     if (!((r[0] >> 18) & 1u)) expand_restore(cx, e, pv);
     return expand_write(cx, e, r, pv);
@@ -1377,6 +1431,7 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
         h->host_groups = force ? atoi(force) : 1;
         if (h->host_groups > ZS_HOST_GROUPS_MAX) h->host_groups = ZS_HOST_GROUPS_MAX;
         if (h->host_groups > h->p.N) h->host_groups = h->p.N;
+        if (const char* v = getenv("ZS_HOST_DIFF")) h->host_diff = atoi(v) != 0;
     }
     CU(cudaMemcpyAsync(h->host_actions_dev, actions_host, act_bytes, cudaMemcpyHostToDevice, st));
     const int N = h->p.N, words = compact_words;
@@ -1399,6 +1454,23 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
     const ExpandCtx cx{h->tmpl_obs_host.data(), h->p.cells, h->p.obs_C, h->p.obs_enc == ZS_OBS_SIMPLE ? 1 : 2, words, first_call != 0,
                        obs_host, reward_host, terminated_host, truncated_host};
     int n_over = 0, gave_up = 0;
+    // restore ahead + write, or every env as the difference of its two records after the flag (expand_diff).
+    // Which of the two is faster depends on the host (its caches, how many ranks share it, the threads this rank got): the
+    // handle times both — sixteen calls of each, then the faster one for 512 calls, then the other one is sampled again.
+    // (Both leave the same rows and the same previous records, so the choice never shows in a result.)
+    bool diff = h->host_diff != 0;
+    if (h->host_diff < 0) {
+        ZsHandle::HostTune& t = h->host_tune;
+        if (t.left <= 0) {  // a phase is over: what its calls took on average is what is known about its mode
+            if (t.n) t.mean[t.mode] = t.sum / t.n;
+            if (t.exploring) {
+                if (t.mean[t.mode ^ 1] < 0) { t.mode ^= 1; t.left = 16; }       // (the very first round: now the other one)
+                else { t.mode = t.mean[1] < t.mean[0] ? 1 : 0; t.exploring = false; t.left = 512; }
+            } else { t.mode ^= 1; t.exploring = true; t.left = 16; }             // time to look at the other one again
+            t.sum = 0; t.n = 0;
+        }
+        diff = t.mode != 0;
+    }
     const volatile uint32_t* const flags = h->host_flag;
     const int n_flags = groups > 0 ? (N + group_envs - 1) / group_envs : 1;
 #pragma omp parallel num_threads(n_threads)
@@ -1409,6 +1481,7 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
         const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
         // while the device works on the step: what the previous records patched goes back to the pristine layer (half of an
         // expansion's stores need nothing from the new records)
+        if (!diff)
         for (int g = 0; g < n_flags; ++g) {
             const int g0 = g * group_envs, gn = (g0 + group_envs < N ? g0 + group_envs : N) - g0;
             const int e0 = g0 + (int)((long long)gn * tid / nt), e1 = g0 + (int)((long long)gn * (tid + 1) / nt);
@@ -1437,7 +1510,9 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
             const int g0 = g * group_envs, gn = (g0 + group_envs < N ? g0 + group_envs : N) - g0;
             const int e0 = g0 + (int)((long long)gn * tid / nt), e1 = g0 + (int)((long long)gn * (tid + 1) / nt);
             for (int e = e0; e < e1; ++e) {
-                if (expand_write(cx, e, compact_pinned + (size_t)e * words, prev_host + (size_t)e * words)) {
+                const uint32_t* const r = compact_pinned + (size_t)e * words;
+                uint32_t* const pv = prev_host + (size_t)e * words;
+                if (diff ? expand_diff(cx, e, r, pv) : expand_write(cx, e, r, pv)) {
                     int at;
 #pragma omp atomic capture
                     at = n_over++;
@@ -1453,6 +1528,11 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
     }
     // rows of overflowing envs: obs_dev is complete when the launch is (the caller reads them next)
     if (n_over > 0) CU(cudaStreamSynchronize(st));
+    if (h->host_diff < 0) {
+        ZsHandle::HostTune& t = h->host_tune;
+        if (!first_call && n_over == 0 && (!t.exploring || t.left <= 12)) { t.sum += us_since(); t.n += 1; }  // (a sample's first four calls settle the caches)
+        t.left -= 1;
+    }
     h->host_stats[0] += 1; h->host_stats[1] += us_launched; h->host_stats[2] += us_restored; h->host_stats[3] += us_flag; h->host_stats[4] += us_since();
     return 0;
 }

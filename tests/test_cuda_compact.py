@@ -17,12 +17,27 @@ KW = dict(rules_name="extermination", player_names=["terminator", "terminator"],
           initial_zombies=10, minimum_zombies=0, observation_scope="world", agent_weapon="rifle")
 
 
-MODES = ["compact", "compact-copy"]
+# zs_step_host expands an env either by restoring the previous record's cells ahead of the flag and writing the new ones
+# after it, or (":diff") as the difference of its two records; left alone (":auto") the handle times both and switches
+# between them — sixteen calls of one, sixteen of the other, then the faster — which must never show in a result
+MODES = ["compact", "compact-copy", "compact:diff", "compact:auto"]
+
+
+def _mode(monkeypatch, mode):
+    if mode.endswith(":diff"):
+        monkeypatch.setenv("ZS_HOST_DIFF", "1")
+        return mode[:-5]
+    if mode.endswith(":auto"):
+        monkeypatch.delenv("ZS_HOST_DIFF", raising=False)
+        return mode[:-5]
+    monkeypatch.setenv("ZS_HOST_DIFF", "0")
+    return mode
 
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("enc,N,threads", [("simple", 4096, 0), ("simple", 333, 3), ("channels", 1024, 0)])
-def test_compact_outputs_equal_device_outputs(enc, N, threads, mode):
+def test_compact_outputs_equal_device_outputs(monkeypatch, enc, N, threads, mode):
+    mode = _mode(monkeypatch, mode)
     plain = ZombsoleVectorEnv(num_envs=N, seed=9, max_episode_steps=30, observation_position_encoding=enc, **KW)
     comp = ZombsoleVectorEnv(num_envs=N, seed=9, max_episode_steps=30, observation_position_encoding=enc,
                              host_outputs=mode, host_threads=threads, **KW)
@@ -52,7 +67,8 @@ def test_compact_outputs_equal_device_outputs(enc, N, threads, mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_compact_overflow_fetches_the_full_row(mode):
+def test_compact_overflow_fetches_the_full_row(monkeypatch, mode):
+    mode = _mode(monkeypatch, mode)
     """More differing cells than a record holds (here: 150 damaged walls in some envs): those envs come over as full rows."""
     N = 64
     plain = ZombsoleVectorEnv(num_envs=N, seed=2, **KW)
@@ -76,7 +92,8 @@ def test_compact_overflow_fetches_the_full_row(mode):
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_compact_overflow_without_growth(mode):
+def test_compact_overflow_without_growth(monkeypatch, mode):
+    mode = _mode(monkeypatch, mode)
     """Records at the size nothing can grow beyond... here held small on purpose: a few envs overflow on every step and
     come over as full rows each time (few enough not to trigger the growth)."""
     N = 256
