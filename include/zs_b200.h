@@ -267,8 +267,10 @@ int zs_expand_compact(const ZsHandle* h, const uint32_t* compact_host, uint32_t*
  * host memory, as for zs_expand_compact) the moment it shows.  No device-to-host copy, no stream synchronisation and no
  * thread wake-up are on the way of a step; when the call returns every env has been expanded, the action buffer is the
  * caller's again, and obs_dev holds the rows of the envs listed in overflow_envs_host (as for zs_expand_compact; the
- * call synchronises the stream when there are any).  prev_host / first_call as for zs_expand_compact (one prev_host per record buffer).  Fails
- * after ten seconds if the flag does not show.  (Reference: the same transition as gym_env.py:99-145 returns to a caller
+ * call synchronises the stream when there are any).  prev_host / first_call as for zs_expand_compact (one prev_host per
+ * record buffer).  How the threads expand — previous cells restored ahead of the flag and the new ones written after it, or
+ * every env as the difference of its two records, which suits a host bound by memory traffic — is timed and chosen by
+ * the handle (ZS_HOST_DIFF=0/1 forces one); the results are the same.  Fails after ten seconds if the flag does not show.  (Reference: the same transition as gym_env.py:99-145 returns to a caller
  * on the host.) */
 int zs_step_host(ZsHandle* h, const int32_t* actions_host, int32_t action_format, uint32_t* compact_pinned,
                  uint32_t* prev_host, int32_t compact_words, int32_t* obs_dev, int32_t* obs_host, double* reward_host,
