@@ -9,6 +9,7 @@
 #include <time.h>
 
 #include <omp.h>
+#include <algorithm>
 #include <vector>
 
 #include "zs_device.cuh"
@@ -596,7 +597,7 @@ struct ZsHandle {
     int32_t* host_group_count = nullptr;     // device: envs of each group done in this step
     int host_groups = 0;
     int host_diff = -1;                      // zs_step_host's expansion: -1 timed and chosen by the handle, 0 restore ahead + write, 1 difference of the records (ZS_HOST_DIFF)
-    struct HostTune { int mode = 0; bool exploring = true; int left = 16; double sum = 0; int n = 0; double mean[2] = {-1, -1}; } host_tune;
+    struct HostTune { int mode = 0; bool exploring = true; int left = 32; int n[2] = {0, 0}; double last[2][16]; } host_tune;
     const void* host_records_checked = nullptr;
     double host_stats[5] = {0, 0, 0, 0, 0};  // zs_step_host: calls, and summed us from entry to: launched / previous cells restored / flag seen / return
     std::vector<int32_t> tmpl_obs_host;  // the pristine observation planes [obs_C][cells] (zs_expand_compact)
@@ -1456,19 +1457,27 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
     int n_over = 0, gave_up = 0;
     // restore ahead + write, or every env as the difference of its two records after the flag (expand_diff).
     // Which of the two is faster depends on the host (its caches, how many ranks share it, the threads this rank got): the
-    // handle times both — sixteen calls of each, then the faster one for 512 calls, then the other one is sampled again.
+    // handle times both — 32 calls alternating between them, then the faster one for 512 calls, then the next sample.
     // (Both leave the same rows and the same previous records, so the choice never shows in a result.)
     bool diff = h->host_diff != 0;
     if (h->host_diff < 0) {
+        // a sample is 32 calls that ALTERNATE between the two (the records grow over the first steps of a batch: sixteen calls of
+        // one and then sixteen of the other would compare different work); the medians decide (one hiccup of the host must not
+        // decide 512 calls)
         ZsHandle::HostTune& t = h->host_tune;
-        if (t.left <= 0) {  // a phase is over: what its calls took on average is what is known about its mode
-            if (t.n) t.mean[t.mode] = t.sum / t.n;
+        if (t.left <= 0) {
             if (t.exploring) {
-                if (t.mean[t.mode ^ 1] < 0) { t.mode ^= 1; t.left = 16; }       // (the very first round: now the other one)
-                else { t.mode = t.mean[1] < t.mean[0] ? 1 : 0; t.exploring = false; t.left = 512; }
-            } else { t.mode ^= 1; t.exploring = true; t.left = 16; }             // time to look at the other one again
-            t.sum = 0; t.n = 0;
+                double med[2];
+                for (int m = 0; m < 2; ++m) {
+                    const int n = t.n[m] < 16 ? t.n[m] : 16;
+                    std::sort(t.last[m], t.last[m] + n);
+                    med[m] = n ? t.last[m][n / 2] : 1e30;
+                }
+                t.mode = med[1] < med[0] ? 1 : 0; t.exploring = false; t.left = 512;
+            } else { t.exploring = true; t.left = 32; }
+            t.n[0] = t.n[1] = 0;
         }
+        if (t.exploring) t.mode = t.left & 1;
         diff = t.mode != 0;
     }
     const volatile uint32_t* const flags = h->host_flag;
@@ -1530,7 +1539,7 @@ extern "C" __attribute__((visibility("default"))) int zs_step_host(ZsHandle* h, 
     if (n_over > 0) CU(cudaStreamSynchronize(st));
     if (h->host_diff < 0) {
         ZsHandle::HostTune& t = h->host_tune;
-        if (!first_call && n_over == 0 && (!t.exploring || t.left <= 12)) { t.sum += us_since(); t.n += 1; }  // (a sample's first four calls settle the caches)
+        if (t.exploring && !first_call && n_over == 0 && t.left <= 28) { t.last[t.mode][t.n[t.mode] & 15] = us_since(); t.n[t.mode] += 1; }  // (the first four settle the caches)
         t.left -= 1;
     }
     h->host_stats[0] += 1; h->host_stats[1] += us_launched; h->host_stats[2] += us_restored; h->host_stats[3] += us_flag; h->host_stats[4] += us_since();
