@@ -1,3 +1,5 @@
+#!/bin/bash
+# usage (GPU box): tools/sweep_final.sh  -> K=1 / 20 / 512 launch times of configs[1] under the tuning switches, final build
 cd "$(dirname "$0")/.."
 export PROBE_KS=1,20,512
 run() { echo "== $*"; env "$@" python tools/probe_launch_cost.py c1_bridge_ext 4096 2>&1 | grep -E "^K=|zs_step"; }
